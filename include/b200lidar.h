@@ -1,0 +1,155 @@
+/*
+ * b200lidar.h -- C-ABI of libb200lidar.so: the sm_100a kernels behind the LiDARCrafter denoiser hot path.
+ *
+ * Conventions: plain pointers + sizes, no torch types; every pointer is a
+ * DEVICE pointer owned by the caller; no allocation inside the library; every call is asynchronous on
+ * `stream` (a cudaStream_t passed as void*) and CUDA-graph capturable; return value 0 = ok, negative =
+ * B200_E_* (never exit()).  Activations are NHWC ("pixels x channels") fp32 unless noted; the sampler
+ * state x_t / eps prediction stay in the reference's NCHW [B,2,H,W] layout.
+ *
+ * Each entry point names the reference code it replaces (paths relative to /root/reference/lidargen).
+ */
+#ifndef B200LIDAR_H_
+#define B200LIDAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_E_ARG (-1)     /* invalid argument / unsupported shape */
+#define B200_E_CUDA (-2)    /* CUDA runtime error at launch */
+#define B200_E_ARCH (-3)    /* device is not sm_100 */
+
+/* library / device info ------------------------------------------------------------------------- */
+int b200_version(void);
+/* returns SM count (>0) if device `dev` is compute capability 10.x, else B200_E_ARCH */
+int b200_device_check(int dev);
+const char* b200_last_error(void);
+
+/* ---- K1: ring conv as implicit GEMM on tcgen05 tensor cores ------------------------------------
+ * replaces: F.pad(circular W / zero H) + nn.Conv2d  (models/unets/ops.py:32-49,149-173) together with
+ *           the bias add, the residual add and the 1/sqrt(2) scale of ResidualBlock.forward
+ *           (models/unets/efficient_unet.py:112-115), and the GroupNorm statistics of the NEXT norm.
+ *   a        : fp16 [parts][B,H,W,Cin] conv operand (already normalised/activated, see b200_gn_act_f16);
+ *              parts = 1: plain fp16;  parts = 2: a = a[0] (hi) + a[1] (lo), the error-compensated split
+ *              (3 tensor-core MMAs per product, ~fp32 accuracy -- the mode that meets the 1e-3 tolerance)
+ *   wpacked  : fp16 image from b200_pack_conv_weight (same bn, same parts), pre-scaled by wscale = 1/w_inv
+ *   out      : fp32 [B,H,W,Cout] = (conv(a)*w_inv + bias + res) * out_scale   (res may be NULL / == out)
+ *   stats    : fp64 [B,Cout,2] += {sum, sum of squares} of `out` over H*W  (may be NULL)
+ *   taps     : 9 (3x3, padding 1) or 1 (1x1);  ring: 1 = circular in W, 0 = zero pad
+ *   bn       : output-channel tile (64 or 128, Cout % bn == 0);  rows: image rows per CTA (1,2,4; H % rows == 0)
+ * constraints: W % 128 == 0, Cin % 32 == 0.                                                       */
+int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
+                 float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
+                 int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
+/* number of fp16 elements of the packed weight image (== parts*taps*Cout*Cin) */
+size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
+/* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
+ * packed fp16 tiles [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8], KC = 32 (parts 1) or 16 (parts 2) */
+int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int parts,
+                          float wscale, void* stream);
+/* plain fp16 copy w16[parts][tap][Cout][Cin] for the CUDA-core checking kernel */
+int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, int Cin, int taps, int parts,
+                                float wscale, void* stream);
+/* CUDA-core (FFMA) implementation of exactly the same contract as b200_conv_tc, weights from
+ * b200_pack_conv_weight_plain.  Debug / cross-check path (tests), any W, Cin % 8 == 0.            */
+int b200_conv_ffma(const void* a, const void* w16, const float* bias, const float* res, float out_scale,
+                   float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
+                   int ring, int parts, void* stream);
+
+/* ---- GroupNorm apply (+AdaGN) + SiLU + fp16 cast (+ channel concat) ------------------------------
+ * replaces: nn.GroupNorm -> SiLU  (efficient_unet.py:77-79,106-110), AdaGN (ops.py:176-200),
+ *           torch.cat of skip features (efficient_unet.py:295-297).
+ *   y[b,p,c] = act( ((x[b,p,c]-mean)*rstd*gamma[c]+beta[c]) * (1+scale[b,c]) + shift[b,c] )  as fp16
+ *   x0/x1    : fp32 [B,HW,C0] / [B,HW,C1] sources concatenated along C (x1 may be NULL, C1 = 0)
+ *   stats0/1 : fp64 [B,C,2] per-channel {sum,sumsq} of the sources; NULL => no normalisation (cast only)
+ *   gamma/beta: [C0+C1] or NULL;  ada: fp32, scale at ada[b*ada_stride + c], shift at
+ *               ada[b*ada_stride + (C0+C1) + c], NULL => none;  silu: 1 = apply x*sigmoid(x)
+ *   y        : fp16 [parts][B,HW,C0+C1]; parts = 2 also writes the residual lo = fp16(v - fp32(hi))      */
+int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
+                    const double* stats1, const float* gamma, const float* beta, const float* ada,
+                    int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int HW,
+                    void* stream);
+/* per-(b,c) {sum,sumsq} of an fp32 NHWC tensor, accumulated (+=) into stats fp64 [B,C,2] */
+int b200_channel_stats(const float* x, double* stats, int B, int HW, int C, void* stream);
+
+/* ---- K3: FIR resampling ------------------------------------------------------------------------
+ * replaces: ops.Resample (ops.py:52-146), window [1,3,3,1], circular in W / zero in H.
+ *   up=0: [B,H,W,C] -> [B,H/2,W/2,C];  up=1: [B,H,W,C] -> [B,2H,2W,C];  stats (optional) as above     */
+int b200_fir_resample(const float* x, float* y, double* stats, int B, int H, int W, int C, int up,
+                      int ring, void* stream);
+
+/* ---- K4: time embedding + all per-block (scale,shift) projections --------------------------------
+ * replaces: SinusoidalPositionalEmbedding + 2 Linear (efficient_unet.py:237-242, ops.py:14-26) and the
+ *           24 AdaGN proj Linear layers (ops.py:190-200), one launch per denoiser step.
+ *   t [B] (log-SNR) -> temb [B,E] = W2 silu(W1 sincos(t) + b1) + b2 (+ temb_add[B,E] if not NULL)
+ *   ada [B,P] = Wp silu(temb) + bp   where Wp [P,E] stacks every block's projection                  */
+int b200_time_embed(const float* t, const float* w1, const float* b1, const float* w2, const float* b2,
+                    const float* temb_add, const float* wp, const float* bp, float* temb, float* ada,
+                    int B, int Cs, int E, int P, void* stream);
+
+/* ---- first / last convs on CUDA cores ------------------------------------------------------------
+ * in_conv: out[b,h,w,:] = cst[(b),h,w,:] + ring_conv3x3(x[b,0:Cx]) ; x NCHW fp32 [B,Cx,H,W] (Cx <= 4),
+ *          w fp32 [Cout,Cx,3,3], cst fp32 [Bc,H,W,Cout] (Bc = 1 broadcast or B) already holds bias +
+ *          the conv of the step-invariant channels (Fourier features / layout condition).
+ *          replaces in_conv + FourierFeatures + cat (efficient_unet.py:283-289, encoding.py:141-146)  */
+int b200_in_conv(const float* x, const float* w, const float* cst, int cst_batched, float* out,
+                 double* stats, int B, int H, int W, int Cx, int Cout, int ring, void* stream);
+/* generic small fp32 direct conv (one-time constant folding): x NHWC fp32 [B,H,W,Cin], w OIHW fp32     */
+int b200_conv_direct_f32(const float* x, const float* w, const float* bias, float* out, int B, int H,
+                         int W, int Cin, int Cout, int k, int ring, void* stream);
+/* out_conv: pred NCHW fp32 [B,Cout<=4,H,W] = ring_conv3x3(a) + bias ; a fp32 NHWC (a_is_f16=0) or fp16 */
+int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias, float* pred, int B,
+                  int H, int W, int Cin, int Cout, int ring, void* stream);
+
+/* ---- K2: attention ---------------------------------------------------------------------------------
+ * softmax(q k^T * scale) v per (batch, head); q/k/v are slices of fp32 token-major tensors
+ *   q: [B,Tq,ldq] at column offset head*dqk (+qoff), k: [B,Tk,ldk], v: [B,Tk,ldv]; out fp16 [parts][B,Tq,ldo]
+ * replaces: nn.MultiheadAttention core (efficient_unet.py:39-53) / QKVAttentionLegacy einsum-softmax-einsum
+ *           (layout_unet_v1.py:488-505)                                                              */
+int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
+                   int ldv, int voff, void* out, int ldo, int parts, int B, int heads, int Tq, int Tk,
+                   int dqk, int dv, float scale, void* stream);
+
+/* ---- K5: sampler update --------------------------------------------------------------------------
+ * replaces p_step's ~25 elementwise ops (diffusion/continuous_time.py:205-231).
+ *   coef fp32 [B,8]: {alpha_t, sigma_t, alpha_s, sigma_s, c1, c2, ddpm_c, 0}; mode 0 = ddim, 1 = ddpm;
+ *   objective 0 = eps, 1 = v, 2 = x_0; clip <= 0 disables clamping; noise may be NULL when c1 == 0.  */
+int b200_sampler_update(const float* x_t, const float* pred, const float* noise, const float* coef,
+                        float* x_s, int B, int n_per_sample, int mode, int objective, float clip,
+                        void* stream);
+
+/* ---- K6: point cloud -> range image ----------------------------------------------------------------
+ * replaces load_points_as_images (dataset/transforms_3d/common.py:26-91, scan_unfolding=False).
+ *   points fp32 [F,M,4] (x,y,z,intensity), npts int32 [F] valid points per frame
+ *   out    fp32 [F,H,W,6] (x,y,z,i,depth,mask), nearest point per pixel wins (ties: highest index)
+ *   grid   int32 [F,M,2] (grid_h, grid_w) for parity checks (may be NULL)
+ *   zbuf   uint64 scratch [F,H,W]                                                                    */
+int b200_range_project(const float* points, const int* npts, float* out, int* grid, void* zbuf, int F,
+                       int M, int H, int W, float min_depth, float max_depth, float fov_up_deg,
+                       float fov_down_deg, void* stream);
+
+/* ---- K7: points in boxes / voxel index ----------------------------------------------------------------
+ * points_in_boxes_cpu semantics (ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-168, MARGIN 1e-2):
+ *   pts [M,3], boxes [N,7] -> out int32 [N,M] in {0,1}                                                */
+int b200_points_in_boxes(const float* pts, const float* boxes, int* out, int N, int M, void* stream);
+/* points_in_boxes_gpu semantics (roiaware_pool3d_kernel.cu:313-336, MARGIN 1e-5): first box or -1     */
+int b200_points_in_boxes_first(const float* pts, const float* boxes, int* out, int B, int N, int M,
+                               void* stream);
+/* generate_pts_mask_for_box3d (roiaware_pool3d_kernel.cu:39-75): -1 or x<<16|y<<8|z voxel code          */
+int b200_voxel_index(const float* pts, const float* rois, int* out, int N, int M, int out_x, int out_y,
+                     int out_z, void* stream);
+
+/* ---- LiDARUtility (utils/lidar.py:34-132) --------------------------------------------------------- */
+/* normalized depth [B,1,H,W] in [-1,1] (sampler output) -> metric depth [B,H,W] and xyz [B,3,H,W]     */
+int b200_depth_to_xyz(const float* x_norm, const float* ray_angles, float* depth, float* xyz, int B,
+                      int H, int W, float min_depth, float max_depth, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LIDAR_H_ */

@@ -1,0 +1,563 @@
+// HBM-bound kernels of the denoiser step: GroupNorm apply + SiLU + fp16 cast (+concat), channel statistics,
+// FIR resampling, time embedding, first/last convs on CUDA cores, sampler update.  All NHWC fp32.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm apply (+AdaGN) + SiLU -> fp16, optional concat of two sources
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GN_MAX_C = 2048;
+constexpr int GN_PIX_PER_BLOCK = 32;
+
+__global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
+                                                     int C1, const double* __restrict__ st0,
+                                                     const double* __restrict__ st1, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ ada,
+                                                     int ada_stride, int groups, float eps, int silu,
+                                                     __half* __restrict__ y, size_t lo_off, int HW) {
+    __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int C = C0 + C1;
+    const int b = blockIdx.y;
+    const bool norm = st0 != nullptr;
+    if (norm) {
+        const int cpg = C / groups;
+        if (threadIdx.x < groups) {
+            double s = 0.0, ss = 0.0;
+            for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+                const double* p = c < C0 ? st0 + ((size_t)b * C0 + c) * 2 : st1 + ((size_t)b * C1 + (c - C0)) * 2;
+                s += p[0];
+                ss += p[1];
+            }
+            const double n = (double)HW * cpg;
+            const double mean = s / n;
+            double var = ss / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[threadIdx.x] = (float)mean;
+            s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / cpg;
+            float a = s_rstd[g], bb = -s_mean[g] * s_rstd[g];
+            if (gamma) { a *= gamma[c]; bb = bb * gamma[c] + beta[c]; }
+            if (ada) {
+                const float sc = 1.f + ada[(size_t)b * ada_stride + c];
+                const float sh = ada[(size_t)b * ada_stride + C + c];
+                a *= sc;
+                bb = bb * sc + sh;
+            }
+            s_a[c] = a;
+            s_b[c] = bb;
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { s_a[c] = 1.f; s_b[c] = 0.f; }
+    }
+    __syncthreads();
+    const int c8n = C / 8;
+    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+    const int np = min(GN_PIX_PER_BLOCK, HW - p0);
+    for (int i = threadIdx.x; i < np * c8n; i += blockDim.x) {
+        const int pp = i / c8n, c8 = i - pp * c8n;
+        const int c = c8 * 8;
+        const size_t pix = (size_t)b * HW + p0 + pp;
+        const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
+        const float4 v0 = *reinterpret_cast<const float4*>(src);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float t = fmaf(v[e], s_a[c + e], s_b[c + e]);
+            if (silu) t = silu_f(t);
+            v[e] = t;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(y + pix * C + c) = *reinterpret_cast<const uint4*>(h);
+        if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
+            __half2 l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 hf = __half22float2(h[e]);
+                l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+            }
+            *reinterpret_cast<uint4*>(y + lo_off + pix * C + c) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-(b, c) sum / sum of squares of an NHWC fp32 tensor (C/4 must divide 256 or be a multiple of it)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ST_PIX_PER_BLOCK = 256;
+
+__device__ __forceinline__ void block_channel_reduce(float4 s1, float4 s2, int C, int b, double* stats,
+                                                     float* red /* [256*8] */) {
+    // threads with equal (threadIdx.x % (C/4)) hold partial sums of the same 4 channels
+    const int c4n = C / 4;
+    float* r = red + threadIdx.x * 8;
+    r[0] = s1.x; r[1] = s1.y; r[2] = s1.z; r[3] = s1.w;
+    r[4] = s2.x; r[5] = s2.y; r[6] = s2.z; r[7] = s2.w;
+    __syncthreads();
+    if ((int)threadIdx.x < c4n) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int t = threadIdx.x; t < (int)blockDim.x; t += c4n)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += red[t * 8 + e];
+        double* st = stats + ((size_t)b * C + threadIdx.x * 4) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            atomicAdd(st + 2 * e, (double)acc[e]);
+            atomicAdd(st + 2 * e + 1, (double)acc[4 + e]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
+                                                            int HW, int C) {
+    __shared__ float red[256 * 8];
+    const int b = blockIdx.y;
+    const int c4n = C / 4;  // <= 256, divides 256
+    const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
+    const int p0 = blockIdx.x * ST_PIX_PER_BLOCK;
+    const int p1 = min(p0 + ST_PIX_PER_BLOCK, HW);
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    for (int pp = p0 + poff; pp < p1; pp += pstep) {
+        const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)b * HW + pp) * C + c4 * 4);
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+        s2.x += v.x * v.x; s2.y += v.y * v.y; s2.z += v.z * v.z; s2.w += v.w * v.w;
+    }
+    block_channel_reduce(s1, s2, C, b, stats, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FIR resample ([1,3,3,1] window), circular W / zero H
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fma4(float4& a, float k, const float4& v) {
+    a.x = fmaf(k, v.x, a.x); a.y = fmaf(k, v.y, a.y); a.z = fmaf(k, v.z, a.z); a.w = fmaf(k, v.w, a.w);
+}
+
+template <bool UP>
+__global__ void __launch_bounds__(256) fir_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                  double* __restrict__ stats, int H, int W, int C, int ring) {
+    __shared__ float red[256 * 8];
+    const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
+    const int b = blockIdx.y;
+    const int c4n = C / 4;
+    const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
+    const int p0 = blockIdx.x * ST_PIX_PER_BLOCK;
+    const int p1 = min(p0 + ST_PIX_PER_BLOCK, Ho * Wo);
+    const float* xb = x + (size_t)b * H * W * C + c4 * 4;
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    for (int pp = p0 + poff; pp < p1; pp += pstep) {
+        const int oh = pp / Wo, ow = pp - oh * Wo;
+        float4 acc = make_float4(0, 0, 0, 0);
+        if (UP) {
+            // out[2i] = (x[i-1] + 3x[i]) / 4 ; out[2i+1] = (3x[i] + x[i+1]) / 4    (per axis)
+            const int ih = oh >> 1, iw = ow >> 1;
+            const int hn = (oh & 1) ? ih + 1 : ih - 1;
+            int wn = (ow & 1) ? iw + 1 : iw - 1;
+            bool wn_ok = true;
+            if (wn < 0) { if (ring) wn += W; else wn_ok = false; }
+            else if (wn >= W) { if (ring) wn -= W; else wn_ok = false; }
+            const bool hn_ok = hn >= 0 && hn < H;
+            fma4(acc, 9.f / 16.f, ld4(xb + ((size_t)ih * W + iw) * C));
+            if (wn_ok) fma4(acc, 3.f / 16.f, ld4(xb + ((size_t)ih * W + wn) * C));
+            if (hn_ok) {
+                fma4(acc, 3.f / 16.f, ld4(xb + ((size_t)hn * W + iw) * C));
+                if (wn_ok) fma4(acc, 1.f / 16.f, ld4(xb + ((size_t)hn * W + wn) * C));
+            }
+        } else {
+            // out[i] = (x[2i-1] + 3x[2i] + 3x[2i+1] + x[2i+2]) / 8    (per axis)
+            const float kk[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int ih = 2 * oh - 1 + a;
+                if (ih < 0 || ih >= H) continue;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int iw = 2 * ow - 1 + c;
+                    if (iw < 0) { if (ring) iw += W; else continue; }
+                    else if (iw >= W) { if (ring) iw -= W; else continue; }
+                    fma4(acc, kk[a] * kk[c], ld4(xb + ((size_t)ih * W + iw) * C));
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(y + ((size_t)b * Ho * Wo + pp) * C + c4 * 4) = acc;
+        s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+        s2.x += acc.x * acc.x; s2.y += acc.y * acc.y; s2.z += acc.z * acc.z; s2.w += acc.w * acc.w;
+    }
+    if (stats) block_channel_reduce(s1, s2, C, b, stats, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// time embedding MLP + stacked (scale, shift) projections
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, const float* __restrict__ w1,
+                                                   const float* __restrict__ b1, const float* __restrict__ w2,
+                                                   const float* __restrict__ b2, const float* __restrict__ add,
+                                                   float* __restrict__ temb, int Cs, int E) {
+    extern __shared__ float sm[];
+    float* e0 = sm;        // [Cs]
+    float* h1 = sm + Cs;   // [E]
+    const int b = blockIdx.x;
+    const float tv = t[b];
+    const int half = Cs / 2;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const float f = expf(-logf(10000.f) / (float)(half - 1) * (float)i);
+        const float a = tv * f;
+        e0[i] = sinf(a);
+        e0[half + i] = cosf(a);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < E; o += blockDim.x) {
+        float acc = b1[o];
+        const float* wr = w1 + (size_t)o * Cs;
+        for (int k = 0; k < Cs; ++k) acc = fmaf(wr[k], e0[k], acc);
+        h1[o] = silu_f(acc);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < E; o += nw) {
+        const float* wr = w2 + (size_t)o * E;
+        float acc = 0.f;
+        for (int k = lane; k < E; k += 32) acc = fmaf(wr[k], h1[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) temb[(size_t)b * E + o] = acc + b2[o] + (add ? add[(size_t)b * E + o] : 0.f);
+    }
+}
+
+constexpr int ADA_ROWS_PER_BLOCK = 32;
+constexpr int ADA_MAX_B = 16;
+
+__global__ void __launch_bounds__(256) ada_proj_kernel(const float* __restrict__ temb, const float* __restrict__ wp,
+                                                       const float* __restrict__ bp, float* __restrict__ ada, int B,
+                                                       int E, int P) {
+    extern __shared__ float sm[];  // silu(temb) [B][E]
+    for (int i = threadIdx.x; i < B * E; i += blockDim.x) sm[i] = silu_f(temb[i]);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < ADA_ROWS_PER_BLOCK; rr += 8) {
+        const int row = blockIdx.x * ADA_ROWS_PER_BLOCK + rr;
+        if (row >= P) break;
+        const float* wr = wp + (size_t)row * E;
+        float acc[ADA_MAX_B];
+#pragma unroll
+        for (int b = 0; b < ADA_MAX_B; ++b) acc[b] = 0.f;
+        for (int k = lane; k < E; k += 32) {
+            const float wv = wr[k];
+#pragma unroll
+            for (int b = 0; b < ADA_MAX_B; ++b)
+                if (b < B) acc[b] = fmaf(wv, sm[b * E + k], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < ADA_MAX_B; ++b) {
+            if (b < B) {
+                const float v = warp_sum(acc[b]);
+                if (lane == 0) ada[(size_t)b * P + row] = v + bp[row];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// in_conv: few dynamic NCHW channels + precomputed constant part -> NHWC
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ cst, int cst_batched,
+                                                      float* __restrict__ out, double* __restrict__ stats, int H, int W,
+                                                      int Cx, int Cout, int ring) {
+    __shared__ float red[256 * 8];
+    __shared__ float sw[4 * 9 * 256];  // [ci][tap][co] , Cout <= 256
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < Cx * 9 * Cout; i += blockDim.x) {
+        const int co = i % Cout, r = i / Cout;
+        const int tap = r % 9, ci = r / 9;
+        sw[i] = w[((size_t)co * Cx + ci) * 9 + tap];
+    }
+    __syncthreads();
+    const int HW = H * W;
+    const int c4n = Cout / 4;
+    const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
+    const int p0 = blockIdx.x * ST_PIX_PER_BLOCK;
+    const int p1 = min(p0 + ST_PIX_PER_BLOCK, HW);
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    for (int pp = p0 + poff; pp < p1; pp += pstep) {
+        const int h = pp / W, ww = pp - h * W;
+        float4 acc = ld4(cst + ((size_t)(cst_batched ? b : 0) * HW + pp) * Cout + c4 * 4);
+        for (int ci = 0; ci < Cx; ++ci) {
+            const float* xp = x + ((size_t)b * Cx + ci) * HW;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int gh = h + tap / 3 - 1;
+                int gw = ww + tap % 3 - 1;
+                if (gh < 0 || gh >= H) continue;
+                if (gw < 0) { if (ring) gw += W; else continue; }
+                else if (gw >= W) { if (ring) gw -= W; else continue; }
+                const float xv = xp[gh * W + gw];
+                fma4(acc, xv, *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4));
+            }
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)b * HW + pp) * Cout + c4 * 4) = acc;
+        s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
+        s2.x += acc.x * acc.x; s2.y += acc.y * acc.y; s2.z += acc.z * acc.z; s2.w += acc.w * acc.w;
+    }
+    if (stats) block_channel_reduce(s1, s2, Cout, b, stats, red);
+}
+
+// generic fp32 direct conv (constant folding only; not a hot kernel)
+__global__ void conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W,
+                                   int Cin, int Cout, int k, int ring) {
+    const long long total = (long long)B * H * W * Cout;
+    const int pad = k / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long pix = i / Cout;
+        const int ww = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+        float acc = bias ? bias[co] : 0.f;
+        for (int dy = 0; dy < k; ++dy) {
+            const int gh = h + dy - pad;
+            if (gh < 0 || gh >= H) continue;
+            for (int dx = 0; dx < k; ++dx) {
+                int gw = ww + dx - pad;
+                if (gw < 0) { if (ring) gw += W; else continue; }
+                else if (gw >= W) { if (ring) gw -= W; else continue; }
+                const float* xp = x + ((size_t)(b * H + gh) * W + gw) * Cin;
+                const float* wp = w + (size_t)co * Cin * k * k + dy * k + dx;
+                for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xp[ci], wp[(size_t)ci * k * k], acc);
+            }
+        }
+        out[i] = acc;
+    }
+}
+
+// out_conv: NHWC (fp32 or fp16) -> NCHW, Cout <= 4; one thread per pixel, weights broadcast from smem
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+    const float4 a = ld4(p), b = ld4(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __half* p, float* v) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(128) out_conv_kernel(const TIn* __restrict__ a, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ pred, int H,
+                                                       int W, int Cin, int Cout, int ring) {
+    extern __shared__ float4 sw4[];  // [tap][ci] -> 4 output channels (zero padded)
+    float* sw = reinterpret_cast<float*>(sw4);
+    for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
+        const int co = i & 3, r = i >> 2;
+        const int ci = r % Cin, tap = r / Cin;
+        sw[i] = co < Cout ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pp >= HW) return;
+    const int h = pp / W, ww = pp - h * W;
+    float acc[4] = {0, 0, 0, 0};
+    for (int tap = 0; tap < 9; ++tap) {
+        const int gh = h + tap / 3 - 1;
+        int gw = ww + tap % 3 - 1;
+        if (gh < 0 || gh >= H) continue;
+        if (gw < 0) { if (ring) gw += W; else continue; }
+        else if (gw >= W) { if (ring) gw -= W; else continue; }
+        const TIn* ap = a + ((size_t)b * HW + (size_t)gh * W + gw) * Cin;
+        const float4* wt = sw4 + tap * Cin;
+        for (int ci = 0; ci < Cin; ci += 8) {
+            float v[8];
+            ld8(ap + ci, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float4 wv = wt[ci + e];
+                acc[0] = fmaf(v[e], wv.x, acc[0]);
+                acc[1] = fmaf(v[e], wv.y, acc[1]);
+                acc[2] = fmaf(v[e], wv.z, acc[2]);
+                acc[3] = fmaf(v[e], wv.w, acc[3]);
+            }
+        }
+    }
+    for (int co = 0; co < Cout; ++co) pred[((size_t)b * Cout + co) * HW + pp] = acc[co] + bias[co];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sampler update (continuous_time.py:205-231)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sampler_update_kernel(const float* __restrict__ x_t, const float* __restrict__ pred,
+                                      const float* __restrict__ noise, const float* __restrict__ coef,
+                                      float* __restrict__ x_s, int n, int mode, int objective, float clip) {
+    const int b = blockIdx.y;
+    const float a_t = coef[b * 8 + 0], s_t = coef[b * 8 + 1], a_s = coef[b * 8 + 2], s_s = coef[b * 8 + 3];
+    const float c1 = coef[b * 8 + 4], c2 = coef[b * 8 + 5], cc = coef[b * 8 + 6];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const size_t gi = (size_t)b * n + i;
+        const float xt = x_t[gi], pr = pred[gi];
+        float x0;
+        if (objective == 0) x0 = (xt - s_t * pr) / a_t;
+        else if (objective == 1) x0 = a_t * xt - s_t * pr;
+        else x0 = pr;
+        if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
+        float out;
+        if (mode == 0) {
+            const float eps = (xt - a_t * x0) / s_t;
+            out = a_s * x0 + c2 * eps;
+            if (noise) out += c1 * noise[gi];
+        } else {
+            const float mean = a_s * (xt * (1.f - cc) / a_t + cc * x0);
+            out = mean + s_s * sqrtf(cc) * noise[gi];
+        }
+        x_s[gi] = out;
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_version(void) { return 100; }
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" int b200_device_check(int dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties(%d) failed", dev);
+        return B200_E_CUDA;
+    }
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d, libb200lidar needs sm_100", dev, prop.major, prop.minor);
+        return B200_E_ARCH;
+    }
+    return prop.multiProcessorCount;
+}
+
+static bool c4_ok(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
+
+extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
+                               const double* stats1, const float* gamma, const float* beta, const float* ada,
+                               int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int HW,
+                               void* stream) {
+    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(x0 && y && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && (C1 == 0 || x1));
+    const int C = C0 + C1;
+    B200_CHECK_ARG(C <= GN_MAX_C);
+    if (stats0) {
+        B200_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0);
+        B200_CHECK_ARG(C1 == 0 || stats1);
+        B200_CHECK_ARG((gamma == nullptr) == (beta == nullptr));
+    } else {
+        B200_CHECK_ARG(!gamma && !ada);
+    }
+    dim3 grid(cdiv(HW, GN_PIX_PER_BLOCK), B);
+    gn_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
+                                                          groups, eps, silu, (__half*)y,
+                                                          parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_channel_stats(const float* x, double* stats, int B, int HW, int C, void* stream) {
+    B200_CHECK_ARG(x && stats && c4_ok(C));
+    dim3 grid(cdiv(HW, ST_PIX_PER_BLOCK), B);
+    channel_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, HW, C);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_fir_resample(const float* x, float* y, double* stats, int B, int H, int W, int C, int up, int ring,
+                                 void* stream) {
+    B200_CHECK_ARG(x && y && c4_ok(C));
+    B200_CHECK_ARG(up || (H % 2 == 0 && W % 2 == 0));
+    const int npo = up ? 4 * H * W : (H / 2) * (W / 2);
+    dim3 grid(cdiv(npo, ST_PIX_PER_BLOCK), B);
+    if (up) fir_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring);
+    else fir_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_time_embed(const float* t, const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* temb_add, const float* wp, const float* bp, float* temb, float* ada, int B,
+                               int Cs, int E, int P, void* stream) {
+    B200_CHECK_ARG(t && w1 && b1 && w2 && b2 && temb);
+    B200_CHECK_ARG(B > 0 && B <= ADA_MAX_B && Cs % 2 == 0 && Cs >= 4);
+    temb_kernel<<<B, 256, (Cs + E) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb_add, temb, Cs, E);
+    B200_CHECK_LAUNCH();
+    if (P > 0) {
+        B200_CHECK_ARG(wp && bp && ada);
+        B200_CHECK_ARG((size_t)B * E * sizeof(float) <= 48 * 1024);
+        ada_proj_kernel<<<cdiv(P, ADA_ROWS_PER_BLOCK), 256, (size_t)B * E * sizeof(float), (cudaStream_t)stream>>>(
+            temb, wp, bp, ada, B, E, P);
+        B200_CHECK_LAUNCH();
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_in_conv(const float* x, const float* w, const float* cst, int cst_batched, float* out,
+                            double* stats, int B, int H, int W, int Cx, int Cout, int ring, void* stream) {
+    B200_CHECK_ARG(x && w && cst && out);
+    B200_CHECK_ARG(Cx >= 1 && Cx <= 4 && Cout <= 256 && c4_ok(Cout));
+    dim3 grid(cdiv(H * W, ST_PIX_PER_BLOCK), B);
+    in_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, cst, cst_batched, out, stats, H, W, Cx, Cout, ring);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_conv_direct_f32(const float* x, const float* w, const float* bias, float* out, int B, int H, int W,
+                                    int Cin, int Cout, int k, int ring, void* stream) {
+    B200_CHECK_ARG(x && w && out && (k == 1 || k == 3));
+    const long long total = (long long)B * H * W * Cout;
+    const int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
+    conv_direct_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, H, W, Cin, Cout, k, ring);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias, float* pred, int B, int H,
+                             int W, int Cin, int Cout, int ring, void* stream) {
+    B200_CHECK_ARG(a && w && bias && pred && Cout >= 1 && Cout <= 4);
+    B200_CHECK_ARG(Cin % 8 == 0);
+    const size_t smem = (size_t)4 * 9 * Cin * sizeof(float);
+    B200_CHECK_ARG(smem <= 48 * 1024);
+    dim3 grid(cdiv(H * W, 128), B);
+    if (a_is_f16)
+        out_conv_kernel<__half><<<grid, 128, smem, (cudaStream_t)stream>>>((const __half*)a, w, bias, pred, H, W, Cin,
+                                                                          Cout, ring);
+    else
+        out_conv_kernel<float><<<grid, 128, smem, (cudaStream_t)stream>>>((const float*)a, w, bias, pred, H, W, Cin,
+                                                                         Cout, ring);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_sampler_update(const float* x_t, const float* pred, const float* noise, const float* coef,
+                                   float* x_s, int B, int n_per_sample, int mode, int objective, float clip,
+                                   void* stream) {
+    B200_CHECK_ARG(x_t && pred && coef && x_s && (mode == 0 || (mode == 1 && noise)));
+    dim3 grid(cdiv(n_per_sample, 256 * 4), B);
+    sampler_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, pred, noise, coef, x_s, n_per_sample, mode,
+                                                                  objective, clip);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}

@@ -1,0 +1,284 @@
+"""Continuous-time Gaussian diffusion sampler on the B200 plan (drop-in for
+lidargen/models/diffusion/{base,continuous_time,continuous_time_cond}.py).
+
+Public surface kept from the reference: constructor kwargs, ``sampling_shape``, ``device``, ``randn`` /
+``randn_like`` (None | Generator | per-sample list), ``log_snr``, ``q_step_from_x_0``, ``q_step``,
+``p_step`` and ``sample`` with the exact reference signatures; ``p_sample_loop`` is an alias of
+``sample`` (BASELINE.json's wording).  Training (``forward`` / ``p_loss``) is out of scope for the
+hot path and raises.
+
+One denoiser step = the model's static kernel plan + one fused sampler-update kernel; ``sample``
+captures that step in a CUDA graph and replays it ``num_steps`` times.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import List, Literal
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+# ---- log-SNR schedules (continuous_time.py:14-63) --------------------------------------------
+def _log(t, eps=1e-20):
+    return torch.log(t.clamp(min=eps))
+
+
+def _log_snr_schedule_linear(t: torch.Tensor) -> torch.Tensor:
+    return -_log(torch.special.expm1(1e-4 + 10 * (t ** 2)))[:, None, None, None]
+
+
+def _log_snr_schedule_cosine(t: torch.Tensor, logsnr_min: float = -15, logsnr_max: float = 15) -> torch.Tensor:
+    t_min = math.atan(math.exp(-0.5 * logsnr_max))
+    t_max = math.atan(math.exp(-0.5 * logsnr_min))
+    return -2 * _log(torch.tan(t_min + t * (t_max - t_min)))[:, None, None, None]
+
+
+def _log_snr_schedule_cosine_shifted(t, image_d, noise_d, logsnr_min=-15, logsnr_max=15):
+    return _log_snr_schedule_cosine(t, logsnr_min, logsnr_max) + 2 * math.log(noise_d / image_d)
+
+
+def _log_snr_schedule_cosine_interpolated(t, image_d, noise_d_low, noise_d_high, logsnr_min=-15, logsnr_max=15):
+    lo = _log_snr_schedule_cosine_shifted(t, image_d, noise_d_low, logsnr_min, logsnr_max)
+    hi = _log_snr_schedule_cosine_shifted(t, image_d, noise_d_high, logsnr_min, logsnr_max)
+    return t * lo + (1 - t) * hi
+
+
+def _log_snr_to_alpha_sigma(log_snr: torch.Tensor):
+    return log_snr.sigmoid().sqrt(), (-log_snr).sigmoid().sqrt()
+
+
+_OBJ = {"eps": 0, "v": 1, "x_0": 2}
+
+
+class GaussianDiffusion(nn.Module):
+    """diffusion/base.py:9-165 (sampling side)."""
+
+    def __init__(self, model: nn.Module, condition_model: nn.Module = None, sampling: str = "ddpm",
+                 prediction_type: str = "eps", loss_type="l2", num_training_steps: int | None = 1000,
+                 noise_schedule: str = "linear", min_snr_loss_weight: bool = True, min_snr_gamma: float = 5.0,
+                 sampling_resolution=None, clip_sample: bool = True, clip_sample_range: float = 1):
+        super().__init__()
+        self.model = model
+        self.condition_model = condition_model
+        self.sampling = sampling
+        self.num_training_steps = num_training_steps
+        self.objective = prediction_type
+        self.noise_schedule = noise_schedule
+        self.min_snr_loss_weight = min_snr_loss_weight
+        self.min_snr_gamma = min_snr_gamma
+        self.clip_sample = clip_sample
+        self.clip_sample_range = clip_sample_range
+        if prediction_type not in _OBJ:
+            raise ValueError(f"invalid objective {prediction_type}")
+        if not (isinstance(loss_type, nn.Module) or loss_type in ("l2", "l1", "huber")):
+            raise ValueError(f"invalid criterion: {loss_type}")
+        self.loss_type = loss_type
+        if sampling_resolution is None:
+            assert hasattr(self.model, "resolution") and hasattr(self.model, "in_channels")
+            self.sampling_shape = (self.model.in_channels, *self.model.resolution)
+        else:
+            assert len(sampling_resolution) == 2 and hasattr(self.model, "in_channels")
+            self.sampling_shape = (self.model.in_channels, *sampling_resolution)
+        self.setup_parameters()
+        self.register_buffer("_dummy", torch.tensor([]))
+
+    @property
+    def device(self):
+        return self._dummy.device
+
+    def randn(self, *shape, rng: List[torch.Generator] | torch.Generator | None = None, **kwargs) -> torch.Tensor:
+        if rng is None:
+            return torch.randn(*shape, **kwargs)
+        elif isinstance(rng, torch.Generator):
+            return torch.randn(*shape, generator=rng, **kwargs)
+        elif isinstance(rng, list):
+            assert len(rng) == shape[0]
+            return torch.stack([torch.randn(*shape[1:], generator=r, **kwargs) for r in rng])
+        raise ValueError(f"invalid rng: {rng}")
+
+    def randn_like(self, x: torch.Tensor, rng=None) -> torch.Tensor:
+        return self.randn(*x.shape, rng=rng, device=x.device, dtype=x.dtype)
+
+    def setup_parameters(self) -> None:
+        raise NotImplementedError
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training loss / backward is out of scope of the B200 hot path (SURVEY 8f-4)")
+
+    p_loss = forward
+
+
+class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
+    """diffusion/continuous_time.py:66-260."""
+
+    def __init__(self, model: nn.Module, condition_model: nn.Module = None, prediction_type: str = "eps",
+                 loss_type="l2", noise_schedule: str = "cosine", min_snr_loss_weight: bool = True,
+                 min_snr_gamma: float = 5.0, sampling_resolution=None, clip_sample: bool = True,
+                 clip_sample_range: float = 1, image_d: float = None, noise_d_low: float = None,
+                 noise_d_high: float = None):
+        self.image_d, self.noise_d_low, self.noise_d_high = image_d, noise_d_low, noise_d_high
+        super().__init__(model=model, condition_model=condition_model, sampling="ddpm",
+                         prediction_type=prediction_type, loss_type=loss_type, num_training_steps=None,
+                         noise_schedule=noise_schedule, min_snr_loss_weight=min_snr_loss_weight,
+                         min_snr_gamma=min_snr_gamma, sampling_resolution=sampling_resolution,
+                         clip_sample=clip_sample, clip_sample_range=clip_sample_range)
+        self._graphs: dict = {}
+        self.use_cuda_graph = True
+
+    def setup_parameters(self) -> None:
+        if self.noise_schedule == "linear":
+            self.log_snr = _log_snr_schedule_linear
+        elif self.noise_schedule == "cosine":
+            self.log_snr = _log_snr_schedule_cosine
+        elif self.noise_schedule == "cosine_shifted":
+            assert self.image_d is not None and self.noise_d_low is not None
+            self.log_snr = partial(_log_snr_schedule_cosine_shifted, image_d=self.image_d, noise_d=self.noise_d_low)
+        elif self.noise_schedule == "cosine_interpolated":
+            assert self.image_d is not None and self.noise_d_low is not None and self.noise_d_high is not None
+            self.log_snr = partial(_log_snr_schedule_cosine_interpolated, image_d=self.image_d,
+                                   noise_d_low=self.noise_d_low, noise_d_high=self.noise_d_high)
+        else:
+            raise ValueError(f"invalid beta schedule: {self.noise_schedule}")
+
+    def sample_timesteps(self, batch_size: int, device) -> torch.Tensor:
+        return torch.rand(batch_size, device=device, dtype=torch.float32)
+
+    def get_network_condition(self, steps):
+        return self.log_snr(steps)[:, 0, 0, 0]
+
+    def q_step_from_x_0(self, x_0, step_t, rng=None):
+        noise = self.randn_like(x_0, rng=rng)
+        alpha, sigma = _log_snr_to_alpha_sigma(self.log_snr(step_t))
+        return x_0 * alpha + noise * sigma, noise
+
+    def q_step(self, x_s, step_t, step_s, rng=None):
+        alpha_t, sigma_t = _log_snr_to_alpha_sigma(self.log_snr(step_t))
+        alpha_s, sigma_s = _log_snr_to_alpha_sigma(self.log_snr(step_s))
+        alpha_ts = alpha_t / alpha_s
+        var_noise = self.randn_like(x_s, rng=rng)
+        var = sigma_t.pow(2) - alpha_ts.pow(2) * sigma_s.pow(2)
+        return x_s * alpha_ts + var.sqrt() * var_noise
+
+    # ---- sampler coefficients: [.., 8] = alpha_t, sigma_t, alpha_s, sigma_s, c1, c2, ddpm_c, 0 ----
+    def _coefficients(self, step_t: torch.Tensor, step_s: torch.Tensor, ddim_eta: float):
+        lt = self.log_snr(step_t)[:, 0, 0, 0]
+        ls = self.log_snr(step_s)[:, 0, 0, 0]
+        a_t, s_t = _log_snr_to_alpha_sigma(lt)
+        a_s, s_s = _log_snr_to_alpha_sigma(ls)
+        c1 = ddim_eta * s_s / s_t * (1 - a_t ** 2 / a_s ** 2).sqrt()
+        c2 = (1 - a_s ** 2 - c1 ** 2).sqrt()
+        cc = -torch.special.expm1(lt - ls)
+        coef = torch.stack([a_t, s_t, a_s, s_s, c1, c2, cc, torch.zeros_like(cc)], dim=-1).float().contiguous()
+        return lt.float().contiguous(), coef
+
+    def _predict(self, x_t: torch.Tensor, log_snr_t: torch.Tensor) -> torch.Tensor:
+        return self.model(x_t, log_snr_t)
+
+    @torch.inference_mode()
+    def p_step(self, x_t: torch.Tensor, step_t: torch.Tensor, step_s: torch.Tensor, rng=None,
+               mode: Literal["ddpm", "ddim"] = "ddpm", ddim_eta: float = 0.0) -> torch.Tensor:
+        """continuous_time.py:194-234: one reverse step (model forward + fused update kernel)."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        lt, coef = self._coefficients(step_t, step_s, ddim_eta)
+        pred = self._predict(x_t, lt).contiguous()
+        noise = self.randn_like(x_t, rng=rng).contiguous()
+        x_t = x_t.contiguous()
+        x_s = torch.empty_like(x_t)
+        lib = _lib.get_lib()
+        B = x_t.shape[0]
+        lib.sampler_update(x_t.data_ptr(), pred.data_ptr(), noise.data_ptr(), coef.data_ptr(), x_s.data_ptr(), B,
+                           x_t[0].numel(), 0 if mode == "ddim" else 1, _OBJ[self.objective],
+                           float(self.clip_sample_range) if self.clip_sample else 0.0,
+                           _lib.current_stream(x_t.device))
+        return x_s
+
+    # ---- fast path: one CUDA graph per (batch, mode) replayed num_steps times ----
+    def _step_graph(self, plan, B: int, mode: str):
+        key = (id(plan), B, mode, self.objective, self.clip_sample, self.clip_sample_range)
+        if key in self._graphs:
+            return self._graphs[key]
+        dev = plan.dev
+        lib = _lib.get_lib()
+        coef = torch.zeros(B, 8, device=dev)
+        coef[:, 0] = 1; coef[:, 1] = 1; coef[:, 2] = 1; coef[:, 3] = 1
+        noise = torch.zeros(B, *self.sampling_shape, device=dev)
+        n_per = int(noise[0].numel())
+        mode_i = 0 if mode == "ddim" else 1
+        clip = float(self.clip_sample_range) if self.clip_sample else 0.0
+
+        def step():
+            st = _lib.current_stream(dev)
+            plan.launch(st)
+            # in-place: x_in <- update(x_in, pred)
+            lib.sampler_update(plan.x_in.data_ptr(), plan.pred.data_ptr(), noise.data_ptr(), coef.data_ptr(),
+                               plan.x_in.data_ptr(), B, n_per, mode_i, _OBJ[self.objective], clip, st)
+
+        entry = {"coef": coef, "noise": noise, "step": step, "graph": None}
+        if self.use_cuda_graph and dev.type == "cuda":
+            x_keep = plan.x_in.clone()
+            s = torch.cuda.Stream(dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                step()  # warm-up outside capture (function attributes, lazy module load)
+            torch.cuda.current_stream(dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            plan.x_in.copy_(x_keep)
+            entry["graph"] = g
+        self._graphs[key] = entry
+        return entry
+
+    @torch.inference_mode()
+    def sample(self, batch_size: int, num_steps: int, progress: bool = True, rng=None, return_all: bool = False,
+               mode: Literal["ddpm", "ddim"] = "ddpm", ddim_eta: float = 0.0):
+        """continuous_time.py:236-260."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        x = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
+        return self._sample_from(x, num_steps, progress, rng, return_all, mode, ddim_eta)
+
+    p_sample_loop = sample
+
+    def _sample_from(self, x, num_steps, progress, rng, return_all, mode, ddim_eta):
+        B = x.shape[0]
+        dev = x.device
+        plan = self.model.get_plan(B)
+        entry = self._step_graph(plan, B, mode)
+        steps = torch.linspace(1.0, 0.0, num_steps + 1, device=dev)
+        # per-step tables (same fp32 torch math as the reference, evaluated once for the whole trajectory)
+        lts, coefs = [], []
+        for i in range(num_steps):
+            lt, coef = self._coefficients(steps[i].repeat(B), steps[i + 1].repeat(B), ddim_eta)
+            lts.append(lt)
+            coefs.append(coef)
+        lts, coefs = torch.stack(lts), torch.stack(coefs)
+        need_noise = mode == "ddpm" or ddim_eta != 0.0
+        plan.x_in.copy_(x)
+        out = [x] if return_all else None
+        it = range(num_steps)
+        if progress:
+            try:
+                from tqdm.auto import tqdm
+                it = tqdm(it, desc="sampling", leave=False)
+            except Exception:  # pragma: no cover
+                pass
+        for i in it:
+            plan.t_in.copy_(lts[i])
+            entry["coef"].copy_(coefs[i])
+            # the reference draws noise every step (even for eta == 0): keep the RNG stream identical
+            noise = self.randn_like(plan.x_in, rng=rng)
+            if need_noise:
+                entry["noise"].copy_(noise)
+            if entry["graph"] is not None:
+                entry["graph"].replay()
+            else:
+                entry["step"]()
+            if return_all:
+                out.append(plan.x_in.clone())
+        return torch.stack(out) if return_all else plan.x_in.clone()

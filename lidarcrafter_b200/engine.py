@@ -1,0 +1,206 @@
+"""Host-side execution plans: turn a denoiser module (reference-compatible parameters) into a static
+sequence of libb200lidar kernel launches over pre-allocated NHWC device buffers.
+
+Layout in HBM: residual stream / conv outputs fp32 [B, H*W, C]; conv operands fp16
+[B, H*W, C]; GroupNorm statistics fp64 [B, C, 2] (sum, sum of squares) in one arena that is zeroed once
+per forward; weights repacked once into the tensor-core tile image (fp16).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+NUM_SMS = 148
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+@dataclass
+class Act:
+    """An NHWC activation: fp32 tensor + (optional) per-channel statistics slice."""
+    t: torch.Tensor            # [B, H*W, C] fp32
+    H: int
+    W: int
+    C: int
+    stats: dict | None = None  # stats slot from Plan.new_stats(): [B, C, 2] fp64 view into the arena
+
+
+def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, sms: int = NUM_SMS):
+    """Choose (bn, rows) for b200_conv_tc: maximise (SM fill) x min(L2-feed, MMA-shape) efficiency."""
+    best = None
+    for bn in (128, 64):
+        if Cout % bn:
+            continue
+        for rows in (4, 2, 1):
+            if H % rows or rows * bn > 512:
+                continue
+            tiles = B * (H // rows) * (W // 128) * (Cout // bn)
+            waves = math.ceil(tiles / sms)
+            fill = tiles / (waves * sms)
+            halo = 2 if taps == 9 else 0
+            l2 = 64.0 / rows + 924.0 * (rows + halo) / (rows * bn)      # bytes / clk / SM needed from L2
+            feed = min(1.0, 40.0 / l2)
+            shape = 1.0 if bn == 128 else 0.7
+            score = fill * min(feed, shape)
+            if best is None or score > best[0] + 1e-9:
+                best = (score, bn, rows)
+    if best is None:
+        raise ValueError(f"no conv tile for Cout={Cout}, H={H}")
+    return best[1], best[2]
+
+
+def weight_scale(weight: torch.Tensor) -> float:
+    """Power of two s with max|w| * s in [256, 512): keeps the fp16 hi/lo split of small weights out of
+    the subnormal range; undone exactly in the conv epilogue (w_inv = 1 / s)."""
+    m = float(weight.detach().abs().max())
+    if not (m > 0.0) or not math.isfinite(m):
+        return 1.0
+    return float(2.0 ** (8 - math.floor(math.log2(m))))
+
+
+class PackedConv:
+    """fp16 tile image of one conv's weights + fp32 bias (device)."""
+
+    def __init__(self, lib, weight: torch.Tensor, bias: torch.Tensor | None, bn: int, parts: int, stream: int):
+        Cout, Cin, kh, kw = weight.shape
+        self.Cout, self.Cin, self.taps, self.bn, self.parts = Cout, Cin, kh * kw, bn, parts
+        w = weight.detach().float().contiguous()
+        self.wscale = weight_scale(w)
+        self.packed = torch.empty(Cout * Cin * self.taps * parts, dtype=torch.float16, device=w.device)
+        lib.pack_conv_weight(_ptr(w), _ptr(self.packed), Cout, Cin, self.taps, bn, parts, self.wscale, stream)
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self._keep = w
+
+
+class Plan:
+    """Recorded launch list for one (module, batch) pair.  ``run(stream)`` replays it."""
+
+    def __init__(self, lib, device, B: int, conv_impl: str = "tc", parts: int = 2):
+        self.lib = lib
+        self.device = device
+        self.B = B
+        self.parts = parts            # 2 = error-compensated fp16 split (meets 1e-3), 1 = single fp16 pass
+        self.ops = []                 # list of (callable, args-without-stream)
+        self.bufs = []                # keep-alive
+        self.stats_chunks = []
+        self.stats_arena = None
+        self.conv_impl = conv_impl
+        self.flops = 0.0              # algorithmic conv / attention FLOPs per forward (for reporting)
+
+    # ---- buffers ----
+    def f32(self, *shape):
+        t = torch.empty(*shape, dtype=torch.float32, device=self.device)
+        self.bufs.append(t)
+        return t
+
+    def f16(self, *shape):
+        """fp16 conv operand [parts][*shape]"""
+        t = torch.empty(self.parts, *shape, dtype=torch.float16, device=self.device)
+        self.bufs.append(t)
+        return t
+
+    def new_stats(self, C: int):
+        """Reserve a [B, C, 2] fp64 slot; materialised by finalize()."""
+        off = sum(n for _, n in self.stats_chunks)
+        holder = {"off": off, "C": C, "t": None}
+        self.stats_chunks.append((holder, self.B * C * 2))
+        return holder
+
+    def finalize(self):
+        total = sum(n for _, n in self.stats_chunks)
+        self.stats_arena = torch.zeros(max(total, 1), dtype=torch.float64, device=self.device)
+        for holder, n in self.stats_chunks:
+            holder["t"] = self.stats_arena[holder["off"]:holder["off"] + n]
+        # resolve late-bound pointers once
+        self.ops = [(fn, tuple(a() if callable(a) else a for a in args)) for fn, args in self.ops]
+
+    def add(self, fn, *args):
+        self.ops.append((fn, args))
+
+    def run(self, stream: int):
+        self.stats_arena.zero_()
+        for fn, args in self.ops:
+            fn(*args, stream)
+
+    @property
+    def n_kernels(self):
+        return len(self.ops) + 1  # + the arena memset
+
+
+def _sp(holder):
+    """late-bound pointer of a stats slot (arena is allocated in finalize())."""
+    if holder is None:
+        return 0
+    return lambda: holder["t"].data_ptr()
+
+
+class PlanBuilder:
+    """Shared building blocks used by the EfficientUNet / LayoutUnetV1 planners."""
+
+    def __init__(self, plan: Plan, ring: bool, stream: int):
+        self.p = plan
+        self.lib = plan.lib
+        self.ring = 1 if ring else 0
+        self.stream = stream
+        self.B = plan.B
+
+    # ---- conv on tensor cores (or the FFMA cross-check path) ----
+    def conv(self, a16: torch.Tensor, H: int, W: int, weight, bias, res: torch.Tensor | None, scale: float,
+             want_stats: bool) -> tuple[torch.Tensor, dict | None]:
+        Cout, Cin, kh, kw = weight.shape
+        taps = kh * kw
+        out = self.p.f32(self.B, H * W, Cout)
+        st = self.p.new_stats(Cout) if want_stats else None
+        self.p.flops += 2.0 * self.B * H * W * taps * Cin * Cout
+        if self.p.conv_impl == "tc":
+            bn, rows = pick_tile(self.B, H, W, Cout, taps)
+            pc = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
+            self.p.bufs.append(pc)
+            self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
+                       1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
+                       self.p.parts)
+        else:
+            w = weight.detach().float().contiguous()
+            ws = weight_scale(w)
+            w16 = torch.empty(Cout * Cin * taps * self.p.parts, dtype=torch.float16, device=w.device)
+            self.lib.pack_conv_weight_plain(_ptr(w), _ptr(w16), Cout, Cin, taps, self.p.parts, ws, self.stream)
+            b32 = None if bias is None else bias.detach().float().contiguous()
+            self.p.bufs += [w, w16, b32]
+            self.p.add(self.lib.conv_ffma, _ptr(a16), _ptr(w16), _ptr(b32), _ptr(res), float(scale), 1.0 / ws,
+                       _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts)
+        return out, st
+
+    # ---- GroupNorm(+AdaGN)+SiLU -> fp16 operand ----
+    def gn_act(self, srcs: list[Act], gamma, beta, groups: int, eps: float, silu: bool, ada=None, ada_stride=0,
+               ada_off=0, normalize: bool = True) -> torch.Tensor:
+        a0 = srcs[0]
+        a1 = srcs[1] if len(srcs) > 1 else None
+        C = a0.C + (a1.C if a1 else 0)
+        HW = a0.H * a0.W
+        y = self.p.f16(self.B, HW, C)
+        g = None if gamma is None else gamma.detach().float().contiguous()
+        b = None if beta is None else beta.detach().float().contiguous()
+        self.p.bufs += [g, b]
+        if normalize:
+            assert a0.stats is not None and (a1 is None or a1.stats is not None)
+        ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * ada_off
+        self.p.add(self.lib.gn_act_f16, _ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0,
+                   _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b),
+                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, HW)
+        return y
+
+    def cast16(self, srcs: list[Act]) -> torch.Tensor:
+        return self.gn_act(srcs, None, None, 1, 0.0, False, normalize=False)
+
+    def fir(self, x: Act, up: bool, want_stats: bool) -> Act:
+        Ho, Wo = (2 * x.H, 2 * x.W) if up else (x.H // 2, x.W // 2)
+        y = self.p.f32(self.B, Ho * Wo, x.C)
+        st = self.p.new_stats(x.C) if want_stats else None
+        self.p.add(self.lib.fir_resample, _ptr(x.t), _ptr(y), _sp(st), self.B, x.H, x.W, x.C, 1 if up else 0, self.ring)
+        return Act(y, Ho, Wo, x.C, st)

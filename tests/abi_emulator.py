@@ -1,0 +1,247 @@
+"""CPU emulator of the libb200lidar C-ABI -- TEST INFRASTRUCTURE.
+
+Each method takes exactly the arguments of the matching ``b200_*`` entry point (raw addresses of CPU
+buffers instead of device pointers) and re-implements the documented contract with torch on the CPU.
+It lets ``-m "not gpu"`` tests execute the HOST logic (plan construction, weight packing order, buffer
+wiring, sampler loop) end to end against the oracle without a GPU.  It is never reachable from the
+product path (only ``tests/`` call ``_lib.set_test_lib``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+KC = 32
+
+
+def _arr(ptr, n, ctype, npdtype):
+    if ptr in (0, None):
+        return None
+    buf = (ctype * int(n)).from_address(int(ptr))
+    return torch.from_numpy(np.frombuffer(buf, dtype=npdtype, count=int(n)))
+
+
+def f32(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_float, np.float32)
+    return None if t is None else t.view(*shape)
+
+
+def f16(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_uint16, np.float16)
+    return None if t is None else t.view(*shape)
+
+
+def f64(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_double, np.float64)
+    return None if t is None else t.view(*shape)
+
+
+def i32(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_int32, np.int32)
+    return None if t is None else t.view(*shape)
+
+
+def _ring_pad(x, pad, ring):
+    if pad == 0:
+        return x
+    x = F.pad(x, (pad, pad, 0, 0), mode="circular" if ring else "constant")
+    return F.pad(x, (0, 0, pad, pad))
+
+
+class EmulatedLib:
+    def __init__(self):
+        self.n_launches = 0
+        self.calls = []
+
+    def _rec(self, name):
+        self.n_launches += 1
+        self.calls.append(name)
+
+    # ---- weights ----
+    @staticmethod
+    def _split(v, parts):
+        hi = v.half()
+        if parts == 1:
+            return hi[None]
+        return torch.stack([hi, (v - hi.float()).half()])
+
+    def pack_conv_weight(self, w, out, Cout, Cin, taps, bn, parts, wscale, stream):
+        self._rec("pack_conv_weight")
+        kc = 16 if parts == 2 else 32
+        W = self._split(f32(w, Cout, Cin, taps) * wscale, parts)        # [parts, Cout, Cin, taps]
+        # -> [Cout/bn][Cin/kc][taps][parts][kc/8][bn][8]
+        t = W.view(parts, Cout // bn, bn, Cin // kc, kc // 8, 8, taps).permute(1, 3, 6, 0, 4, 2, 5).contiguous()
+        f16(out, Cout * Cin * taps * parts).copy_(t.reshape(-1))
+        return 0
+
+    def pack_conv_weight_plain(self, w, out, Cout, Cin, taps, parts, wscale, stream):
+        self._rec("pack_conv_weight_plain")
+        W = self._split(f32(w, Cout, Cin, taps) * wscale, parts)
+        f16(out, parts, taps, Cout, Cin).copy_(W.permute(0, 3, 1, 2))
+        return 0
+
+    def _conv(self, a, W4, bias, res, scale, w_inv, out, stats, B, H, Wd, Cin, Cout, taps, ring, parts):
+        k = 3 if taps == 9 else 1
+        x = f16(a, parts, B, H, Wd, Cin).float().sum(0).permute(0, 3, 1, 2)
+        y = F.conv2d(_ring_pad(x, k // 2, ring), W4.float()) * w_inv
+        y = y.permute(0, 2, 3, 1)
+        if bias:
+            y = y + f32(bias, Cout)
+        if res:
+            y = y + f32(res, B, H, Wd, Cout)
+        y = (y * scale).float()
+        f32(out, B, H, Wd, Cout).copy_(y)
+        if stats:
+            st = f64(stats, B, Cout, 2)
+            st[:, :, 0] += y.double().sum(dim=(1, 2))
+            st[:, :, 1] += (y.double() ** 2).sum(dim=(1, 2))
+
+    def conv_tc(self, a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
+                parts, stream):
+        self._rec("conv_tc")
+        assert W % 128 == 0 and Cin % KC == 0 and Cout % bn == 0 and H % rows == 0 and rows * bn <= 512
+        k = 3 if taps == 9 else 1
+        kc = 16 if parts == 2 else 32
+        t = f16(wpacked, Cout // bn, Cin // kc, taps, parts, kc // 8, bn, 8).float().sum(3)
+        W4 = t.permute(0, 4, 1, 3, 5, 2).reshape(Cout, Cin, k, k)
+        self._conv(a, W4, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
+        return 0
+
+    def conv_ffma(self, a, w16, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts, stream):
+        self._rec("conv_ffma")
+        k = 3 if taps == 9 else 1
+        W4 = f16(w16, parts, taps, Cout, Cin).float().sum(0).permute(1, 2, 0).reshape(Cout, Cin, k, k)
+        self._conv(a, W4, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
+        return 0
+
+    # ---- GN / stats ----
+    def gn_act_f16(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, y, parts, B, HW,
+                   stream):
+        self._rec("gn_act_f16")
+        x = f32(x0, B, HW, C0)
+        if C1:
+            x = torch.cat([x, f32(x1, B, HW, C1)], dim=-1)
+        C = C0 + C1
+        if st0:
+            st = f64(st0, B, C0, 2)
+            if C1:
+                st = torch.cat([st, f64(st1, B, C1, 2)], dim=1)
+            cpg = C // groups
+            g = st.view(B, groups, cpg, 2).sum(dim=2)
+            n = HW * cpg
+            mean = g[..., 0] / n
+            var = (g[..., 1] / n - mean * mean).clamp(min=0)
+            rstd = 1.0 / torch.sqrt(var + eps)
+            mean = mean.float().repeat_interleave(cpg, dim=1)
+            rstd = rstd.float().repeat_interleave(cpg, dim=1)
+            a = rstd
+            b = -mean * rstd
+            if gamma:
+                a = a * f32(gamma, C)
+                b = b * f32(gamma, C) + f32(beta, C)
+            if ada:
+                full = _arr(ada, (B - 1) * ada_stride + 2 * C, ctypes.c_float, np.float32)
+                rows = torch.stack([full[i * ada_stride:i * ada_stride + 2 * C] for i in range(B)])
+                sc, sh = 1 + rows[:, :C], rows[:, C:]
+                a = a * sc
+                b = b * sc + sh
+            x = x * a[:, None, :] + b[:, None, :]
+        if silu:
+            x = F.silu(x)
+        f16(y, parts, B, HW, C).copy_(self._split(x, parts))
+        return 0
+
+    def channel_stats(self, x, stats, B, HW, C, stream):
+        self._rec("channel_stats")
+        t = f32(x, B, HW, C).double()
+        st = f64(stats, B, C, 2)
+        st[:, :, 0] += t.sum(1)
+        st[:, :, 1] += (t * t).sum(1)
+        return 0
+
+    def fir_resample(self, x, y, stats, B, H, W, C, up, ring, stream):
+        self._rec("fir_resample")
+        from oracle import unet_torch as O
+        t = f32(x, B, H, W, C).permute(0, 3, 1, 2)
+        r = (O.fir_up2(t, bool(ring)) if up else O.fir_down2(t, bool(ring))).permute(0, 2, 3, 1).contiguous()
+        f32(y, *r.shape).copy_(r)
+        if stats:
+            st = f64(stats, B, C, 2)
+            st[:, :, 0] += r.double().sum(dim=(1, 2))
+            st[:, :, 1] += (r.double() ** 2).sum(dim=(1, 2))
+        return 0
+
+    def time_embed(self, t, w1, b1, w2, b2, add, wp, bp, temb, ada, B, Cs, E, P, stream):
+        self._rec("time_embed")
+        tv = f32(t, B)
+        half = Cs // 2
+        fr = torch.exp(-math.log(10000.0) / (half - 1) * torch.arange(half, dtype=torch.float32))
+        a = tv[:, None] * fr[None]
+        e = torch.cat([a.sin(), a.cos()], -1)
+        h = F.silu(F.linear(e, f32(w1, E, Cs), f32(b1, E)))
+        te = F.linear(h, f32(w2, E, E), f32(b2, E))
+        if add:
+            te = te + f32(add, B, E)
+        f32(temb, B, E).copy_(te)
+        if P > 0:
+            f32(ada, B, P).copy_(F.linear(F.silu(te), f32(wp, P, E), f32(bp, P)))
+        return 0
+
+    def in_conv(self, x, w, cst, cst_batched, out, stats, B, H, W, Cx, Cout, ring, stream):
+        self._rec("in_conv")
+        xt = f32(x, B, Cx, H, W)
+        y = F.conv2d(_ring_pad(xt, 1, ring), f32(w, Cout, Cx, 3, 3)).permute(0, 2, 3, 1)
+        y = (y + f32(cst, B if cst_batched else 1, H, W, Cout)).contiguous()
+        f32(out, B, H, W, Cout).copy_(y)
+        if stats:
+            st = f64(stats, B, Cout, 2)
+            st[:, :, 0] += y.double().sum(dim=(1, 2))
+            st[:, :, 1] += (y.double() ** 2).sum(dim=(1, 2))
+        return 0
+
+    def conv_direct_f32(self, x, w, bias, out, B, H, W, Cin, Cout, k, ring, stream):
+        self._rec("conv_direct_f32")
+        xt = f32(x, B, H, W, Cin).permute(0, 3, 1, 2)
+        y = F.conv2d(_ring_pad(xt, k // 2, ring), f32(w, Cout, Cin, k, k), f32(bias, Cout) if bias else None)
+        f32(out, B, H, W, Cout).copy_(y.permute(0, 2, 3, 1))
+        return 0
+
+    def out_conv(self, a, a_is_f16, w, bias, pred, B, H, W, Cin, Cout, ring, stream):
+        self._rec("out_conv")
+        xt = (f16(a, B, H, W, Cin).float() if a_is_f16 else f32(a, B, H, W, Cin)).permute(0, 3, 1, 2)
+        y = F.conv2d(_ring_pad(xt, 1, ring), f32(w, Cout, Cin, 3, 3), f32(bias, Cout))
+        f32(pred, B, Cout, H, W).copy_(y)
+        return 0
+
+    def attention(self, q, ldq, qoff, k, ldk, koff, v, ldv, voff, out, ldo, parts, B, heads, Tq, Tk, dqk, dv, scale,
+                  stream):
+        self._rec("attention")
+        Q = f32(q, B, Tq, ldq)[:, :, qoff:qoff + heads * dqk].reshape(B, Tq, heads, dqk).transpose(1, 2)
+        K = f32(k, B, Tk, ldk)[:, :, koff:koff + heads * dqk].reshape(B, Tk, heads, dqk).transpose(1, 2)
+        V = f32(v, B, Tk, ldv)[:, :, voff:voff + heads * dv].reshape(B, Tk, heads, dv).transpose(1, 2)
+        att = torch.softmax(Q @ K.transpose(-1, -2) * scale, dim=-1)
+        o = (att @ V).transpose(1, 2).reshape(B, Tq, heads * dv)
+        f16(out, parts, B, Tq, ldo)[:, :, :, :heads * dv].copy_(self._split(o, parts))
+        return 0
+
+    def sampler_update(self, x_t, pred, noise, coef, x_s, B, n, mode, objective, clip, stream):
+        self._rec("sampler_update")
+        xt, pr = f32(x_t, B, n).clone(), f32(pred, B, n)
+        c = f32(coef, B, 8)
+        a_t, s_t, a_s, s_s, c1, c2, cc = [c[:, i:i + 1] for i in range(7)]
+        x0 = (xt - s_t * pr) / a_t if objective == 0 else (a_t * xt - s_t * pr if objective == 1 else pr)
+        if clip > 0:
+            x0 = x0.clamp(-clip, clip)
+        if mode == 0:
+            eps = (xt - a_t * x0) / s_t
+            o = a_s * x0 + c2 * eps
+            if noise:
+                o = o + c1 * f32(noise, B, n)
+        else:
+            o = a_s * (xt * (1 - cc) / a_t + cc * x0) + s_s * cc.sqrt() * f32(noise, B, n)
+        f32(x_s, B, n).copy_(o)
+        return 0
