@@ -271,7 +271,8 @@ class EfficientUNetPlan:
               te[3].weight.detach().float().contiguous(), te[3].bias.detach().float().contiguous()]
         plan.bufs += tw
         plan.add(self.lib.time_embed, _ptr(self.t_in), _ptr(tw[0]), _ptr(tw[1]), _ptr(tw[2]), _ptr(tw[3]), 0,
-                 _ptr(self.wp), _ptr(self.bp), _ptr(self.temb), _ptr(self.ada), B, m.base_channels, E, self.P)
+                 _ptr(self.wp), _ptr(self.bp), _ptr(self.temb), _ptr(self.ada), B, m.base_channels, E, self.P,
+                 name="time_embed", nbytes=4.0 * self.P * E)
 
         # ---- in_conv: constant (Fourier) part folded once, dynamic 2-channel part per step ----
         w_in = m.in_conv.weight.detach().float()
@@ -294,7 +295,7 @@ class EfficientUNetPlan:
         h0 = plan.f32(B, H * W, C0)
         st0 = plan.new_stats(C0)
         plan.add(self.lib.in_conv, _ptr(self.x_in), _ptr(w_dyn), _ptr(self.cst), 0, _ptr(h0), _sp(st0), B, H, W, cx, C0,
-                 1 if m.ring else 0)
+                 1 if m.ring else 0, name="in_conv", nbytes=4.0 * H * W * C0 * (B + 1))
         h = Act(h0, H, W, C0, st0)
 
         # ---- U-Net ----
@@ -312,7 +313,7 @@ class EfficientUNetPlan:
         b_out = m.out_conv.bias.detach().float().contiguous()
         plan.bufs += [w_out, b_out]
         plan.add(self.lib.out_conv, _ptr(u.t), 0, _ptr(w_out), _ptr(b_out), _ptr(self.pred), B, u.H, u.W, u.C,
-                 m.out_channels, 1 if m.ring else 0)
+                 m.out_channels, 1 if m.ring else 0, name="out_conv", nbytes=4.0 * B * u.H * u.W * (u.C + m.out_channels))
         plan.finalize()
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
@@ -347,7 +348,8 @@ class EfficientUNetPlan:
         att = self.plan.f16(self.B, T, E)
         d = E // nh
         self.plan.add(self.lib.attention, _ptr(qkv), 3 * E, 0, _ptr(qkv), 3 * E, E, _ptr(qkv), 3 * E, 2 * E,
-                      _ptr(att), E, self.plan.parts, self.B, nh, T, T, d, d, 1.0 / math.sqrt(d))
+                      _ptr(att), E, self.plan.parts, self.B, nh, T, T, d, d, 1.0 / math.sqrt(d), name="attention",
+                      flops=4.0 * self.B * nh * T * T * d)
         self.plan.flops += 4.0 * self.B * nh * T * T * d
         w_o = ab.attn.out_proj.weight.detach().reshape(E, E, 1, 1)
         out, st = pb.conv(att, x.H, x.W, w_o, ab.attn.out_proj.bias, x.t, float(ab.scale), True)

@@ -87,6 +87,7 @@ class Plan:
         self.B = B
         self.parts = parts            # 2 = error-compensated fp16 split (meets 1e-3), 1 = single fp16 pass
         self.ops = []                 # list of (callable, args-without-stream)
+        self.meta = []                # (kernel name, algorithmic flops, algorithmic bytes) per op
         self.bufs = []                # keep-alive
         self.stats_chunks = []
         self.stats_arena = None
@@ -120,8 +121,28 @@ class Plan:
         # resolve late-bound pointers once
         self.ops = [(fn, tuple(a() if callable(a) else a for a in args)) for fn, args in self.ops]
 
-    def add(self, fn, *args):
+    def add(self, fn, *args, name: str = "", flops: float = 0.0, nbytes: float = 0.0):
         self.ops.append((fn, args))
+        self.meta.append((name or getattr(fn, "__name__", "op"), flops, nbytes))
+
+    def profile(self, stream: int, reps: int = 3):
+        """Per-launch device time (CUDA events on the launching stream), one op at a time.
+        Returns [(name, ms, algorithmic flops, algorithmic bytes)]."""
+        out = []
+        self.run(stream)
+        torch.cuda.synchronize(self.device)
+        for (fn, args), (name, fl, by) in zip(self.ops, self.meta):
+            best = float("inf")
+            for _ in range(reps):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(*args, stream)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out.append((name, best, fl, by))
+        return out
 
     def run(self, stream: int):
         self.stats_arena.zero_()
@@ -157,14 +178,18 @@ class PlanBuilder:
         taps = kh * kw
         out = self.p.f32(self.B, H * W, Cout)
         st = self.p.new_stats(Cout) if want_stats else None
-        self.p.flops += 2.0 * self.B * H * W * taps * Cin * Cout
+        fl = 2.0 * self.B * H * W * taps * Cin * Cout
+        self.p.flops += fl
+        npix = self.B * H * W
+        by = npix * (2.0 * self.p.parts * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
+            + 2.0 * self.p.parts * taps * Cin * Cout
         if self.p.conv_impl == "tc":
             bn, rows = pick_tile(self.B, H, W, Cout, taps)
             pc = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
             self.p.bufs.append(pc)
             self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
                        1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
-                       self.p.parts)
+                       self.p.parts, name="conv_tc", flops=fl, nbytes=by)
         else:
             w = weight.detach().float().contiguous()
             ws = weight_scale(w)
@@ -173,7 +198,8 @@ class PlanBuilder:
             b32 = None if bias is None else bias.detach().float().contiguous()
             self.p.bufs += [w, w16, b32]
             self.p.add(self.lib.conv_ffma, _ptr(a16), _ptr(w16), _ptr(b32), _ptr(res), float(scale), 1.0 / ws,
-                       _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts)
+                       _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts,
+                       name="conv_ffma", flops=fl, nbytes=by)
         return out, st
 
     # ---- GroupNorm(+AdaGN)+SiLU -> fp16 operand ----
@@ -192,7 +218,8 @@ class PlanBuilder:
         ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * ada_off
         self.p.add(self.lib.gn_act_f16, _ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0,
                    _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b),
-                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, HW)
+                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, HW,
+                   name="gn_act_f16", nbytes=self.B * HW * C * (4.0 + 2.0 * self.p.parts))
         return y
 
     def cast16(self, srcs: list[Act]) -> torch.Tensor:
@@ -202,5 +229,6 @@ class PlanBuilder:
         Ho, Wo = (2 * x.H, 2 * x.W) if up else (x.H // 2, x.W // 2)
         y = self.p.f32(self.B, Ho * Wo, x.C)
         st = self.p.new_stats(x.C) if want_stats else None
-        self.p.add(self.lib.fir_resample, _ptr(x.t), _ptr(y), _sp(st), self.B, x.H, x.W, x.C, 1 if up else 0, self.ring)
+        self.p.add(self.lib.fir_resample, _ptr(x.t), _ptr(y), _sp(st), self.B, x.H, x.W, x.C, 1 if up else 0, self.ring,
+                   name="fir_resample", nbytes=4.0 * self.B * x.C * (x.H * x.W + Ho * Wo))
         return Act(y, Ho, Wo, x.C, st)

@@ -1,0 +1,277 @@
+"""GPU parity tests, kernel by kernel, THROUGH THE C-ABI: every libb200lidar entry point is run on the
+B200 with seeded inputs and compared with tests/abi_emulator.py (a CPU restatement of each kernel's
+contract built on the same torch ops the oracle uses)."""
+import math
+
+import pytest
+import torch
+
+from abi_emulator import EmulatedLib
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _lib():
+    from lidarcrafter_b200 import _lib as L
+    assert L._TEST_LIB is None
+    L.require_b200(0)
+    return L.get_lib()
+
+
+class Both:
+    """Run one entry point on the GPU library and on the emulator; tensors are given as CPU tensors
+    (inputs and zero-filled outputs) and mirrored to the device."""
+
+    def __init__(self):
+        self.gpu = _lib()
+        self.emu = EmulatedLib()
+        self.cpu, self.dev = [], []
+
+    def t(self, x):
+        x = x.contiguous()
+        self.cpu.append(x)
+        self.dev.append(x.cuda())
+        return len(self.cpu) - 1
+
+    def call(self, name, args):
+        """args: ints/floats, or ('t', idx) tensor handles, or None."""
+        ga = [self.dev[a[1]].data_ptr() if isinstance(a, tuple) else (0 if a is None else a) for a in args]
+        ca = [self.cpu[a[1]].data_ptr() if isinstance(a, tuple) else (0 if a is None else a) for a in args]
+        getattr(self.gpu, name)(*ga, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        getattr(self.emu, name)(*ca, 0)
+
+    def out(self, idx):
+        return self.dev[idx].cpu(), self.cpu[idx]
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def randn(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def split(v, parts):
+    return EmulatedLib._split(v, parts).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("taps", [9, 1])
+@pytest.mark.parametrize("bn,rows,Cin,Cout,H,W,B", [
+    (64, 4, 64, 64, 8, 256, 2),
+    (64, 2, 96, 64, 4, 128, 1),
+    (64, 1, 32, 128, 3, 128, 2),
+    (128, 4, 128, 128, 4, 256, 1),
+    (128, 2, 64, 256, 2, 128, 2),
+    (128, 1, 256, 128, 1, 128, 3),
+])
+def test_conv_tc_matches_contract(parts, taps, bn, rows, Cin, Cout, H, W, B):
+    """tcgen05 implicit-GEMM conv (+bias, +residual, *scale, +stats) vs F.conv2d on the same fp16 operands."""
+    h = Both()
+    k = 3 if taps == 9 else 1
+    w = h.t(randn(Cout, Cin, k, k, seed=1, scale=1 / math.sqrt(Cin * taps)))
+    a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
+    bias = h.t(randn(Cout, seed=3, scale=0.1))
+    res = h.t(randn(B, H, W, Cout, seed=4))
+    wp = h.t(torch.zeros(Cout * Cin * taps * parts, dtype=torch.float16))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    wscale = 64.0
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, parts, wscale])
+    g, c = h.out(wp)
+    assert torch.equal(g, c), "packed weight image differs"
+    h.call("conv_tc", [("t", a), ("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out), ("t", st),
+                       B, H, W, Cin, Cout, taps, 1, bn, rows, parts])
+    g, c = h.out(out)
+    assert rel(g, c) < 2e-6, rel(g, c)
+    gs, cs = h.out(st)
+    assert rel(gs, cs) < 1e-6
+
+
+def test_conv_tc_zero_pad_no_bias_no_res():
+    h = Both()
+    B, H, W, Cin, Cout = 1, 4, 128, 64, 64
+    w = h.t(randn(Cout, Cin, 3, 3, seed=1, scale=0.05))
+    a = h.t(split(randn(B, H, W, Cin, seed=2), 2))
+    wp = h.t(torch.zeros(Cout * Cin * 9 * 2, dtype=torch.float16))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 64, 2, 128.0])
+    h.call("conv_tc", [("t", a), ("t", wp), None, None, 1.0, 1.0 / 128.0, ("t", out), None, B, H, W, Cin, Cout, 9, 0, 64,
+                       4, 2])
+    g, c = h.out(out)
+    assert rel(g, c) < 2e-6
+
+
+def test_conv_tc_split_reaches_fp32_accuracy():
+    """fp16x3 split vs an fp64 convolution of the ORIGINAL fp32 operands: ~1e-6, single fp16 ~5e-4."""
+    import torch.nn.functional as F
+    B, H, W, Cin, Cout = 1, 4, 128, 128, 128
+    w32 = randn(Cout, Cin, 3, 3, seed=1, scale=1 / math.sqrt(Cin * 9))
+    x32 = randn(B, H, W, Cin, seed=2)
+    xp = F.pad(F.pad(x32.permute(0, 3, 1, 2).double(), (1, 1, 0, 0), mode="circular"), (0, 0, 1, 1))
+    ref = F.conv2d(xp, w32.double()).permute(0, 2, 3, 1).float()
+    errs = {}
+    for parts in (2, 1):
+        h = Both()
+        w = h.t(w32)
+        a = h.t(split(x32, parts))
+        wp = h.t(torch.zeros(Cout * Cin * 9 * parts, dtype=torch.float16))
+        out = h.t(torch.zeros(B, H, W, Cout))
+        ws = 2.0 ** (8 - math.floor(math.log2(float(w32.abs().max()))))
+        h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 128, parts, ws])
+        h.call("conv_tc", [("t", a), ("t", wp), None, None, 1.0, 1.0 / ws, ("t", out), None, B, H, W, Cin, Cout, 9, 1,
+                           128, 4, parts])
+        errs[parts] = rel(h.out(out)[0], ref)
+    assert errs[2] < 5e-6, errs
+    assert errs[1] < 2e-3, errs
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+def test_conv_ffma_matches_contract(parts):
+    h = Both()
+    B, H, W, Cin, Cout, taps = 2, 4, 64, 40, 64, 9
+    w = h.t(randn(Cout, Cin, 3, 3, seed=1, scale=0.05))
+    a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
+    bias = h.t(randn(Cout, seed=3, scale=0.1))
+    res = h.t(randn(B, H, W, Cout, seed=4))
+    w16 = h.t(torch.zeros(Cout * Cin * taps * parts, dtype=torch.float16))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    h.call("pack_conv_weight_plain", [("t", w), ("t", w16), Cout, Cin, taps, parts, 32.0])
+    h.call("conv_ffma", [("t", a), ("t", w16), ("t", bias), ("t", res), 1.0, 1 / 32.0, ("t", out), ("t", st), B, H, W,
+                         Cin, Cout, taps, 1, parts])
+    g, c = h.out(out)
+    assert rel(g, c) < 2e-6
+    assert rel(*h.out(st)) < 1e-6
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("C0,C1,groups,affine,ada,silu,norm", [
+    (64, 0, 8, True, False, True, True),
+    (64, 0, 8, False, True, True, True),
+    (128, 64, 8, True, False, True, True),
+    (256, 128, 32, True, True, False, True),
+    (64, 64, 1, False, False, False, False),
+])
+def test_gn_act(parts, C0, C1, groups, affine, ada, silu, norm):
+    h = Both()
+    B, HW = 3, 200
+    C = C0 + C1
+    x0 = randn(B, HW, C0, seed=1) * 2 + 0.3
+    x1 = randn(B, HW, max(C1, 8), seed=2) - 0.5
+    ix0, ix1 = h.t(x0), h.t(x1)
+
+    def stats(x):
+        return torch.stack([x.double().sum(1), (x.double() ** 2).sum(1)], -1).contiguous()
+    s0, s1 = h.t(stats(x0)), h.t(stats(x1[..., :max(C1, 8)]))
+    gam, bet = h.t(1 + 0.1 * randn(C, seed=3)), h.t(0.1 * randn(C, seed=4))
+    P = 2 * C + 24
+    adat = h.t(0.3 * randn(B, P, seed=5))
+    y = h.t(torch.zeros(parts, B, HW, C, dtype=torch.float16))
+    # ada pointer offset of 8 floats inside the row, as the planner does
+    args = [("t", ix0), C0, ("t", ix1) if C1 else None, C1, ("t", s0) if norm else None,
+            ("t", s1) if (norm and C1) else None, ("t", gam) if affine else None, ("t", bet) if affine else None,
+            ("t", adat) if ada else None, P, groups, 1e-6, 1 if silu else 0, ("t", y), parts, B, HW]
+    h.call("gn_act_f16", args)
+    g, c = h.out(y)
+    full_g, full_c = g.float().sum(0), c.float().sum(0)
+    assert rel(full_g, full_c) < (3e-6 if parts == 2 else 6e-4)
+
+
+def test_channel_stats_and_fir():
+    for up in (0, 1):
+        h = Both()
+        B, H, W, C = 2, 6, 32, 64
+        x = h.t(randn(B, H, W, C, seed=1))
+        Ho, Wo = (2 * H, 2 * W) if up else (H // 2, W // 2)
+        y = h.t(torch.zeros(B, Ho, Wo, C))
+        st = h.t(torch.zeros(B, C, 2, dtype=torch.float64))
+        h.call("fir_resample", [("t", x), ("t", y), ("t", st), B, H, W, C, up, 1])
+        assert rel(*h.out(y)) < 1e-6
+        assert rel(*h.out(st)) < 1e-6
+    h = Both()
+    x = h.t(randn(2, 700, 128, seed=3))
+    st = h.t(torch.zeros(2, 128, 2, dtype=torch.float64))
+    h.call("channel_stats", [("t", x), ("t", st), 2, 700, 128])
+    assert rel(*h.out(st)) < 1e-6
+
+
+def test_time_embed():
+    h = Both()
+    B, Cs, E, P = 4, 64, 256, 640
+    t = h.t(torch.tensor([-14.5, -3.0, 0.7, 12.0]))
+    w1, b1 = h.t(randn(E, Cs, seed=1, scale=0.1)), h.t(randn(E, seed=2, scale=0.1))
+    w2, b2 = h.t(randn(E, E, seed=3, scale=0.06)), h.t(randn(E, seed=4, scale=0.1))
+    wp, bp = h.t(randn(P, E, seed=5, scale=0.06)), h.t(randn(P, seed=6, scale=0.1))
+    add = h.t(randn(B, E, seed=7))
+    temb, ada = h.t(torch.zeros(B, E)), h.t(torch.zeros(B, P))
+    h.call("time_embed", [("t", t), ("t", w1), ("t", b1), ("t", w2), ("t", b2), ("t", add), ("t", wp), ("t", bp),
+                          ("t", temb), ("t", ada), B, Cs, E, P])
+    assert rel(*h.out(temb)) < 1e-5
+    assert rel(*h.out(ada)) < 1e-5
+
+
+def test_in_conv_out_conv_direct():
+    h = Both()
+    B, H, W, Cx, Cout = 2, 5, 64, 2, 64
+    x = h.t(randn(B, Cx, H, W, seed=1))
+    w = h.t(randn(Cout, Cx, 3, 3, seed=2, scale=0.2))
+    cst = h.t(randn(1, H, W, Cout, seed=3))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    h.call("in_conv", [("t", x), ("t", w), ("t", cst), 0, ("t", out), ("t", st), B, H, W, Cx, Cout, 1])
+    assert rel(*h.out(out)) < 1e-6
+    assert rel(*h.out(st)) < 1e-6
+
+    h = Both()
+    Cin, Co = 30, 64
+    x = h.t(randn(1, H, W, Cin, seed=1))
+    w = h.t(randn(Co, Cin, 3, 3, seed=2, scale=0.1))
+    b = h.t(randn(Co, seed=3))
+    out = h.t(torch.zeros(1, H, W, Co))
+    h.call("conv_direct_f32", [("t", x), ("t", w), ("t", b), ("t", out), 1, H, W, Cin, Co, 3, 1])
+    assert rel(*h.out(out)) < 1e-6
+
+    for is16 in (0, 1):
+        h = Both()
+        a32 = randn(B, H, W, 64, seed=4)
+        a = h.t(a32.half() if is16 else a32)
+        w = h.t(randn(2, 64, 3, 3, seed=5, scale=0.1))
+        b = h.t(randn(2, seed=6))
+        pred = h.t(torch.zeros(B, 2, H, W))
+        h.call("out_conv", [("t", a), is16, ("t", w), ("t", b), ("t", pred), B, H, W, 64, 2, 1])
+        assert rel(*h.out(pred)) < 1e-6
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("E,heads,T", [(512, 8, 512), (256, 8, 128)])
+def test_attention(parts, E, heads, T):
+    h = Both()
+    B = 2
+    d = E // heads
+    qkv = h.t(randn(B, T, 3 * E, seed=1))
+    out = h.t(torch.zeros(parts, B, T, E, dtype=torch.float16))
+    h.call("attention", [("t", qkv), 3 * E, 0, ("t", qkv), 3 * E, E, ("t", qkv), 3 * E, 2 * E, ("t", out), E, parts, B,
+                         heads, T, T, d, d, 1 / math.sqrt(d)])
+    g, c = h.out(out)
+    assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)
+
+
+@pytest.mark.parametrize("mode,objective", [(0, 0), (0, 1), (0, 2), (1, 0)])
+def test_sampler_update(mode, objective):
+    h = Both()
+    B, n = 3, 5000
+    xt, pr, nz = h.t(randn(B, n, seed=1)), h.t(randn(B, n, seed=2)), h.t(randn(B, n, seed=3))
+    lt, ls = torch.tensor([-4.0, 0.5, 3.0]), torch.tensor([-3.0, 1.5, 5.0])
+    a_t, s_t, a_s, s_s = lt.sigmoid().sqrt(), (-lt).sigmoid().sqrt(), ls.sigmoid().sqrt(), (-ls).sigmoid().sqrt()
+    c1 = 0.3 * s_s / s_t * (1 - a_t ** 2 / a_s ** 2).sqrt()
+    c2 = (1 - a_s ** 2 - c1 ** 2).sqrt()
+    cc = -torch.expm1(lt - ls)
+    coef = h.t(torch.stack([a_t, s_t, a_s, s_s, c1, c2, cc, torch.zeros(3)], -1))
+    xs = h.t(torch.zeros(B, n))
+    h.call("sampler_update", [("t", xt), ("t", pr), ("t", nz), ("t", coef), ("t", xs), B, n, mode, objective, 1.0])
+    assert rel(*h.out(xs)) < 1e-6
