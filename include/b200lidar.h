@@ -34,15 +34,19 @@ const char* b200_last_error(void);
  * replaces: F.pad(circular W / zero H) + nn.Conv2d  (models/unets/ops.py:32-49,149-173) together with
  *           the bias add, the residual add and the 1/sqrt(2) scale of ResidualBlock.forward
  *           (models/unets/efficient_unet.py:112-115), and the GroupNorm statistics of the NEXT norm.
- *   a        : fp16 [parts][B,H,W,Cin] conv operand (already normalised/activated, see b200_gn_act_f16);
+ *   a        : fp16 conv operand in SLAB-MAJOR layout [parts][B][H][Cin/8][W][8] (for one image row and one
+ *              8-channel group all pixels are contiguous at a 16 B pitch = the tcgen05 no-swizzle K-major
+ *              shared-memory image, so the TMA engine stages it with plain bulk copies), already
+ *              normalised/activated by b200_gn_act_f16;
  *              parts = 1: plain fp16;  parts = 2: a = a[0] (hi) + a[1] (lo), the error-compensated split
  *              (3 tensor-core MMAs per product, ~fp32 accuracy -- the mode that meets the 1e-3 tolerance)
  *   wpacked  : fp16 image from b200_pack_conv_weight (same bn, same parts), pre-scaled by wscale = 1/w_inv
  *   out      : fp32 [B,H,W,Cout] = (conv(a)*w_inv + bias + res) * out_scale   (res may be NULL / == out)
  *   stats    : fp64 [B,Cout,2] += {sum, sum of squares} of `out` over H*W  (may be NULL)
  *   taps     : 9 (3x3, padding 1) or 1 (1x1);  ring: 1 = circular in W, 0 = zero pad
- *   bn       : output-channel tile (64 or 128, Cout % bn == 0);  rows: image rows per CTA (1,2,4; H % rows == 0)
- * constraints: W % 128 == 0, Cin % 32 == 0.                                                       */
+ *   bn       : output-channel tile (64 or 128, Cout % bn == 0);  rows: image rows per tile (1,2,4; H % rows == 0,
+ *              rows*bn <= 256: two TMEM accumulator sets so the epilogue overlaps the next tile's MMAs)
+ * constraints: W % 128 == 0, Cin % 32 == 0.  Persistent kernel: grid = min(#tiles, #SMs).          */
 int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
                  float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
                  int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
@@ -69,10 +73,11 @@ int b200_conv_ffma(const void* a, const void* w16, const float* bias, const floa
  *   stats0/1 : fp64 [B,C,2] per-channel {sum,sumsq} of the sources; NULL => no normalisation (cast only)
  *   gamma/beta: [C0+C1] or NULL;  ada: fp32, scale at ada[b*ada_stride + c], shift at
  *               ada[b*ada_stride + (C0+C1) + c], NULL => none;  silu: 1 = apply x*sigmoid(x)
- *   y        : fp16 [parts][B,HW,C0+C1]; parts = 2 also writes the residual lo = fp16(v - fp32(hi))      */
+ *   y        : fp16 slab-major [parts][B][H][(C0+C1)/8][W][8] (the conv operand layout);
+ *              parts = 2 also writes the residual lo = fp16(v - fp32(hi))                                */
 int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                     const double* stats1, const float* gamma, const float* beta, const float* ada,
-                    int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int HW,
+                    int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
                     void* stream);
 /* per-(b,c) {sum,sumsq} of an fp32 NHWC tensor, accumulated (+=) into stats fp64 [B,C,2] */
 int b200_channel_stats(const float* x, double* stats, int B, int HW, int C, void* stream);
@@ -108,12 +113,13 @@ int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias
 
 /* ---- K2: attention ---------------------------------------------------------------------------------
  * softmax(q k^T * scale) v per (batch, head); q/k/v are slices of fp32 token-major tensors
- *   q: [B,Tq,ldq] at column offset head*dqk (+qoff), k: [B,Tk,ldk], v: [B,Tk,ldv]; out fp16 [parts][B,Tq,ldo]
+ *   q: [B,Tq,ldq] at column offset head*dqk (+qoff), k: [B,Tk,ldk], v: [B,Tk,ldv];
+ *   out fp16 slab-major conv operand [parts][B][Tq/out_w][ldo/8][out_w][8] (token t = row t/out_w, col t%out_w)
  * replaces: nn.MultiheadAttention core (efficient_unet.py:39-53) / QKVAttentionLegacy einsum-softmax-einsum
  *           (layout_unet_v1.py:488-505)                                                              */
 int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
-                   int ldv, int voff, void* out, int ldo, int parts, int B, int heads, int Tq, int Tk,
-                   int dqk, int dv, float scale, void* stream);
+                   int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq,
+                   int Tk, int dqk, int dv, float scale, void* stream);
 
 /* ---- K5: sampler update --------------------------------------------------------------------------
  * replaces p_step's ~25 elementwise ops (diffusion/continuous_time.py:205-231).

@@ -13,7 +13,7 @@ struct AttnParams {
     const float *q, *k, *v;
     __half* out;
     size_t lo_off;
-    int ldq, qoff, ldk, koff, ldv, voff, ldo;
+    int ldq, qoff, ldk, koff, ldv, voff, ldo, Wimg;
     int heads, Tq, Tk, dqk, dv;
     float scale;
 };
@@ -95,7 +95,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     }
     if (qi < nq) {
         const float inv = sInv[qi];
-        __half* o = p.out + ((size_t)b * p.Tq + q0 + qi) * p.ldo + head * p.dv + dc * dper;
+        // slab-major conv operand: token t = (h, w) of an image of width Wimg; [b][h][ldo/8][w][8]
+        const int tq = q0 + qi;
+        const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
+        const int ch = head * p.dv + dc * dper;
+        __half* o = p.out + ((((size_t)b * (p.Tq / p.Wimg) + hh) * (p.ldo / 8) + ch / 8) * p.Wimg + ww) * 8 + (ch & 7);
         for (int e = 0; e < dper; ++e) {
             const float val = acc[e] * inv;
             const __half hi = __float2half_rn(val);
@@ -110,13 +114,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 using namespace b200;
 
 extern "C" int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
-                              int ldv, int voff, void* out, int ldo, int parts, int B, int heads, int Tq, int Tk, int dqk,
-                              int dv, float scale, void* stream) {
+                              int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq, int Tk,
+                              int dqk, int dv, float scale, void* stream) {
     B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(out_w > 0 && Tq % out_w == 0 && ldo % 8 == 0);
     B200_CHECK_ARG(q && k && v && out);
     B200_CHECK_ARG(dqk % 4 == 0 && (dv == 32 || dv == 64));
     B200_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && qoff % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
-    AttnParams p{q, k, v, (__half*)out, parts == 2 ? (size_t)B * Tq * ldo : 0, ldq, qoff, ldk, koff, ldv, voff, ldo, heads, Tq, Tk, dqk, dv, scale};
+    AttnParams p{q, k, v, (__half*)out, parts == 2 ? (size_t)B * Tq * ldo : 0, ldq, qoff, ldk, koff, ldv, voff, ldo, out_w, heads, Tq, Tk, dqk, dv, scale};
     const size_t smem = ((size_t)ATT_QT * dqk + (size_t)ATT_QT * (Tk + 1) + ATT_QT) * sizeof(float);
     B200_CHECK_ARG(smem <= 200 * 1024);
     static size_t smem_set = 0;

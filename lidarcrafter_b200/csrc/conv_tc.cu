@@ -1,26 +1,28 @@
 // K1: ring-padded 3x3 / 1x1 convolution as an implicit GEMM on the sm_100a tensor cores.
 //
-//   out[b,h,w,n] = ( sum_{dy,dx,k} a[b, h+dy-1, (w+dx-1) mod W, k] * wgt[n,k,dy,dx] + bias[n] + res[b,h,w,n] ) * scale
+//   out[b,h,w,n] = ( w_inv * sum_{dy,dx,k} a[b, h+dy-1, (w+dx-1) mod W, k] * wgt[n,k,dy,dx] + bias[n] + res[b,h,w,n] ) * scale
 //
 // replaces F.pad(circular)+nn.Conv2d (+bias, +skip, *1/sqrt2, next GroupNorm statistics) of the reference
 // (lidargen/models/unets/ops.py:32-49,149-173; efficient_unet.py:104-115).
 //
-// Design (one CTA = 128 consecutive pixels of R image rows x BN output channels):
-//   * operands are fp16, accumulation fp32 in TMEM: R accumulators of 128 lanes x BN columns.
+// Design: PERSISTENT CTAs (one per SM) loop over output tiles; one tile = 128 consecutive pixels of R image rows x
+// BN output channels.
+//   * operands fp16, accumulation fp32 in TMEM.  Two accumulator sets of R x (128 lanes x BN columns) so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
 //   * precision: NP = 1 -> one fp16 MMA per product (rel. error ~2e-3 through the whole UNet);
-//                NP = 2 -> error-compensated split: a = a_hi + a_lo, w = w_hi + w_lo (all fp16) and
+//                NP = 2 -> error-compensated split a = a_hi + a_lo, w = w_hi + w_lo (all fp16):
 //                a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (3 MMAs, ~2^-22 relative) -- the mode that meets the
 //                reference's 1e-3 fp32 tolerance.  Weights are pre-scaled by a power of two (w_inv undoes it).
-//   * A (activations): for every 32-channel chunk the R+2 halo rows x 130 pixels are staged ONCE into shared
-//     memory in the canonical no-swizzle K-major layout, organised as "slabs" (one 8-channel group of every
-//     pixel of a row, 16 B per pixel).  Because pixels sit at a uniform 16-byte pitch, each of the 9 filter
-//     taps is just a different START ADDRESS of the same slab (dx*16 bytes, dy = other row) -- no im2col
-//     copies, no swizzle.  Circular W padding / zero H padding are folded into the cp.async addressing.
-//   * B (weights): host-prepacked tiles in exactly the shared-memory image, fetched with one cp.async.bulk
-//     (TMA engine) per (chunk, filter row) and tracked with mbarrier transaction bytes.
+//   * A (activations) live in HBM "slab-major": [part][b][h][C/8][w][8] fp16, i.e. for one image row and one
+//     8-channel group all pixels are contiguous at a 16-byte pitch -- which IS the canonical no-swizzle K-major
+//     shared-memory layout of a tcgen05 operand.  For every K chunk the R+2 halo rows are staged ONCE by the TMA
+//     engine (cp.async.bulk, 2 KB per slab + two 16-byte wrap-around halo pixels, zero rows from a zero page) and
+//     each of the 9 filter taps is just a different START ADDRESS of the same slab (dx*16 bytes, dy = other row):
+//     no im2col copies, no 9x re-reads, no swizzle.
+//   * B (weights): host-prepacked tiles in exactly the shared-memory image, one cp.async.bulk per (chunk, filter row).
 //   * warp roles: 0-3 epilogue (TMEM -> regs -> smem transpose -> coalesced fp32 store + residual + per-channel
-//     sum / sum-of-squares for the next GroupNorm), 4-7 A producers (cp.async), 8 B producer (bulk copy),
-//     9 MMA issuer (single thread, tcgen05.mma kind::f16, M=128 N=BN K=16) + TMEM owner.
+//     sum / sum-of-squares for the next GroupNorm), 4 producer (TMA bulk copies, mbarrier tx bytes),
+//     5 MMA issuer (single thread, tcgen05.mma kind::f16, M=128 N=BN K=16) + TMEM owner.
 #include "common.cuh"
 
 namespace b200 {
@@ -35,10 +37,13 @@ struct ConvParams {
     float out_scale;
     float w_inv;  // 1 / (power-of-two scale applied to the packed weights)
     int B, H, W, Cin, Cout, ring;
+    int n_tiles;
 };
 
+__device__ __align__(128) unsigned char g_zero_page[4096];  // source of zero-padding rows / pixels
+
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
-constexpr int CONV_THREADS = 320;
+constexpr int CONV_THREADS = 192;
 
 template <int BN, int R, int TAPS, int NP>
 struct ConvCfg {
@@ -49,24 +54,28 @@ struct ConvCfg {
     static constexpr int NPX = PIX + 2 * HALO;
     static constexpr int SLAB = NPX * 16;  // bytes: one 8-channel group of one staged row
     static constexpr int RA = R + 2 * HALO;
+    static constexpr int NSLAB = NP * RA * KG;
     static constexpr int A_PART = RA * KG * SLAB;
     static constexpr int A_STAGE = NP * A_PART;
-    static constexpr int SA = 2;
     static constexpr int TW = TAPS == 9 ? 3 : 1;  // taps per B stage (one filter row)
     static constexpr int TG = TAPS == 9 ? 3 : 1;  // B stages per chunk
     static constexpr int B_PART = BN * KC * 2;
     static constexpr int B_TAP = NP * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
-    static constexpr int SB = 3;
     static constexpr int EPI = 4 * 32 * 36 * 4;
+    static constexpr int BUDGET = 227 * 1024 - EPI - 256;
+    static constexpr int SB = 4;
+    static constexpr int SA = (BUDGET - SB * B_STAGE) / A_STAGE >= 4 ? 4 : ((BUDGET - SB * B_STAGE) / A_STAGE >= 3 ? 3 : 2);
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI;
-    static constexpr int SMEM = OFF_BAR + 128;
-    static constexpr int TMEM_COLS = R * BN;
+    static constexpr int SMEM = OFF_BAR + 256;
+    static constexpr int ACC_COLS = R * BN;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(SLAB <= 4096, "zero page too small");
 };
 
 template <int BN, int R, int TAPS, int NP>
@@ -76,188 +85,227 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + C::OFF_BAR;
-    const uint32_t acc_full = bar0 + 80;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 96);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 192);
 #define FULL_A(s) (bar0 + 8u * (s))
-#define EMPTY_A(s) (bar0 + 16u + 8u * (s))
-#define FULL_B(s) (bar0 + 32u + 8u * (s))
-#define EMPTY_B(s) (bar0 + 56u + 8u * (s))
+#define EMPTY_A(s) (bar0 + 32u + 8u * (s))
+#define FULL_B(s) (bar0 + 64u + 8u * (s))
+#define EMPTY_B(s) (bar0 + 96u + 8u * (s))
+#define ACC_FULL(s) (bar0 + 128u + 8u * (s))
+#define ACC_EMPTY(s) (bar0 + 144u + 8u * (s))
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = p.Cout / BN;
-    const int b = blockIdx.z / ntiles, nt = blockIdx.z % ntiles;
-    const int w0 = blockIdx.x * PIX, h0 = blockIdx.y * R, n0 = nt * BN;
+    const int NT = p.Cout / BN, WT = p.W / PIX, HG = p.H / R;
     const int NCH = p.Cin / KC;
+    const int CG = p.Cin / 8;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::SA; ++s) {
-            mbar_init(FULL_A(s), 128);
+            mbar_init(FULL_A(s), 1);
             mbar_init(EMPTY_A(s), 1);
         }
         for (int s = 0; s < C::SB; ++s) {
             mbar_init(FULL_B(s), 1);
             mbar_init(EMPTY_B(s), 1);
         }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(ACC_FULL(s), 1);
+            mbar_init(ACC_EMPTY(s), 128);
+        }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
-        // ------------------------------ A producers: 128 threads, cp.async 16 B pieces ------------------------------
-        const int t = threadIdx.x - 128;
-        for (int c = 0; c < NCH; ++c) {
-            const int s = c % C::SA;
-            const uint32_t ph = (c / C::SA) & 1;
-            mbar_wait(EMPTY_A(s), ph ^ 1);
-            const uint32_t dst0 = sbase + C::OFF_A + s * C::A_STAGE;
-            const __half* src_c = p.a + (size_t)c * KC;
-            const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
-            for (int i = t; i < NP * C::RA * C::NPX * C::KG; i += 128) {
-                const int j = i % C::KG;
-                const int q = i / C::KG;
-                const int r2 = q / C::NPX;  // part * RA + row
-                const int px = q - r2 * C::NPX;
-                const int part = r2 / C::RA;
-                const int r = r2 - part * C::RA;
-                const int gh = h0 + r - C::HALO;
-                int gw = w0 + px - C::HALO;
-                bool ok = (gh >= 0) && (gh < p.H);
-                if (gw < 0) {
-                    if (p.ring) gw += p.W; else ok = false;
-                } else if (gw >= p.W) {
-                    if (p.ring) gw -= p.W; else ok = false;
-                }
-                const __half* src =
-                    ok ? src_c + part * part_elems + ((size_t)(b * p.H + gh) * p.W + gw) * p.Cin + j * 8 : p.a;
-                cp_async_16(dst0 + (r2 * C::KG + j) * C::SLAB + px * 16, src, ok ? 16u : 0u);
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
-            fence_proxy_async();
-            mbar_arrive(FULL_A(s));
-        }
-    } else if (warp == 8) {
-        // ------------------------------ B producer: one thread, TMA-engine bulk copies ------------------------------
-        if (lane == 0) {
+    if (warp == 4) {
+        // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
+        uint32_t ia = 0, ib = 0;
+        const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int nt = t % NT; t /= NT;
+            const int wt = t % WT; t /= WT;
+            const int hg = t % HG;
+            const int b = t / HG;
+            const int w0 = wt * PIX, h0 = hg * R;
             const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (NP * BN * KC);
-            const int nq = NCH * C::TG;
-            for (int q = 0; q < nq; ++q) {
-                const int s = q % C::SB;
-                const uint32_t ph = (q / C::SB) & 1;
-                mbar_wait(EMPTY_B(s), ph ^ 1);
-                mbar_expect_tx(FULL_B(s), C::B_STAGE);
-                bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE, wsrc + (size_t)q * (C::B_STAGE / 2), C::B_STAGE,
-                              FULL_B(s));
-            }
-        }
-    } else if (warp == 9) {
-        // ------------------------------ MMA issuer: one thread ------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(128, BN);
-            int qb = 0;
             for (int c = 0; c < NCH; ++c) {
-                const int sa = c % C::SA;
-                mbar_wait(FULL_A(sa), (c / C::SA) & 1);
-                const uint32_t a_stage = sbase + C::OFF_A + sa * C::A_STAGE;
-                for (int dy = 0; dy < C::TG; ++dy, ++qb) {
-                    const int sb = qb % C::SB;
-                    mbar_wait(FULL_B(sb), (qb / C::SB) & 1);
-                    tc_fence_after();
-                    const uint32_t b_stage = sbase + C::OFF_B + sb * C::B_STAGE;
-#pragma unroll
-                    for (int dx = 0; dx < C::TW; ++dx) {
-#pragma unroll
-                        for (int o = 0; o < R; ++o) {
-                            const int ri = o + dy;  // staged input row feeding output row o through filter row dy
-#pragma unroll
-                            for (int ks = 0; ks < C::KS; ++ks) {
-                                const uint32_t a_addr = a_stage + (ri * C::KG + ks * 2) * C::SLAB + dx * 16;
-                                const uint32_t b_addr = b_stage + dx * C::B_TAP + ks * 2 * (BN * 16);
-                                const uint64_t a_hi = make_smem_desc(a_addr, C::SLAB, 128);
-                                const uint64_t b_hi = make_smem_desc(b_addr, BN * 16, 128);
-                                tc_mma_f16(tmem_base + o * BN, a_hi, b_hi, idesc, (uint32_t)((c | dy | dx | ks) != 0));
-                                if (NP == 2) {
-                                    const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
-                                    const uint64_t b_lo = make_smem_desc(b_addr + C::B_PART, BN * 16, 128);
-                                    tc_mma_f16(tmem_base + o * BN, a_lo, b_hi, idesc, 1u);
-                                    tc_mma_f16(tmem_base + o * BN, a_hi, b_lo, idesc, 1u);
-                                }
+                {
+                    const int s = ia % C::SA;
+                    const uint32_t ph = (ia / C::SA) & 1;
+                    if (lane == 0) {
+                        mbar_wait(EMPTY_A(s), ph ^ 1);
+                        mbar_expect_tx(FULL_A(s), C::A_STAGE);
+                    }
+                    __syncwarp();
+                    const uint32_t dst0 = sbase + C::OFF_A + s * C::A_STAGE;
+                    for (int sl = lane; sl < C::NSLAB; sl += 32) {
+                        const int j = sl % C::KG;
+                        const int r2 = sl / C::KG;  // part * RA + row
+                        const int part = r2 / C::RA;
+                        const int r = r2 - part * C::RA;
+                        const int gh = h0 + r - C::HALO;
+                        const uint32_t dst = dst0 + sl * C::SLAB;
+                        if (gh < 0 || gh >= p.H) {
+                            bulk_copy_g2s(dst, g_zero_page, C::SLAB, FULL_A(s));
+                        } else {
+                            const __half* row = p.a + part * part_elems +
+                                                (((size_t)(b * p.H + gh) * CG + (size_t)c * C::KG + j) * p.W) * 8;
+                            bulk_copy_g2s(dst + C::HALO * 16, row + (size_t)w0 * 8, PIX * 16, FULL_A(s));
+                            if (C::HALO) {
+                                int wl = w0 - 1, wr = w0 + PIX;
+                                if (wl < 0) wl = p.ring ? p.W - 1 : -1;
+                                if (wr >= p.W) wr = p.ring ? 0 : -1;
+                                bulk_copy_g2s(dst, wl >= 0 ? (const void*)(row + (size_t)wl * 8) : (const void*)g_zero_page,
+                                              16, FULL_A(s));
+                                bulk_copy_g2s(dst + (PIX + 1) * 16,
+                                              wr >= 0 ? (const void*)(row + (size_t)wr * 8) : (const void*)g_zero_page, 16,
+                                              FULL_A(s));
                             }
                         }
                     }
-                    tc_commit(EMPTY_B(sb));  // weights slot free once these MMAs retire
+                    ++ia;
                 }
-                tc_commit(EMPTY_A(sa));
+                if (lane == 0) {
+                    for (int dy = 0; dy < C::TG; ++dy, ++ib) {
+                        const int s = ib % C::SB;
+                        const uint32_t ph = (ib / C::SB) & 1;
+                        mbar_wait(EMPTY_B(s), ph ^ 1);
+                        mbar_expect_tx(FULL_B(s), C::B_STAGE);
+                        bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE,
+                                      wsrc + (size_t)(c * C::TG + dy) * (C::B_STAGE / 2), C::B_STAGE, FULL_B(s));
+                    }
+                }
+                __syncwarp();
             }
-            tc_commit(acc_full);
+        }
+    } else if (warp == 5) {
+        // ------------------------------ MMA issuer: one thread ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            uint32_t ia = 0, ib = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = it & 1;
+                mbar_wait(ACC_EMPTY(buf), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * C::ACC_COLS;
+                for (int c = 0; c < NCH; ++c, ++ia) {
+                    const int sa = ia % C::SA;
+                    mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
+                    const uint32_t a_stage = sbase + C::OFF_A + sa * C::A_STAGE;
+                    for (int dy = 0; dy < C::TG; ++dy, ++ib) {
+                        const int sb = ib % C::SB;
+                        mbar_wait(FULL_B(sb), (ib / C::SB) & 1);
+                        tc_fence_after();
+                        const uint32_t b_stage = sbase + C::OFF_B + sb * C::B_STAGE;
+#pragma unroll
+                        for (int dx = 0; dx < C::TW; ++dx) {
+#pragma unroll
+                            for (int o = 0; o < R; ++o) {
+                                const int ri = o + dy;  // staged input row feeding output row o through filter row dy
+#pragma unroll
+                                for (int ks = 0; ks < C::KS; ++ks) {
+                                    const uint32_t a_addr = a_stage + (ri * C::KG + ks * 2) * C::SLAB + dx * 16;
+                                    const uint32_t b_addr = b_stage + dx * C::B_TAP + ks * 2 * (BN * 16);
+                                    const uint64_t a_hi = make_smem_desc(a_addr, C::SLAB, 128);
+                                    const uint64_t b_hi = make_smem_desc(b_addr, BN * 16, 128);
+                                    tc_mma_f16(acc + o * BN, a_hi, b_hi, idesc, (uint32_t)((c | dy | dx | ks) != 0));
+                                    if (NP == 2) {
+                                        const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
+                                        const uint64_t b_lo = make_smem_desc(b_addr + C::B_PART, BN * 16, 128);
+                                        tc_mma_f16(acc + o * BN, a_lo, b_hi, idesc, 1u);
+                                        tc_mma_f16(acc + o * BN, a_hi, b_lo, idesc, 1u);
+                                    }
+                                }
+                            }
+                        }
+                        tc_commit(EMPTY_B(sb));  // weights slot free once these MMAs retire
+                    }
+                    tc_commit(EMPTY_A(sa));
+                }
+                tc_commit(ACC_FULL(buf));
+            }
         }
     } else {
         // ------------------------------ epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ------------------------------
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
         float* stg = reinterpret_cast<float*>(smem + C::OFF_EPI) + warp * (32 * 36);
         const int col4 = lane & 7, rb = lane >> 3;
         const float scale = p.out_scale, winv = p.w_inv;
-        for (int o = 0; o < R; ++o) {
-            const int h = h0 + o;
-            const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + warp * 32) * p.Cout;
-            for (int sl = 0; sl < BN / 32; ++sl) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + o * BN + sl * 32, v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                const int nb = n0 + sl * 32 + col4 * 4;
-                const float4 bi = p.bias ? *reinterpret_cast<const float4*>(p.bias + nb) : make_float4(0, 0, 0, 0);
-                float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = rb + 4 * i;
-                    float4 tv = *reinterpret_cast<const float4*>(stg + row * 36 + col4 * 4);
-                    const size_t gi = row_base + (size_t)row * p.Cout + nb;
-                    tv.x = fmaf(tv.x, winv, bi.x); tv.y = fmaf(tv.y, winv, bi.y);
-                    tv.z = fmaf(tv.z, winv, bi.z); tv.w = fmaf(tv.w, winv, bi.w);
-                    if (p.res) {
-                        const float4 rv = *reinterpret_cast<const float4*>(p.res + gi);
-                        tv.x += rv.x; tv.y += rv.y; tv.z += rv.z; tv.w += rv.w;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            int t = tile;
+            const int nt = t % NT; t /= NT;
+            const int wt = t % WT; t /= WT;
+            const int hg = t % HG;
+            const int b = t / HG;
+            const int w0 = wt * PIX, h0 = hg * R, n0 = nt * BN;
+            const uint32_t buf = it & 1;
+            mbar_wait(ACC_FULL(buf), (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
+            for (int o = 0; o < R; ++o) {
+                const int h = h0 + o;
+                const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + warp * 32) * p.Cout;
+                for (int sl = 0; sl < BN / 32; ++sl) {
+                    float v[32];
+                    tmem_ld_32x32(acc + o * BN + sl * 32, v);
+                    if (o == R - 1 && sl == BN / 32 - 1) {
+                        // all TMEM reads of this accumulator set are done -> hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(ACC_EMPTY(buf));
                     }
-                    tv.x *= scale; tv.y *= scale; tv.z *= scale; tv.w *= scale;
-                    *reinterpret_cast<float4*>(p.out + gi) = tv;
-                    s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
-                    s2[0] += tv.x * tv.x; s2[1] += tv.y * tv.y; s2[2] += tv.z * tv.z; s2[3] += tv.w * tv.w;
-                }
-                if (p.stats) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
-                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
-                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const int nb = n0 + sl * 32 + col4 * 4;
+                    const float4 bi = p.bias ? *reinterpret_cast<const float4*>(p.bias + nb) : make_float4(0, 0, 0, 0);
+                    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = rb + 4 * i;
+                        float4 tv = *reinterpret_cast<const float4*>(stg + row * 36 + col4 * 4);
+                        const size_t gi = row_base + (size_t)row * p.Cout + nb;
+                        tv.x = fmaf(tv.x, winv, bi.x); tv.y = fmaf(tv.y, winv, bi.y);
+                        tv.z = fmaf(tv.z, winv, bi.z); tv.w = fmaf(tv.w, winv, bi.w);
+                        if (p.res) {
+                            const float4 rv = *reinterpret_cast<const float4*>(p.res + gi);
+                            tv.x += rv.x; tv.y += rv.y; tv.z += rv.z; tv.w += rv.w;
+                        }
+                        tv.x *= scale; tv.y *= scale; tv.z *= scale; tv.w *= scale;
+                        *reinterpret_cast<float4*>(p.out + gi) = tv;
+                        s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
+                        s2[0] += tv.x * tv.x; s2[1] += tv.y * tv.y; s2[2] += tv.z * tv.z; s2[3] += tv.w * tv.w;
                     }
-                    if (rb == 0) {
-                        double* st = p.stats + ((size_t)b * p.Cout + nb) * 2;
+                    if (p.stats) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            atomicAdd(st + 2 * e, (double)s1[e]);
-                            atomicAdd(st + 2 * e + 1, (double)s2[e]);
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+                        }
+                        if (rb == 0) {
+                            double* st = p.stats + ((size_t)b * p.Cout + nb) * 2;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                atomicAdd(st + 2 * e, (double)s1[e]);
+                                atomicAdd(st + 2 * e + 1, (double)s2[e]);
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 5) {
         __syncwarp();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
@@ -265,22 +313,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 #undef EMPTY_A
 #undef FULL_B
 #undef EMPTY_B
+#undef ACC_FULL
+#undef ACC_EMPTY
 }
 
 template <int BN, int R, int TAPS, int NP>
-static int launch_conv(const ConvParams& p, cudaStream_t st) {
+static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     using C = ConvCfg<BN, R, TAPS, NP>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, R, TAPS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, R, TAPS, NP>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             set_error("conv_tc: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM, cudaGetErrorString(e));
             return B200_E_CUDA;
         }
         attr_set = true;
     }
-    dim3 grid(p.W / PIX, p.H / R, p.B * (p.Cout / BN));
+    p.n_tiles = (p.W / PIX) * (p.H / R) * p.B * (p.Cout / BN);
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     conv_tc_kernel<BN, R, TAPS, NP><<<grid, CONV_THREADS, C::SMEM, st>>>(p);
     B200_CHECK_LAUNCH();
     return B200_OK;
@@ -363,15 +414,17 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
         bool ok = valid && gh >= 0 && gh < p.H;
         if (gw < 0) { if (p.ring) gw += p.W; else ok = false; }
         else if (gw >= p.W) { if (p.ring) gw -= p.W; else ok = false; }
-        const __half* ap = p.a + ((size_t)(b * p.H + gh) * p.W + gw) * p.Cin;
+        // slab-major operand: [part][b][h][C/8][w][8]
+        const __half* ap = p.a + (((size_t)(b * p.H + gh) * (p.Cin / 8)) * p.W + gw) * 8;
         const __half* wp = p.w + ((size_t)tap * p.Cout + co0) * p.Cin;
         for (int k = 0; k < p.Cin; k += 8) {
             float av[8];
             if (ok) {
-                load8h(ap + k, av);
+                const __half* apk = ap + (size_t)(k / 8) * p.W * 8;
+                load8h(apk, av);
                 if (parts == 2) {
                     float lo[8];
-                    load8h(ap + a_part + k, lo);
+                    load8h(apk + a_part, lo);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) av[e] += lo[e];
                 }
@@ -461,25 +514,30 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(parts == 1 || parts == 2);
     B200_CHECK_ARG(W % PIX == 0 && Cin % 32 == 0 && Cin >= 32);
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
-    B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
-    B200_CHECK_ARG((long long)B * (Cout / bn) <= 65535 && H / rows <= 65535);
+    B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0 && rows * bn <= 256);
     ConvParams p{(const __half*)a, (const __half*)wpacked, bias, res, out, stats, out_scale, w_inv,
-                 B, H, W, Cin, Cout, ring};
+                 B, H, W, Cin, Cout, ring, 0};
     cudaStream_t st = (cudaStream_t)stream;
-#define B200_CONV_CASE(BN_, R_)                                                                      \
-    if (bn == BN_ && rows == R_) {                                                                   \
-        if (parts == 2)                                                                              \
-            return taps == 9 ? launch_conv<BN_, R_, 9, 2>(p, st) : launch_conv<BN_, R_, 1, 2>(p, st); \
-        return taps == 9 ? launch_conv<BN_, R_, 9, 1>(p, st) : launch_conv<BN_, R_, 1, 1>(p, st);     \
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+#define B200_CONV_CASE(BN_, R_)                                                                                        \
+    if (bn == BN_ && rows == R_) {                                                                                     \
+        if (parts == 2)                                                                                                \
+            return taps == 9 ? launch_conv<BN_, R_, 9, 2>(p, num_sms, st) : launch_conv<BN_, R_, 1, 2>(p, num_sms, st); \
+        return taps == 9 ? launch_conv<BN_, R_, 9, 1>(p, num_sms, st) : launch_conv<BN_, R_, 1, 1>(p, num_sms, st);     \
     }
     B200_CONV_CASE(64, 1)
     B200_CONV_CASE(64, 2)
     B200_CONV_CASE(64, 4)
     B200_CONV_CASE(128, 1)
     B200_CONV_CASE(128, 2)
-    B200_CONV_CASE(128, 4)
 #undef B200_CONV_CASE
-    set_error("conv_tc: unsupported tile bn=%d rows=%d", bn, rows);
+    set_error("conv_tc: unsupported tile bn=%d rows=%d (need rows*bn <= 256)", bn, rows);
     return B200_E_ARG;
 }
 
@@ -492,7 +550,7 @@ extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias,
     B200_CHECK_ARG(Cin % 8 == 0 && Cout % 32 == 0);
     B200_CHECK_ARG(!stats || (H * W) % 32 == 0);
     ConvParams p{(const __half*)a, (const __half*)w16, bias, res, out, stats, out_scale, w_inv,
-                 B, H, W, Cin, Cout, ring};
+                 B, H, W, Cin, Cout, ring, 0};
     const long long npix = (long long)B * H * W;
     dim3 grid((unsigned)((npix + 31) / 32), Cout / 32);
     conv_ffma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, taps, parts);

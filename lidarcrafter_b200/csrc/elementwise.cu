@@ -18,14 +18,16 @@ void set_error(const char* fmt, ...) {
 // GroupNorm apply (+AdaGN) + SiLU -> fp16, optional concat of two sources
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GN_MAX_C = 2048;
-constexpr int GN_PIX_PER_BLOCK = 32;
 
+// output layout ("slab-major", the tcgen05 no-swizzle K-major operand image of one image row):
+//   y[part][b][h][C/8][w][8]  -- for a fixed (row, 8-channel group) all pixels are contiguous at a 16 B pitch
 __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                      int C1, const double* __restrict__ st0,
                                                      const double* __restrict__ st1, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const float* __restrict__ ada,
                                                      int ada_stride, int groups, float eps, int silu,
-                                                     __half* __restrict__ y, size_t lo_off, int HW) {
+                                                     __half* __restrict__ y, size_t lo_off, int HW, int W,
+                                                     int pix_per_block) {
     __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
     __shared__ float s_mean[64], s_rstd[64];
     const int C = C0 + C1;
@@ -66,12 +68,14 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
     }
     __syncthreads();
     const int c8n = C / 8;
-    const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-    const int np = min(GN_PIX_PER_BLOCK, HW - p0);
+    const int p0 = blockIdx.x * pix_per_block;
+    const int np = min(pix_per_block, HW - p0);
+    // consecutive threads -> consecutive pixels of one 8-channel group: 512 B contiguous stores per warp
     for (int i = threadIdx.x; i < np * c8n; i += blockDim.x) {
-        const int pp = i / c8n, c8 = i - pp * c8n;
+        const int c8 = i / np, pp = i - c8 * np;
         const int c = c8 * 8;
-        const size_t pix = (size_t)b * HW + p0 + pp;
+        const int pl = p0 + pp;
+        const size_t pix = (size_t)b * HW + pl;
         const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
         const float4 v0 = *reinterpret_cast<const float4*>(src);
         const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
@@ -85,7 +89,9 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-        *reinterpret_cast<uint4*>(y + pix * C + c) = *reinterpret_cast<const uint4*>(h);
+        const int hh = pl / W, ww = pl - hh * W;
+        const size_t oi = ((((size_t)b * (HW / W) + hh) * c8n + c8) * W + ww) * 8;
+        *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
         if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
             __half2 l[4];
 #pragma unroll
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                 const float2 hf = __half22float2(h[e]);
                 l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
             }
-            *reinterpret_cast<uint4*>(y + lo_off + pix * C + c) = *reinterpret_cast<const uint4*>(l);
+            *reinterpret_cast<uint4*>(y + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
         }
     }
 }
@@ -456,9 +462,10 @@ static bool c4_ok(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) ==
 
 extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                                const double* stats1, const float* gamma, const float* beta, const float* ada,
-                               int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int HW,
+                               int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
                                void* stream) {
     B200_CHECK_ARG(parts == 1 || parts == 2);
+    const int HW = H * W;
     B200_CHECK_ARG(x0 && y && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && (C1 == 0 || x1));
     const int C = C0 + C1;
     B200_CHECK_ARG(C <= GN_MAX_C);
@@ -469,10 +476,13 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     } else {
         B200_CHECK_ARG(!gamma && !ada);
     }
-    dim3 grid(cdiv(HW, GN_PIX_PER_BLOCK), B);
+    // pixels per block: large enough to amortise the per-block coefficient prologue, small enough to fill the GPU
+    int ppb = 256;
+    while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
+    dim3 grid(cdiv(HW, ppb), B);
     gn_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
                                                           groups, eps, silu, (__half*)y,
-                                                          parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW);
+                                                          parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW, W, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

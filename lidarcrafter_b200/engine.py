@@ -38,7 +38,7 @@ def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, sms: int = NUM_SMS):
         if Cout % bn:
             continue
         for rows in (4, 2, 1):
-            if H % rows or rows * bn > 512:
+            if H % rows or rows * bn > 256:
                 continue
             tiles = B * (H // rows) * (W // 128) * (Cout // bn)
             waves = math.ceil(tiles / sms)
@@ -218,7 +218,7 @@ class PlanBuilder:
         ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * ada_off
         self.p.add(self.lib.gn_act_f16, _ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0,
                    _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b),
-                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, HW,
+                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, a0.H, a0.W,
                    name="gn_act_f16", nbytes=self.B * HW * C * (4.0 + 2.0 * self.p.parts))
         return y
 

@@ -45,6 +45,18 @@ def i32(ptr, *shape):
     return None if t is None else t.view(*shape)
 
 
+def to_slab(x):
+    """[..., H, W, C] -> slab-major [..., H, C/8, W, 8] (the conv operand layout)"""
+    *lead, H, W, C = x.shape
+    return x.reshape(*lead, H, W, C // 8, 8).transpose(-3, -2).contiguous()
+
+
+def from_slab(x):
+    """slab-major [..., H, C/8, W, 8] -> [..., H, W, C]"""
+    *lead, H, G, W, E = x.shape
+    return x.transpose(-3, -2).reshape(*lead, H, W, G * E)
+
+
 def _ring_pad(x, pad, ring):
     if pad == 0:
         return x
@@ -86,7 +98,7 @@ class EmulatedLib:
 
     def _conv(self, a, W4, bias, res, scale, w_inv, out, stats, B, H, Wd, Cin, Cout, taps, ring, parts):
         k = 3 if taps == 9 else 1
-        x = f16(a, parts, B, H, Wd, Cin).float().sum(0).permute(0, 3, 1, 2)
+        x = from_slab(f16(a, parts, B, H, Cin // 8, Wd, 8)).float().sum(0).permute(0, 3, 1, 2)
         y = F.conv2d(_ring_pad(x, k // 2, ring), W4.float()) * w_inv
         y = y.permute(0, 2, 3, 1)
         if bias:
@@ -103,7 +115,7 @@ class EmulatedLib:
     def conv_tc(self, a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
                 parts, stream):
         self._rec("conv_tc")
-        assert W % 128 == 0 and Cin % KC == 0 and Cout % bn == 0 and H % rows == 0 and rows * bn <= 512
+        assert W % 128 == 0 and Cin % KC == 0 and Cout % bn == 0 and H % rows == 0 and rows * bn <= 256
         k = 3 if taps == 9 else 1
         kc = 16 if parts == 2 else 32
         t = f16(wpacked, Cout // bn, Cin // kc, taps, parts, kc // 8, bn, 8).float().sum(3)
@@ -119,9 +131,10 @@ class EmulatedLib:
         return 0
 
     # ---- GN / stats ----
-    def gn_act_f16(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, y, parts, B, HW,
+    def gn_act_f16(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, y, parts, B, H, W,
                    stream):
         self._rec("gn_act_f16")
+        HW = H * W
         x = f32(x0, B, HW, C0)
         if C1:
             x = torch.cat([x, f32(x1, B, HW, C1)], dim=-1)
@@ -152,7 +165,7 @@ class EmulatedLib:
             x = x * a[:, None, :] + b[:, None, :]
         if silu:
             x = F.silu(x)
-        f16(y, parts, B, HW, C).copy_(self._split(x, parts))
+        f16(y, parts, B, H, C // 8, W, 8).copy_(to_slab(self._split(x, parts).view(parts, B, H, W, C)))
         return 0
 
     def channel_stats(self, x, stats, B, HW, C, stream):
@@ -217,15 +230,17 @@ class EmulatedLib:
         f32(pred, B, Cout, H, W).copy_(y)
         return 0
 
-    def attention(self, q, ldq, qoff, k, ldk, koff, v, ldv, voff, out, ldo, parts, B, heads, Tq, Tk, dqk, dv, scale,
-                  stream):
+    def attention(self, q, ldq, qoff, k, ldk, koff, v, ldv, voff, out, ldo, out_w, parts, B, heads, Tq, Tk, dqk, dv,
+                  scale, stream):
         self._rec("attention")
         Q = f32(q, B, Tq, ldq)[:, :, qoff:qoff + heads * dqk].reshape(B, Tq, heads, dqk).transpose(1, 2)
         K = f32(k, B, Tk, ldk)[:, :, koff:koff + heads * dqk].reshape(B, Tk, heads, dqk).transpose(1, 2)
         V = f32(v, B, Tk, ldv)[:, :, voff:voff + heads * dv].reshape(B, Tk, heads, dv).transpose(1, 2)
         att = torch.softmax(Q @ K.transpose(-1, -2) * scale, dim=-1)
         o = (att @ V).transpose(1, 2).reshape(B, Tq, heads * dv)
-        f16(out, parts, B, Tq, ldo)[:, :, :, :heads * dv].copy_(self._split(o, parts))
+        assert ldo == heads * dv
+        f16(out, parts, B, Tq // out_w, ldo // 8, out_w, 8).copy_(
+            to_slab(self._split(o, parts).view(parts, B, Tq // out_w, out_w, ldo)))
         return 0
 
     def sampler_update(self, x_t, pred, noise, coef, x_s, B, n, mode, objective, clip, stream):

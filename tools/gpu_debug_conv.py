@@ -20,11 +20,21 @@ CASES = [
     dict(taps=1, Cin=256, Cout=128, bn=128, rows=1, parts=1, B=1, H=2, W=128),
     dict(taps=9, Cin=32, Cout=64, bn=64, rows=1, parts=1, B=1, H=3, W=128),
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=1, B=1, H=4, W=256),
-    dict(taps=9, Cin=64, Cout=128, bn=128, rows=4, parts=1, B=2, H=8, W=256),
+    dict(taps=9, Cin=64, Cout=128, bn=128, rows=2, parts=1, B=2, H=8, W=256),
     dict(taps=1, Cin=32, Cout=64, bn=64, rows=1, parts=2, B=1, H=1, W=128),
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=2, B=1, H=4, W=256),
     dict(taps=9, Cin=128, Cout=128, bn=128, rows=2, parts=2, B=2, H=4, W=128),
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=2, B=8, H=32, W=1024),
+    dict(taps=9, Cin=64, Cout=64, bn=64, rows=2, parts=2, B=8, H=32, W=1024),
+    dict(taps=9, Cin=128, Cout=128, bn=128, rows=2, parts=2, B=8, H=16, W=512),
+    dict(taps=9, Cin=128, Cout=128, bn=64, rows=4, parts=2, B=8, H=16, W=512),
+    dict(taps=9, Cin=256, Cout=256, bn=128, rows=2, parts=2, B=8, H=8, W=256),
+    dict(taps=9, Cin=256, Cout=256, bn=128, rows=1, parts=2, B=8, H=8, W=256),
+    dict(taps=9, Cin=512, Cout=512, bn=128, rows=1, parts=2, B=8, H=4, W=128),
+    dict(taps=9, Cin=512, Cout=512, bn=128, rows=2, parts=2, B=8, H=4, W=128),
+    dict(taps=9, Cin=512, Cout=512, bn=64, rows=4, parts=2, B=8, H=4, W=128),
+    dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=1, B=8, H=32, W=1024),
+    dict(taps=1, Cin=512, Cout=1536, bn=128, rows=2, parts=2, B=8, H=4, W=128),
 ]
 
 
@@ -41,7 +51,8 @@ def run_case(c):
     w = (torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * taps)).contiguous()
     x = torch.randn(B, H, W, Cin, device=dev)
     hi = x.half()
-    a = torch.stack([hi, (x - hi.float()).half()])[:parts].contiguous()
+    a_nhwc = torch.stack([hi, (x - hi.float()).half()])[:parts].contiguous()
+    a = a_nhwc.reshape(parts, B, H, W, Cin // 8, 8).transpose(-3, -2).contiguous()   # slab-major operand
     wscale = 2.0 ** (8 - math.floor(math.log2(float(w.abs().max()))))
     wp = torch.zeros(Cout * Cin * taps * parts, dtype=torch.float16, device=dev)
     out = torch.full((B, H, W, Cout), float("nan"), device=dev)
@@ -55,7 +66,7 @@ def run_case(c):
     ws = w * wscale
     whi = ws.half()
     wq = (whi.double() + ((ws - whi.float()).half().double() if parts == 2 else 0)) / wscale
-    xq = a.double().sum(0).permute(0, 3, 1, 2)
+    xq = a_nhwc.double().sum(0).permute(0, 3, 1, 2)
     xp = F.pad(F.pad(xq, (k // 2, k // 2, 0, 0), mode="circular"), (0, 0, k // 2, k // 2)) if k == 3 else xq
     ref = F.conv2d(xp, wq).permute(0, 2, 3, 1)
     err = (out.double() - ref)
