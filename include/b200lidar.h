@@ -79,6 +79,10 @@ int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const doub
                     const double* stats1, const float* gamma, const float* beta, const float* ada,
                     int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
                     void* stream);
+/* fp32 NHWC variant y = act(GroupNorm(x)) (no concat / AdaGN): feeds the FIR resampler of the up/down
+ * ResBlocks (layout_unet_v1.py:229-235) and the final `out` head (layout_unet_v1.py:899-900)        */
+int b200_gn_act_f32(const float* x, const double* stats, const float* gamma, const float* beta, int groups,
+                    float eps, int silu, float* y, int B, int HW, int C, void* stream);
 /* per-(b,c) {sum,sumsq} of an fp32 NHWC tensor, accumulated (+=) into stats fp64 [B,C,2] */
 int b200_channel_stats(const float* x, double* stats, int B, int HW, int C, void* stream);
 
@@ -120,6 +124,16 @@ int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias
 int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
                    int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq,
                    int Tk, int dqk, int dv, float scale, void* stream);
+
+/* ObjectAwareCrossAttention core (models/unets/layout_unet_v1.py:416-505, norm_first=False, scale 1.0):
+ *   qkv fp32 [B,T,3C] (q|k|v of qkv_projector, head-major), pos_p fp32 [B,T,C] (normalised image-patch
+ *   positional embedding), kl / pos_l / vl fp32 [B,L2,C] (layout key content, positional, value);
+ *   per head (d = C/heads = 32): q = [q_c;pos_p], k = [[k_c;pos_p] | [k_l;pos_l]], v = [v_c | v_l];
+ *   scale2 = 1/sqrt(2d) (the reference multiplies q and k each by (2d)^-1/4).
+ *   out fp16 slab-major conv operand [parts][B][T/out_w][C/8][out_w][8]                              */
+int b200_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
+                      const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
+                      int L2, float scale2, void* stream);
 
 /* ---- K5: sampler update --------------------------------------------------------------------------
  * replaces p_step's ~25 elementwise ops (diffusion/continuous_time.py:205-231).

@@ -5,9 +5,13 @@ Host side mirrors the reference interfaces (string registries, ctor kwargs, stat
 """
 from ._lib import B200LidarError, LIB_PATH, get_lib, require_b200  # noqa: F401
 from .efficient_unet import EfficientUNet  # noqa: F401
-from .diffusion import ContinuousTimeGaussianDiffusion, GaussianDiffusion  # noqa: F401
+from .layout_unet_v1 import LayoutUnetV1  # noqa: F401
+from .layout_encoder import LayoutTransformerEncoder  # noqa: F401
+from .diffusion import (ContinuousTimeGaussianDiffusion, CondContinuousTimeGaussianDiffusion,  # noqa: F401
+                        GaussianDiffusion)
 from .lidar import LiDARUtility, get_linear_ray_angles  # noqa: F401
 from . import unets  # noqa: F401
 
-__all__ = ["EfficientUNet", "ContinuousTimeGaussianDiffusion", "GaussianDiffusion", "LiDARUtility",
+__all__ = ["EfficientUNet", "LayoutUnetV1", "LayoutTransformerEncoder", "ContinuousTimeGaussianDiffusion",
+           "CondContinuousTimeGaussianDiffusion", "GaussianDiffusion", "LiDARUtility",
            "get_linear_ray_angles", "unets", "get_lib", "require_b200", "B200LidarError"]

@@ -104,6 +104,54 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
     }
 }
 
+// fp32 NHWC variant: y = act(GN(x)) kept in fp32 (input of the FIR resampler in up/down ResBlocks,
+// layout_unet_v1.py:229-235, and of the final out conv).  Same coefficient prologue as gn_act_kernel.
+__global__ void __launch_bounds__(256) gn_act_f32_kernel(const float* __restrict__ x, int C,
+                                                         const double* __restrict__ st, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int groups, float eps, int silu,
+                                                         float* __restrict__ y, double* __restrict__ stats_out, int HW,
+                                                         int pix_per_block) {
+    __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.y;
+    const int cpg = C / groups;
+    if (threadIdx.x < groups) {
+        double s = 0.0, ss = 0.0;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+            const double* p = st + ((size_t)b * C + c) * 2;
+            s += p[0];
+            ss += p[1];
+        }
+        const double n = (double)HW * cpg;
+        const double mean = s / n;
+        double var = ss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float a = s_rstd[g], bb = -s_mean[g] * s_rstd[g];
+        if (gamma) { a *= gamma[c]; bb = bb * gamma[c] + beta[c]; }
+        s_a[c] = a;
+        s_b[c] = bb;
+    }
+    __syncthreads();
+    const int c4n = C / 4;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int np = min(pix_per_block, HW - p0);
+    for (int i = threadIdx.x; i < np * c4n; i += blockDim.x) {
+        const int pp = i / c4n, c = (i - pp * c4n) * 4;
+        const size_t gi = ((size_t)b * HW + p0 + pp) * C + c;
+        float4 v = *reinterpret_cast<const float4*>(x + gi);
+        v.x = fmaf(v.x, s_a[c], s_b[c]); v.y = fmaf(v.y, s_a[c + 1], s_b[c + 1]);
+        v.z = fmaf(v.z, s_a[c + 2], s_b[c + 2]); v.w = fmaf(v.w, s_a[c + 3], s_b[c + 3]);
+        if (silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+        *reinterpret_cast<float4*>(y + gi) = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // per-(b, c) sum / sum of squares of an NHWC fp32 tensor (C/4 must divide 256 or be a multiple of it)
 // ---------------------------------------------------------------------------------------------------------
@@ -483,6 +531,20 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     gn_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
                                                           groups, eps, silu, (__half*)y,
                                                           parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW, W, ppb);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_gn_act_f32(const float* x, const double* stats, const float* gamma, const float* beta, int groups,
+                               float eps, int silu, float* y, int B, int HW, int C, void* stream) {
+    B200_CHECK_ARG(x && stats && y && C % 4 == 0 && C <= GN_MAX_C);
+    B200_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0);
+    B200_CHECK_ARG((gamma == nullptr) == (beta == nullptr));
+    int ppb = 256;
+    while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
+    dim3 grid(cdiv(HW, ppb), B);
+    gn_act_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, stats, gamma, beta, groups, eps, silu, y, nullptr, HW,
+                                                              ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

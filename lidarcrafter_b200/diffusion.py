@@ -245,10 +245,11 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
 
     p_sample_loop = sample
 
-    def _sample_from(self, x, num_steps, progress, rng, return_all, mode, ddim_eta):
+    def _sample_from(self, x, num_steps, progress, rng, return_all, mode, ddim_eta, plan=None):
         B = x.shape[0]
         dev = x.device
-        plan = self.model.get_plan(B)
+        if plan is None:
+            plan = self.model.get_plan(B)
         entry = self._step_graph(plan, B, mode)
         steps = torch.linspace(1.0, 0.0, num_steps + 1, device=dev)
         # per-step tables (same fp32 torch math as the reference, evaluated once for the whole trajectory)
@@ -282,3 +283,67 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
             if return_all:
                 out.append(plan.x_in.clone())
         return torch.stack(out) if return_all else plan.x_in.clone()
+
+
+class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
+    """diffusion/continuous_time_cond.py:66-281: layout-conditioned sampling (cond_mode='concat').
+
+    ``sample(batch_dict, batch_size, num_steps, ...)`` runs ``condition_model(batch_dict)`` once, folds the condition
+    into the denoiser plan (LayoutUnetPlan.set_condition) and replays the captured step graph."""
+
+    def __init__(self, model: nn.Module, condition_model: nn.Module = None, prediction_type: str = "eps",
+                 loss_type="l2", noise_schedule: str = "cosine", min_snr_loss_weight: bool = True,
+                 min_snr_gamma: float = 5.0, sampling_resolution=None, clip_sample: bool = True,
+                 clip_sample_range: float = 1, image_d: float = None, noise_d_low: float = None,
+                 noise_d_high: float = None, cond_mode: str = "concat", w_loss_weight: float = 1.0):
+        super().__init__(model=model, condition_model=condition_model, prediction_type=prediction_type,
+                         loss_type=loss_type, noise_schedule=noise_schedule, min_snr_loss_weight=min_snr_loss_weight,
+                         min_snr_gamma=min_snr_gamma, sampling_resolution=sampling_resolution,
+                         clip_sample=clip_sample, clip_sample_range=clip_sample_range, image_d=image_d,
+                         noise_d_low=noise_d_low, noise_d_high=noise_d_high)
+        self.cond_mode = cond_mode
+        self.w_loss_weight = w_loss_weight
+        if self.cond_mode == "concat":
+            self.sampling_shape = (self.model.in_channels - condition_model.out_channels, *self.sampling_shape[1:])
+
+    def get_network_condition(self, steps=None, input_dict=None, only_custom_condition=False):
+        other_condition = self.condition_model(input_dict)
+        if only_custom_condition:
+            return dict(other_condition=other_condition)
+        return dict(time_condition=self.log_snr(steps)[:, 0, 0, 0], other_condition=other_condition)
+
+    @torch.inference_mode()
+    def p_step(self, x_t: torch.Tensor, condition_dict: dict, step_t: torch.Tensor, step_s: torch.Tensor, rng=None,
+               mode: Literal["ddpm", "ddim"] = "ddpm", ddim_eta: float = 0.0) -> torch.Tensor:
+        """continuous_time_cond.py:206-253."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        lt, coef = self._coefficients(step_t, step_s, ddim_eta)
+        condition_dict.update(dict(time_condition=lt))
+        other = condition_dict["other_condition"]
+        if self.cond_mode == "concat" and isinstance(other, torch.Tensor):
+            raise NotImplementedError("tensor-valued concat condition: wrap it as {'concat_cond': tensor, ...} "
+                                      "(every nuScenes layout config passes the encoder's dict)")
+        pred = self.model(x_t, condition_dict).contiguous()
+        noise = self.randn_like(x_t, rng=rng).contiguous()
+        x_t = x_t.contiguous()
+        x_s = torch.empty_like(x_t)
+        _lib.get_lib().sampler_update(x_t.data_ptr(), pred.data_ptr(), noise.data_ptr(), coef.data_ptr(), x_s.data_ptr(),
+                                      x_t.shape[0], x_t[0].numel(), 0 if mode == "ddim" else 1, _OBJ[self.objective],
+                                      float(self.clip_sample_range) if self.clip_sample else 0.0,
+                                      _lib.current_stream(x_t.device))
+        return x_s
+
+    @torch.inference_mode()
+    def sample(self, batch_dict: dict, batch_size: int, num_steps: int, progress: bool = True, rng=None,
+               return_all: bool = False, mode: Literal["ddpm", "ddim"] = "ddpm", ddim_eta: float = 0.0):
+        """continuous_time_cond.py:255-281."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        x = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
+        condition_dict = self.get_network_condition(input_dict=batch_dict, only_custom_condition=True)
+        plan = self.model.get_plan(batch_size)
+        plan.set_condition(condition_dict["other_condition"])
+        return self._sample_from(x, num_steps, progress, rng, return_all, mode, ddim_eta, plan=plan)
+
+    p_sample_loop = sample

@@ -317,7 +317,7 @@ def randomize_state_dict(sd: dict, seed: int = 0) -> dict:
             out[k] = v.clone()
             continue
         g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) % (2 ** 31))
-        if "norm" in k and leaf == "weight" and v.dim() == 1:
+        if leaf == "weight" and v.dim() == 1:      # GroupNorm / LayerNorm gamma (any 1-D ``weight``)
             out[k] = 1 + 0.1 * torch.randn(v.shape, generator=g)
         elif "norm" in k and leaf == "bias" and "proj" not in k:
             out[k] = 0.1 * torch.randn(v.shape, generator=g)
@@ -327,3 +327,228 @@ def randomize_state_dict(sd: dict, seed: int = 0) -> dict:
             fan_in = v[0].numel()
             out[k] = torch.randn(v.shape, generator=g) / math.sqrt(fan_in)
     return out
+
+
+# =============================================================================================
+# LayoutUnetV1 + LayoutTransformerEncoder (layout-conditioned denoiser, configs 3 and 5)
+#   reference: lidargen/models/unets/layout_unet_v1.py, layout_encoder.py, nn.py
+# =============================================================================================
+@dataclass
+class LayoutUnetCfg:
+    """ctor kwargs of LayoutUnetV1 that matter for inference (option_nusc_box_layout_v3.py:10-33)."""
+    in_channels: int = 12
+    resolution: tuple = (32, 1024)
+    model_channels: int = 64
+    out_channels: int = 2
+    num_res_blocks: int = 2
+    attention_ds: tuple = (4, 8)
+    encoder_channels: int = 64
+    channel_mult: tuple = (1, 2, 4, 8)
+    num_head_channels: int = 32
+    image_size: int = 32
+    ring: bool = True
+    gn_groups: int = 32
+    gn_eps: float = 1e-5
+
+
+def _gn32(x, w, b, cfg):
+    """nn.py:17-19,104-111 -- GroupNorm(32, C) computed in fp32 (works for [B,C,L] and [B,C,H,W])."""
+    return F.group_norm(x.float(), cfg.gn_groups, w, b, cfg.gn_eps)
+
+
+def _layout_resblock(sd, p, x, emb, cfg, up=False, down=False):
+    """layout_unet_v1.py:143-249 (ResBlock, use_scale_shift_norm=True)."""
+    h = F.silu(_gn32(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"], cfg))
+    if up:
+        h, x = fir_up2(h, cfg.ring), fir_up2(x, cfg.ring)
+    elif down:
+        h, x = fir_down2(h, cfg.ring), fir_down2(x, cfg.ring)
+    h = conv2d_ring(h, sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], cfg.ring)
+    e = F.linear(F.silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"])
+    scale, shift = e.chunk(2, dim=1)
+    h = _gn32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"], cfg)
+    h = h * (1 + scale[:, :, None, None]) + shift[:, :, None, None]
+    h = conv2d_ring(F.silu(h), sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], cfg.ring)
+    if (p + "skip_connection.weight") in sd:
+        x = F.conv2d(x, sd[p + "skip_connection.weight"], sd[p + "skip_connection.bias"])
+    return x + h
+
+
+def _object_aware_attention(sd, p, x, cond, cfg: LayoutUnetCfg):
+    """layout_unet_v1.py:347-532 (norm_first=False, channels_scale_for_positional_embedding=1, no padding mask)."""
+    B, C, H, W = x.shape
+    nh = C // cfg.num_head_channels
+    T = H * W
+    xf = x.reshape(B, C, T)
+    qkv = F.conv1d(_gn32(xf, sd[p + "norm_for_qkv.weight"], sd[p + "norm_for_qkv.bias"], cfg),
+                   sd[p + "qkv_projector.weight"], sd[p + "qkv_projector.bias"])
+    res = cfg.image_size // (cfg.resolution[0] // H)
+    pw, pb = sd[p + "layout_position_embedding_projector.weight"], sd[p + "layout_position_embedding_projector.bias"]
+    pos_p = _gn32(F.conv1d(cond[f"image_patch_bbox_embedding_for_resolution{res}"], pw, pb),
+                  sd[p + "norm_for_image_patch_positional_embedding.weight"],
+                  sd[p + "norm_for_image_patch_positional_embedding.bias"], cfg)
+    pos_l = _gn32(F.conv1d(cond["obj_bbox_embedding"], pw, pb), sd[p + "norm_for_layout_positional_embedding.weight"],
+                  sd[p + "norm_for_layout_positional_embedding.bias"], cfg)
+    content = (cond["xf_out"] + _gn32(cond["obj_class_embedding"], sd[p + "norm_for_obj_class_embedding.weight"],
+                                      sd[p + "norm_for_obj_class_embedding.bias"], cfg)) / 2
+    kl, vl = F.conv1d(content, sd[p + "layout_content_embedding_projector.weight"],
+                      sd[p + "layout_content_embedding_projector.bias"]).split(C, dim=1)
+    L2 = kl.shape[-1]
+    d = C // nh
+
+    def hd(t, n):
+        return t.reshape(B * nh, d, n)
+    q, k, v = [hd(t, T) for t in qkv.split(C, dim=1)]
+    pp, pl = hd(pos_p, T), hd(pos_l, L2)
+    qm = torch.cat([q, pp], 1)
+    km = torch.cat([torch.cat([k, pp], 1), torch.cat([hd(kl, L2), pl], 1)], 2)
+    vm = torch.cat([v, hd(vl, L2)], 2)
+    scale = 1 / math.sqrt(math.sqrt(2 * d))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", qm * scale, km * scale).float(), dim=-1)
+    a = torch.einsum("bts,bcs->bct", w, vm).reshape(B, C, T)
+    h = F.conv1d(a, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+    return (xf + h).reshape(B, C, H, W)
+
+
+def layout_block_list(cfg: LayoutUnetCfg):
+    """Mirror of the constructor's block schedule (layout_unet_v1.py:690-852): returns
+    (input_blocks, output_blocks) as lists of lists of (kind, cin, cout) with kind in
+    {'conv','res','res_down','res_up','attn'}; also the running skip-channel stack."""
+    mc = cfg.model_channels
+    ch = int(cfg.channel_mult[0] * mc)
+    inputs = [[("conv", None, ch)]]
+    chans = [ch]
+    ds = 1
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            layers = [("res", ch, int(mult * mc))]
+            ch = int(mult * mc)
+            if ds in cfg.attention_ds:
+                layers.append(("attn", ch, ch))
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            inputs.append([("res_down", ch, ch)])
+            chans.append(ch)
+            ds *= 2
+    middle = [("res", ch, ch), ("attn", ch, ch), ("res", ch, ch)]
+    outputs = []
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            layers = [("res", ch + ich, int(mc * mult))]
+            ch = int(mc * mult)
+            if ds in cfg.attention_ds:
+                layers.append(("attn", ch, ch))
+            if level and i == cfg.num_res_blocks:
+                layers.append(("res_up", ch, ch))
+                ds //= 2
+            outputs.append(layers)
+    return inputs, middle, outputs
+
+
+def layout_unet_forward(sd: dict, x: torch.Tensor, log_snr: torch.Tensor, cond: dict, cfg: LayoutUnetCfg):
+    """layout_unet_v1.py:866-902.  ``cond`` = output dict of layout_encoder_forward."""
+    B = x.shape[0]
+    e = sinusoidal_embedding(log_snr.float(), cfg.model_channels)
+    e = F.silu(F.linear(e, sd["time_embed.1.weight"], sd["time_embed.1.bias"]))
+    emb = F.linear(e, sd["time_embed.3.weight"], sd["time_embed.3.bias"]) + cond["xf_proj"]
+    h = x
+    if "concat_cond" in cond:
+        h = torch.cat([h, cond["concat_cond"]], dim=1)
+    h = torch.cat([h, fourier_features(sd["coords"], cfg.resolution).repeat_interleave(B, dim=0)], dim=1)
+    inputs, middle, outputs = layout_block_list(cfg)
+
+    def run(layers, prefix, h):
+        for j, (kind, cin, cout) in enumerate(layers):
+            p = f"{prefix}{j}."
+            if kind == "conv":
+                h = conv2d_ring(h, sd[p + "weight"], sd[p + "bias"], cfg.ring)
+            elif kind == "attn":
+                h = _object_aware_attention(sd, p, h, cond, cfg)
+            else:
+                h = _layout_resblock(sd, p, h, emb, cfg, up=kind == "res_up", down=kind == "res_down")
+        return h
+    hs = []
+    for i, layers in enumerate(inputs):
+        h = run(layers, f"input_blocks.{i}.", h)
+        hs.append(h)
+    h = run(middle, "middle_block.", h)
+    for i, layers in enumerate(outputs):
+        h = run(layers, f"output_blocks.{i}.", torch.cat([h, hs.pop()], dim=1))
+    h = F.silu(_gn32(h, sd["out.0.weight"], sd["out.0.bias"], cfg))
+    return conv2d_ring(h, sd["out.2.weight"], sd["out.2.bias"], cfg.ring)
+
+
+def layout_encoder_forward(sd: dict, batch: dict, feature_map_size=(32, 1024), resolutions=(4, 8), heads: int = 4,
+                           layers: int = 6):
+    """layout_encoder.py:237-303 (used_condition_types = obj_class, obj_bbox, is_valid_obj; no positional
+    embedding; final LayerNorm; no key padding mask)."""
+    obj_bbox = batch["scaled_gt_boxes"][..., :8].float()
+    obj_bbox_2d = batch["gt_boxes_2d"].float()
+    obj_class = batch["scaled_gt_boxes"][..., -1].long()
+    out = {}
+    cls_e = F.embedding(obj_class, sd["obj_class_embedding.weight"])
+    box_e = F.linear(obj_bbox, sd["obj_bbox_embedding.weight"], sd["obj_bbox_embedding.bias"])
+    box2_e = F.linear(obj_bbox_2d, sd["obj_bbox_2d_embedding.weight"], sd["obj_bbox_2d_embedding.bias"])
+    x = cls_e + box_e + box2_e
+    out["obj_class_embedding"] = cls_e.permute(0, 2, 1)
+    out["obj_bbox_embedding"] = box2_e.permute(0, 2, 1)
+    Bn = x.shape[0]
+    for r in resolutions:
+        Hr, Wr = int(feature_map_size[0] / r), int(feature_map_size[1] / r)
+        ii, ij = 1.0 / (feature_map_size[0] / r), 1.0 / (feature_map_size[1] / r)
+        tab = torch.tensor([(ij * j, ii * i, ij * (j + 1), ii * (i + 1)) for i in range(Hr) for j in range(Wr)],
+                           dtype=torch.float32)
+        emb = F.linear(tab, sd["obj_bbox_2d_embedding.weight"], sd["obj_bbox_2d_embedding.bias"])
+        out[f"image_patch_bbox_embedding_for_resolution{Hr}"] = emb[None].repeat_interleave(Bn, 0).permute(0, 2, 1)
+    out["key_padding_mask"] = (1 - batch["is_valid_obj"]).bool()
+    width = x.shape[-1]
+    ach = width // heads
+    sc = 1 / math.sqrt(math.sqrt(ach))
+    for l in range(layers):
+        p = f"transform.resblocks.{l}."
+        y = F.layer_norm(x, (width,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"])
+        qkv = F.linear(y, sd[p + "attn.c_qkv.weight"], sd[p + "attn.c_qkv.bias"])
+        bs, n, _ = qkv.shape
+        q, k, v = qkv.view(bs, n, heads, -1).split(ach, dim=-1)
+        w = torch.softmax(torch.einsum("bthc,bshc->bhts", q * sc, k * sc).float(), dim=-1)
+        a = torch.einsum("bhts,bshc->bthc", w, v).reshape(bs, n, -1)
+        x = x + F.linear(a, sd[p + "attn.c_proj.weight"], sd[p + "attn.c_proj.bias"])
+        y = F.layer_norm(x, (width,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"])
+        y = F.linear(F.gelu(F.linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])),
+                     sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        x = x + y
+    x = F.layer_norm(x, (width,), sd["final_ln.weight"], sd["final_ln.bias"])
+    out["xf_proj"] = F.linear(x[:, 0], sd["transformer_proj.weight"], sd["transformer_proj.bias"])
+    out["xf_out"] = x.permute(0, 2, 1)
+    if "concat_cond" in batch:
+        if "autoregressive_cond" in batch:
+            out["concat_cond"] = torch.cat([batch["concat_cond"], batch["autoregressive_cond"]], dim=1)
+        else:
+            out["concat_cond"] = batch["concat_cond"]
+    return out
+
+
+def synth_layout_batch(B: int, H: int = 32, W: int = 1024, seed: int = 0, n_obj: int = 13, autoreg: bool = False):
+    """Seeded synthetic conditioning with the shapes the layout pipeline produces:
+    scaled_gt_boxes [B,13,9], gt_boxes_2d [B,13,4], is_valid_obj [B,13], concat_cond [B,10,H,W]
+    (one-hot class map (9) + normalised centre depth), optional autoregressive_cond [B,1,H,W]."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    boxes = torch.rand(B, n_obj, 9, generator=g)
+    boxes[..., 8] = torch.randint(0, 9, (B, n_obj), generator=g).float()
+    b2 = torch.rand(B, n_obj, 4, generator=g)
+    b2 = torch.cat([b2[..., :2].min(b2[..., 2:]), b2[..., :2].max(b2[..., 2:])], -1)
+    valid = (torch.rand(B, n_obj, generator=g) > 0.2).float()
+    cls_map = torch.zeros(B, H, W, dtype=torch.long)
+    depth = torch.zeros(B, 1, H, W)
+    for b in range(B):
+        for o in range(n_obj):
+            x1, y1, x2, y2 = (b2[b, o] * torch.tensor([W, H, W, H])).long().tolist()
+            cls_map[b, y1:y2, x1:x2] = int(boxes[b, o, 8])
+            depth[b, 0, y1:y2, x1:x2] = float(torch.rand(1, generator=g))
+    concat = torch.cat([F.one_hot(cls_map, 9).permute(0, 3, 1, 2).float(), depth], dim=1)
+    batch = dict(scaled_gt_boxes=boxes, gt_boxes_2d=b2, is_valid_obj=valid, concat_cond=concat)
+    if autoreg:
+        batch["autoregressive_cond"] = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    return batch

@@ -168,6 +168,45 @@ class EmulatedLib:
         f16(y, parts, B, H, C // 8, W, 8).copy_(to_slab(self._split(x, parts).view(parts, B, H, W, C)))
         return 0
 
+    def gn_act_f32(self, x, st, gamma, beta, groups, eps, silu, y, B, HW, C, stream):
+        self._rec("gn_act_f32")
+        xt = f32(x, B, HW, C)
+        s = f64(st, B, C, 2)
+        cpg = C // groups
+        g = s.view(B, groups, cpg, 2).sum(dim=2)
+        n = HW * cpg
+        mean = g[..., 0] / n
+        var = (g[..., 1] / n - mean * mean).clamp(min=0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float().repeat_interleave(cpg, dim=1)
+        mean = mean.float().repeat_interleave(cpg, dim=1)
+        a, b = rstd, -mean * rstd
+        if gamma:
+            a = a * f32(gamma, C)
+            b = b * f32(gamma, C) + f32(beta, C)
+        o = xt * a[:, None, :] + b[:, None, :]
+        if silu:
+            o = F.silu(o)
+        f32(y, B, HW, C).copy_(o)
+        return 0
+
+    def attention_oa(self, qkv, pos_p, kl, pos_l, vl, out, out_w, parts, B, C, heads, T, L2, scale2, stream):
+        self._rec("attention_oa")
+        d = C // heads
+        QKV = f32(qkv, B, T, 3 * C)
+        def hd(t, n):
+            return t.reshape(B, n, heads, d).transpose(1, 2)       # B, h, n, d
+        q, k, v = hd(QKV[..., :C], T), hd(QKV[..., C:2 * C], T), hd(QKV[..., 2 * C:], T)
+        pp, pl = hd(f32(pos_p, B, T, C), T), hd(f32(pos_l, B, L2, C), L2)
+        klh, vlh = hd(f32(kl, B, L2, C), L2), hd(f32(vl, B, L2, C), L2)
+        qm = torch.cat([q, pp], -1)
+        km = torch.cat([torch.cat([k, pp], -1), torch.cat([klh, pl], -1)], 2)
+        vm = torch.cat([v, vlh], 2)
+        att = torch.softmax(qm @ km.transpose(-1, -2) * scale2, dim=-1)
+        o = (att @ vm).transpose(1, 2).reshape(B, T, C)
+        f16(out, parts, B, T // out_w, C // 8, out_w, 8).copy_(
+            to_slab(self._split(o, parts).view(parts, B, T // out_w, out_w, C)))
+        return 0
+
     def channel_stats(self, x, stats, B, HW, C, stream):
         self._rec("channel_stats")
         t = f32(x, B, HW, C).double()

@@ -278,3 +278,31 @@ def test_sampler_update(mode, objective):
     xs = h.t(torch.zeros(B, n))
     h.call("sampler_update", [("t", xt), ("t", pr), ("t", nz), ("t", coef), ("t", xs), B, n, mode, objective, 1.0])
     assert rel(*h.out(xs)) < 1e-6
+
+
+def test_gn_act_f32():
+    h = Both()
+    B, HW, C = 2, 300, 128
+    x = randn(B, HW, C, seed=1) * 1.7 + 0.2
+    ix = h.t(x)
+    st = h.t(torch.stack([x.double().sum(1), (x.double() ** 2).sum(1)], -1).contiguous())
+    gam, bet = h.t(1 + 0.1 * randn(C, seed=3)), h.t(0.1 * randn(C, seed=4))
+    y = h.t(torch.zeros(B, HW, C))
+    h.call("gn_act_f32", [("t", ix), ("t", st), ("t", gam), ("t", bet), 32, 1e-5, 1, ("t", y), B, HW, C])
+    assert rel(*h.out(y)) < 3e-6
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("C,T,W", [(256, 2048, 256), (512, 512, 128)])
+def test_attention_oa(parts, C, T, W):
+    h = Both()
+    B, L2 = 2, 13
+    heads = C // 32
+    qkv = h.t(randn(B, T, 3 * C, seed=1))
+    pos_p = h.t(randn(B, T, C, seed=2))
+    kl, pos_l, vl = h.t(randn(B, L2, C, seed=3)), h.t(randn(B, L2, C, seed=4)), h.t(randn(B, L2, C, seed=5))
+    out = h.t(torch.zeros(parts, B, T // W, C // 8, W, 8, dtype=torch.float16))
+    h.call("attention_oa", [("t", qkv), ("t", pos_p), ("t", kl), ("t", pos_l), ("t", vl), ("t", out), W, parts, B, C,
+                            heads, T, L2, 1 / math.sqrt(64)])
+    g, c = h.out(out)
+    assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)

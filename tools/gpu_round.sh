@@ -22,4 +22,4 @@ if [ "${NCU:-1}" = "1" ]; then
       python tools/gpu_debug_conv.py '{"taps": 9, "Cin": 64, "Cout": 64, "bn": 64, "rows": 4, "parts": 2, "B": 8, "H": 32, "W": 1024}' > gpurun_out/ncu_conv.log 2>&1
   echo "ncu full rc=$?"
 fi
-timeout 200 python tools/cpu_threads_probe.py > gpurun_out/cpu_threads.json 2>&1
+timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
