@@ -71,7 +71,13 @@ struct ConvCfg {
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI;
     static constexpr int SMEM = OFF_BAR + 256;
-    static constexpr int ACC_COLS = R * BN;
+    // MERGE (fp16x3 with BN = 64): the weight tile keeps hi and lo rows adjacent ([KG][hi|lo][BN][8]) so that
+    // a_hi x [w_hi ; w_lo] is ONE N = 128 MMA (A is fetched from shared memory once for 128 accumulator columns
+    // instead of twice) and only a_lo x w_hi remains an N = 64 MMA: 64 + 48 instead of 3 x 48 tensor-pipe cycles.
+    // The two partial accumulators (columns [0,64) and [64,128)) are added in the epilogue.
+    static constexpr bool MERGE = (NP == 2 && BN == 64);
+    static constexpr int ACC_ROW = MERGE ? 2 * BN : BN;
+    static constexpr int ACC_COLS = R * ACC_ROW;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         // ------------------------------ MMA issuer: one thread ------------------------------
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(128, BN);
+            constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * BN);
+            constexpr uint32_t KGS = C::MERGE ? 2 * BN * 16 : BN * 16;   // byte stride between 8-channel groups of B
             uint32_t ia = 0, ib = 0, it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1;
@@ -208,15 +216,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 #pragma unroll
                                 for (int ks = 0; ks < C::KS; ++ks) {
                                     const uint32_t a_addr = a_stage + (ri * C::KG + ks * 2) * C::SLAB + dx * 16;
-                                    const uint32_t b_addr = b_stage + dx * C::B_TAP + ks * 2 * (BN * 16);
+                                    const uint32_t b_addr = b_stage + dx * C::B_TAP + ks * 2 * KGS;
                                     const uint64_t a_hi = make_smem_desc(a_addr, C::SLAB, 128);
-                                    const uint64_t b_hi = make_smem_desc(b_addr, BN * 16, 128);
-                                    tc_mma_f16(acc + o * BN, a_hi, b_hi, idesc, (uint32_t)((c | dy | dx | ks) != 0));
-                                    if (NP == 2) {
+                                    const uint64_t b_hi = make_smem_desc(b_addr, KGS, 128);
+                                    const uint32_t first = (uint32_t)((c | dy | dx | ks) != 0);
+                                    if (C::MERGE) {
                                         const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
-                                        const uint64_t b_lo = make_smem_desc(b_addr + C::B_PART, BN * 16, 128);
-                                        tc_mma_f16(acc + o * BN, a_lo, b_hi, idesc, 1u);
-                                        tc_mma_f16(acc + o * BN, a_hi, b_lo, idesc, 1u);
+                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc2, first);   // [hi*hi | hi*lo]
+                                        tc_mma_f16(acc + o * C::ACC_ROW, a_lo, b_hi, idesc, 1u);       // += lo*hi
+                                    } else {
+                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc, first);
+                                        if (NP == 2) {
+                                            const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
+                                            const uint64_t b_lo = make_smem_desc(b_addr + C::B_PART, KGS, 128);
+                                            tc_mma_f16(acc + o * C::ACC_ROW, a_lo, b_hi, idesc, 1u);
+                                            tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_lo, idesc, 1u);
+                                        }
                                     }
                                 }
                             }
@@ -250,7 +265,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + warp * 32) * p.Cout;
                 for (int sl = 0; sl < BN / 32; ++sl) {
                     float v[32];
-                    tmem_ld_32x32(acc + o * BN + sl * 32, v);
+                    tmem_ld_32x32(acc + o * C::ACC_ROW + sl * 32, v);
+                    if (C::MERGE) {
+                        float v2[32];
+                        tmem_ld_32x32(acc + o * C::ACC_ROW + BN + sl * 32, v2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                    }
                     if (o == R - 1 && sl == BN / 32 - 1) {
                         // all TMEM reads of this accumulator set are done -> hand it back to the MMA warp
                         tc_fence_before();
@@ -351,8 +372,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
         size_t r = i;
         const int e = r % 8; r /= 8;
         const int n = r % bn; r /= bn;
-        const int j = r % kg; r /= kg;
-        const int part = r % parts; r /= parts;
+        int j, part;
+        if (parts == 2 && bn == 64) {   // merged layout [KG][hi|lo][bn][8] (see ConvCfg::MERGE)
+            part = r % parts; r /= parts;
+            j = r % kg; r /= kg;
+        } else {
+            j = r % kg; r /= kg;
+            part = r % parts; r /= parts;
+        }
         const int tap = r % taps; r /= taps;
         const int c = r % nch; r /= nch;
         const int nt = (int)r;
@@ -514,7 +541,8 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(parts == 1 || parts == 2);
     B200_CHECK_ARG(W % PIX == 0 && Cin % 32 == 0 && Cin >= 32);
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
-    B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0 && rows * bn <= 256);
+    B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
+    B200_CHECK_ARG(rows * bn * ((parts == 2 && bn == 64) ? 2 : 1) <= 256);   // two TMEM accumulator sets <= 512 columns
     ConvParams p{(const __half*)a, (const __half*)wpacked, bias, res, out, stats, out_scale, w_inv,
                  B, H, W, Cin, Cout, ring, 0};
     cudaStream_t st = (cudaStream_t)stream;
@@ -525,17 +553,18 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-#define B200_CONV_CASE(BN_, R_)                                                                                        \
-    if (bn == BN_ && rows == R_) {                                                                                     \
-        if (parts == 2)                                                                                                \
-            return taps == 9 ? launch_conv<BN_, R_, 9, 2>(p, num_sms, st) : launch_conv<BN_, R_, 1, 2>(p, num_sms, st); \
-        return taps == 9 ? launch_conv<BN_, R_, 9, 1>(p, num_sms, st) : launch_conv<BN_, R_, 1, 1>(p, num_sms, st);     \
-    }
-    B200_CONV_CASE(64, 1)
-    B200_CONV_CASE(64, 2)
-    B200_CONV_CASE(64, 4)
-    B200_CONV_CASE(128, 1)
-    B200_CONV_CASE(128, 2)
+#define B200_CONV_CASE(BN_, R_, NP_)                                                                              \
+    if (bn == BN_ && rows == R_ && parts == NP_)                                                                      \
+        return taps == 9 ? launch_conv<BN_, R_, 9, NP_>(p, num_sms, st) : launch_conv<BN_, R_, 1, NP_>(p, num_sms, st);
+    B200_CONV_CASE(64, 1, 1)
+    B200_CONV_CASE(64, 2, 1)
+    B200_CONV_CASE(64, 4, 1)
+    B200_CONV_CASE(128, 1, 1)
+    B200_CONV_CASE(128, 2, 1)
+    B200_CONV_CASE(64, 1, 2)
+    B200_CONV_CASE(64, 2, 2)
+    B200_CONV_CASE(128, 1, 2)
+    B200_CONV_CASE(128, 2, 2)
 #undef B200_CONV_CASE
     set_error("conv_tc: unsupported tile bn=%d rows=%d (need rows*bn <= 256)", bn, rows);
     return B200_E_ARG;

@@ -17,7 +17,53 @@ void set_error(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------------------
 // GroupNorm apply (+AdaGN) + SiLU -> fp16, optional concat of two sources
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GN_MAX_C = 2048;
+constexpr int GN_MAX_C = 1024;
+
+
+// Per-channel affine coefficients of GroupNorm(+AdaGN) for sample b:  y = x * s_a[c] + s_b[c].
+// All threads load the per-channel {sum, sumsq} in parallel (the serial per-group loop of the first version cost
+// ~10 us of dependent DRAM latency per block and dominated the kernel).
+__device__ __forceinline__ void gn_coefficients(const double* __restrict__ st0, int C0, const double* __restrict__ st1,
+                                                int C1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ ada, int ada_stride, int groups, float eps,
+                                                int HW, int b, float* s_a, float* s_b, double* s_st, float* s_mean,
+                                                float* s_rstd) {
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double* p = c < C0 ? st0 + ((size_t)b * C0 + c) * 2 : st1 + ((size_t)b * C1 + (c - C0)) * 2;
+        s_st[2 * c] = p[0];
+        s_st[2 * c + 1] = p[1];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+        double s = 0.0, ss = 0.0;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+            s += s_st[2 * c];
+            ss += s_st[2 * c + 1];
+        }
+        const double n = (double)HW * cpg;
+        const double mean = s / n;
+        double var = ss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float a = s_rstd[g], bb = -s_mean[g] * s_rstd[g];
+        if (gamma) { a *= gamma[c]; bb = bb * gamma[c] + beta[c]; }
+        if (ada) {
+            const float sc = 1.f + ada[(size_t)b * ada_stride + c];
+            const float sh = ada[(size_t)b * ada_stride + C + c];
+            a *= sc;
+            bb = bb * sc + sh;
+        }
+        s_a[c] = a;
+        s_b[c] = bb;
+    }
+}
 
 // output layout ("slab-major", the tcgen05 no-swizzle K-major operand image of one image row):
 //   y[part][b][h][C/8][w][8]  -- for a fixed (row, 8-channel group) all pixels are contiguous at a 16 B pitch
@@ -29,40 +75,12 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                                                      __half* __restrict__ y, size_t lo_off, int HW, int W,
                                                      int pix_per_block) {
     __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
+    __shared__ double s_st[2 * GN_MAX_C];
     __shared__ float s_mean[64], s_rstd[64];
     const int C = C0 + C1;
     const int b = blockIdx.y;
-    const bool norm = st0 != nullptr;
-    if (norm) {
-        const int cpg = C / groups;
-        if (threadIdx.x < groups) {
-            double s = 0.0, ss = 0.0;
-            for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-                const double* p = c < C0 ? st0 + ((size_t)b * C0 + c) * 2 : st1 + ((size_t)b * C1 + (c - C0)) * 2;
-                s += p[0];
-                ss += p[1];
-            }
-            const double n = (double)HW * cpg;
-            const double mean = s / n;
-            double var = ss / n - mean * mean;
-            if (var < 0.0) var = 0.0;
-            s_mean[threadIdx.x] = (float)mean;
-            s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const int g = c / cpg;
-            float a = s_rstd[g], bb = -s_mean[g] * s_rstd[g];
-            if (gamma) { a *= gamma[c]; bb = bb * gamma[c] + beta[c]; }
-            if (ada) {
-                const float sc = 1.f + ada[(size_t)b * ada_stride + c];
-                const float sh = ada[(size_t)b * ada_stride + C + c];
-                a *= sc;
-                bb = bb * sc + sh;
-            }
-            s_a[c] = a;
-            s_b[c] = bb;
-        }
+    if (st0 != nullptr) {
+        gn_coefficients(st0, C0, st1, C1, gamma, beta, ada, ada_stride, groups, eps, HW, b, s_a, s_b, s_st, s_mean, s_rstd);
     } else {
         for (int c = threadIdx.x; c < C; c += blockDim.x) { s_a[c] = 1.f; s_b[c] = 0.f; }
     }
@@ -112,31 +130,10 @@ __global__ void __launch_bounds__(256) gn_act_f32_kernel(const float* __restrict
                                                          float* __restrict__ y, double* __restrict__ stats_out, int HW,
                                                          int pix_per_block) {
     __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
+    __shared__ double s_st[2 * GN_MAX_C];
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y;
-    const int cpg = C / groups;
-    if (threadIdx.x < groups) {
-        double s = 0.0, ss = 0.0;
-        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-            const double* p = st + ((size_t)b * C + c) * 2;
-            s += p[0];
-            ss += p[1];
-        }
-        const double n = (double)HW * cpg;
-        const double mean = s / n;
-        double var = ss / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        float a = s_rstd[g], bb = -s_mean[g] * s_rstd[g];
-        if (gamma) { a *= gamma[c]; bb = bb * gamma[c] + beta[c]; }
-        s_a[c] = a;
-        s_b[c] = bb;
-    }
+    gn_coefficients(st, C, nullptr, 0, gamma, beta, nullptr, 0, groups, eps, HW, b, s_a, s_b, s_st, s_mean, s_rstd);
     __syncthreads();
     const int c4n = C / 4;
     const int p0 = blockIdx.x * pix_per_block;
@@ -206,14 +203,15 @@ __device__ __forceinline__ void fma4(float4& a, float k, const float4& v) {
 
 template <bool UP>
 __global__ void __launch_bounds__(256) fir_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                  double* __restrict__ stats, int H, int W, int C, int ring) {
+                                                  double* __restrict__ stats, int H, int W, int C, int ring,
+                                                  int pix_per_block) {
     __shared__ float red[256 * 8];
     const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
     const int b = blockIdx.y;
     const int c4n = C / 4;
     const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
-    const int p0 = blockIdx.x * ST_PIX_PER_BLOCK;
-    const int p1 = min(p0 + ST_PIX_PER_BLOCK, Ho * Wo);
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, Ho * Wo);
     const float* xb = x + (size_t)b * H * W * C + c4 * 4;
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
     for (int pp = p0 + poff; pp < p1; pp += pstep) {
@@ -562,9 +560,12 @@ extern "C" int b200_fir_resample(const float* x, float* y, double* stats, int B,
     B200_CHECK_ARG(x && y && c4_ok(C));
     B200_CHECK_ARG(up || (H % 2 == 0 && W % 2 == 0));
     const int npo = up ? 4 * H * W : (H / 2) * (W / 2);
-    dim3 grid(cdiv(npo, ST_PIX_PER_BLOCK), B);
-    if (up) fir_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring);
-    else fir_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring);
+    int ppb = ST_PIX_PER_BLOCK;
+    const int pmin = 256 / (C / 4) > 8 ? 256 / (C / 4) : 8;   // at least one pixel per thread row
+    while (ppb > pmin && (long long)cdiv(npo, ppb) * B < 4 * 148) ppb >>= 1;
+    dim3 grid(cdiv(npo, ppb), B);
+    if (up) fir_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring, ppb);
+    else fir_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

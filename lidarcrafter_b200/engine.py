@@ -31,14 +31,15 @@ class Act:
     stats: dict | None = None  # stats slot from Plan.new_stats(): [B, C, 2] fp64 view into the arena
 
 
-def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, sms: int = NUM_SMS):
+def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, parts: int = 2, sms: int = NUM_SMS):
     """Choose (bn, rows) for b200_conv_tc: maximise (SM fill) x min(L2-feed, MMA-shape) efficiency."""
     best = None
     for bn in (128, 64):
         if Cout % bn:
             continue
         for rows in (4, 2, 1):
-            if H % rows or rows * bn > 256:
+            merged = parts == 2 and bn == 64      # conv_tc ConvCfg::MERGE: 2 x BN accumulator columns per row
+            if H % rows or rows * bn * (2 if merged else 1) > 256:
                 continue
             tiles = B * (H // rows) * (W // 128) * (Cout // bn)
             waves = math.ceil(tiles / sms)
@@ -145,7 +146,8 @@ class Plan:
         return out
 
     def run(self, stream: int):
-        self.stats_arena.zero_()
+        with torch.inference_mode():     # buffers may have been created under sample()'s inference_mode
+            self.stats_arena.zero_()
         for fn, args in self.ops:
             fn(*args, stream)
 
@@ -184,7 +186,7 @@ class PlanBuilder:
         by = npix * (2.0 * self.p.parts * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
             + 2.0 * self.p.parts * taps * Cin * Cout
         if self.p.conv_impl == "tc":
-            bn, rows = pick_tile(self.B, H, W, Cout, taps)
+            bn, rows = pick_tile(self.B, H, W, Cout, taps, self.p.parts)
             pc = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
             self.p.bufs.append(pc)
             self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),

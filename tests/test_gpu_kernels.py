@@ -63,8 +63,8 @@ def split(v, parts):
 @pytest.mark.parametrize("parts", [2, 1])
 @pytest.mark.parametrize("taps", [9, 1])
 @pytest.mark.parametrize("bn,rows,Cin,Cout,H,W,B", [
-    (64, 4, 64, 64, 8, 256, 2),
-    (64, 4, 64, 64, 32, 1024, 3),        # > 148 tiles: persistent loop + TMEM double buffering
+    (64, 2, 64, 64, 8, 256, 2),
+    (64, 2, 64, 64, 32, 1024, 3),        # > 148 tiles: persistent loop + TMEM double buffering
     (64, 2, 96, 64, 4, 128, 1),
     (64, 1, 32, 128, 3, 128, 2),
     (128, 2, 128, 128, 4, 256, 1),
@@ -103,7 +103,7 @@ def test_conv_tc_zero_pad_no_bias_no_res():
     out = h.t(torch.zeros(B, H, W, Cout))
     h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 64, 2, 128.0])
     h.call("conv_tc", [("t", a), ("t", wp), None, None, 1.0, 1.0 / 128.0, ("t", out), None, B, H, W, Cin, Cout, 9, 0, 64,
-                       4, 2])  # ring = 0: zero padding in W as well
+                       2, 2])  # ring = 0: zero padding in W as well
     g, c = h.out(out)
     assert rel(g, c) < 2e-6
 

@@ -57,6 +57,7 @@ def test_cond_sampler_vs_oracle():
     x_T = torch.randn(1, 2, 32, 1024, generator=g)
     noises = [torch.randn(1, 2, 32, 1024, generator=g) for _ in range(3)]
     it = iter(noises)
+    orig_randn_like = ddpm.randn_like
     ddpm.randn_like = lambda x, rng=None: next(it).to(x.device)
     cond = ddpm.get_network_condition(input_dict=to_cuda(dict(batch)), only_custom_condition=True)
     plan = ddpm.model.get_plan(1)
@@ -68,6 +69,7 @@ def test_cond_sampler_vs_oracle():
                           return_all=True)
     assert rel_l2(xs[1], ref[1]) < TOL and rel_l2(xs[-1], ref[-1]) < TOL
     # public sample(): shapes + the condition is re-folded when the batch dict changes
+    ddpm.randn_like = orig_randn_like
     out = ddpm.sample(to_cuda(dict(O.synth_layout_batch(1, seed=4))), batch_size=1, num_steps=2, progress=False,
                       mode="ddim")
     assert out.shape == (1, 2, 32, 1024) and torch.isfinite(out).all()

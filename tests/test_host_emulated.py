@@ -97,5 +97,7 @@ def test_tile_picker_respects_kernel_limits():
     for B in (1, 2, 8, 64):
         for (H, W, C) in ((32, 1024, 64), (16, 512, 128), (8, 256, 256), (4, 128, 512), (1, 128, 1536)):
             for taps in (1, 9):
-                bn, rows = pick_tile(B, H, W, C, taps)
-                assert C % bn == 0 and H % rows == 0 and rows * bn <= 512
+                for parts in (1, 2):
+                    bn, rows = pick_tile(B, H, W, C, taps, parts)
+                    assert C % bn == 0 and H % rows == 0
+                    assert rows * bn * (2 if (parts == 2 and bn == 64) else 1) <= 256

@@ -22,17 +22,17 @@ CASES = [
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=1, B=1, H=4, W=256),
     dict(taps=9, Cin=64, Cout=128, bn=128, rows=2, parts=1, B=2, H=8, W=256),
     dict(taps=1, Cin=32, Cout=64, bn=64, rows=1, parts=2, B=1, H=1, W=128),
-    dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=2, B=1, H=4, W=256),
+    dict(taps=9, Cin=64, Cout=64, bn=64, rows=2, parts=2, B=1, H=4, W=256),
     dict(taps=9, Cin=128, Cout=128, bn=128, rows=2, parts=2, B=2, H=4, W=128),
-    dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=2, B=8, H=32, W=1024),
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=2, parts=2, B=8, H=32, W=1024),
     dict(taps=9, Cin=128, Cout=128, bn=128, rows=2, parts=2, B=8, H=16, W=512),
-    dict(taps=9, Cin=128, Cout=128, bn=64, rows=4, parts=2, B=8, H=16, W=512),
+    dict(taps=9, Cin=128, Cout=128, bn=64, rows=2, parts=2, B=8, H=16, W=512),
+    dict(taps=9, Cin=64, Cout=64, bn=64, rows=1, parts=2, B=8, H=32, W=1024),
     dict(taps=9, Cin=256, Cout=256, bn=128, rows=2, parts=2, B=8, H=8, W=256),
     dict(taps=9, Cin=256, Cout=256, bn=128, rows=1, parts=2, B=8, H=8, W=256),
     dict(taps=9, Cin=512, Cout=512, bn=128, rows=1, parts=2, B=8, H=4, W=128),
     dict(taps=9, Cin=512, Cout=512, bn=128, rows=2, parts=2, B=8, H=4, W=128),
-    dict(taps=9, Cin=512, Cout=512, bn=64, rows=4, parts=2, B=8, H=4, W=128),
+    dict(taps=9, Cin=512, Cout=512, bn=64, rows=2, parts=2, B=8, H=4, W=128),
     dict(taps=9, Cin=64, Cout=64, bn=64, rows=4, parts=1, B=8, H=32, W=1024),
     dict(taps=1, Cin=512, Cout=1536, bn=128, rows=2, parts=2, B=8, H=4, W=128),
 ]

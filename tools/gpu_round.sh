@@ -19,7 +19,7 @@ if [ "${NCU:-1}" = "1" ]; then
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   echo "ncu launches rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 2 -f -o gpurun_out/prof_conv \
-      python tools/gpu_debug_conv.py '{"taps": 9, "Cin": 64, "Cout": 64, "bn": 64, "rows": 4, "parts": 2, "B": 8, "H": 32, "W": 1024}' > gpurun_out/ncu_conv.log 2>&1
+      python tools/gpu_debug_conv.py '{"taps": 9, "Cin": 64, "Cout": 64, "bn": 64, "rows": 2, "parts": 2, "B": 8, "H": 32, "W": 1024}' > gpurun_out/ncu_conv.log 2>&1
   echo "ncu full rc=$?"
 fi
 timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
