@@ -50,6 +50,9 @@ const char* b200_last_error(void);
 int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
                  float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
                  int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
+/* profiling aid: device buffer of [#CTAs][8] uint64 cycle counters filled by b200_conv_tc (NULL disables; see
+ * conv_tc.cu g_conv_dbg for the slot meaning).  Not used on the product path.                          */
+int b200_conv_set_debug(void* dbg_u64);
 /* number of fp16 elements of the packed weight image (== parts*taps*Cout*Cin) */
 size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
 /* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
@@ -134,6 +137,14 @@ int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, i
 int b200_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
                       const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                       int L2, float scale2, void* stream);
+
+/* Flash-style (online softmax, register-tiled fp32) versions of the two attention cores above: same inputs /
+ * outputs, scores never leave the SM and shared memory does not grow with T (used by the plans).        */
+int b200_flash_attention(const float* qkv, int E, void* out, int out_w, int parts, int B, int heads, int T,
+                         float scale, void* stream);
+int b200_flash_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
+                            const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
+                            int L2, float scale2, void* stream);
 
 /* ---- K5: sampler update --------------------------------------------------------------------------
  * replaces p_step's ~25 elementwise ops (diffusion/continuous_time.py:205-231).

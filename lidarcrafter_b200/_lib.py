@@ -23,6 +23,7 @@ PROTOTYPES = {
     "b200_device_check": (I, [I]),
     "b200_last_error": (C.c_char_p, []),
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+    "b200_conv_set_debug": (I, [P]),
     "b200_packed_weight_elems": (SZ, [I, I, I, I]),
     "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, F, P]),
     "b200_pack_conv_weight_plain": (I, [P, P, I, I, I, I, F, P]),
@@ -30,6 +31,8 @@ PROTOTYPES = {
     "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, I, I, I, I, P]),
     "b200_gn_act_f32": (I, [P, P, P, P, I, F, I, P, I, I, I, P]),
     "b200_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
+    "b200_flash_attention": (I, [P, I, P, I, I, I, I, I, F, P]),
+    "b200_flash_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
     "b200_channel_stats": (I, [P, P, I, I, I, P]),
     "b200_fir_resample": (I, [P, P, P, I, I, I, I, I, I, P]),
     "b200_time_embed": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),

@@ -293,3 +293,222 @@ extern "C" int b200_attention_oa(const float* qkv, const float* pos_p, const flo
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
+
+// =========================================================================================================
+// Flash-style fp32 attention (online softmax, 64-query x 64-key register-tiled blocks): replaces the two
+// score-row kernels above on the hot path.  One kernel, two operand loaders:
+//   MHA : q/k/v = column slices of the fused qkv tensor (efficient_unet.py:39-53), d = dv = 32 or 64
+//   OA  : q = [q_c ; pos_p], k = [[k_c ; pos_p] | [k_l ; pos_l]], v = [v_c | v_l], d = 32 + 32, dv = 32
+//         (layout_unet_v1.py:488-505)
+// Scores never leave the SM; all math fp32 (the tolerance budget is spent nowhere here).
+// =========================================================================================================
+namespace b200 {
+
+constexpr int FA_BQ = 64, FA_BK = 64, FA_THREADS = 256, FA_PAD = 68;
+
+struct FAParams {
+    // q/k/v "source 1" (content) and optional "source 2" (positional) pointers; token-major fp32
+    const float *q1, *q2, *k1, *k2, *v;      // main tokens
+    const float *xk1, *xk2, *xv;             // extra (layout) keys / values, may be null
+    int ldq1, ldq2, ldk1, ldk2, ldv, ldx;    // row strides (floats)
+    int d1, d2, dv;                          // per-head dims of source 1 / 2 and of v
+    int T, Tx;                               // #queries == #main keys, #extra keys
+    __half* out;
+    size_t lo_off;
+    int C, Wimg;                             // output channels (heads * dv) and image width for the slab-major store
+    float scale;                             // applied to q (full softmax scale)
+};
+
+template <int DQ, int DV>
+__global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const FAParams p) {
+    extern __shared__ float sm[];
+    float* sQ = sm;                       // [DQ][FA_PAD]   (d-major: 4 consecutive queries = one LDS.128)
+    float* sK = sQ + DQ * FA_PAD;         // [DQ][FA_PAD]
+    float* sV = sK + DQ * FA_PAD;         // [FA_BK][DV]
+    float* sP = sV + FA_BK * DV;          // [FA_BK][FA_PAD] (key-major)
+    const int q0 = blockIdx.x * FA_BQ, head = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int DPT = DV / 16;          // value dims per thread
+
+    // ---- load the query tile (pre-scaled), transposed ----
+    for (int i = tid; i < FA_BQ * (DQ / 4); i += FA_THREADS) {
+        const int qi = i / (DQ / 4), c4 = (i - qi * (DQ / 4)) * 4;
+        const int tq = q0 + qi;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (tq < p.T) {
+            const size_t tok = (size_t)b * p.T + tq;
+            v = c4 < p.d1 ? *reinterpret_cast<const float4*>(p.q1 + tok * p.ldq1 + head * p.d1 + c4)
+                          : *reinterpret_cast<const float4*>(p.q2 + tok * p.ldq2 + head * p.d2 + (c4 - p.d1));
+        }
+        sQ[(c4 + 0) * FA_PAD + qi] = v.x * p.scale; sQ[(c4 + 1) * FA_PAD + qi] = v.y * p.scale;
+        sQ[(c4 + 2) * FA_PAD + qi] = v.z * p.scale; sQ[(c4 + 3) * FA_PAD + qi] = v.w * p.scale;
+    }
+    float m_run[4], l_run[4], o[4][DPT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_run[i] = -INFINITY; l_run[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) o[i][j] = 0.f;
+    }
+    const int S = p.T + p.Tx;
+    const int ntiles = (S + FA_BK - 1) / FA_BK;
+    for (int kt = 0; kt < ntiles; ++kt) {
+        const int k0 = kt * FA_BK;
+        __syncthreads();   // previous tile's sK / sV / sP fully consumed (also orders the sQ stores on iteration 0)
+        // ---- K tile (transposed) and V tile ----
+        for (int i = tid; i < FA_BK * (DQ / 4); i += FA_THREADS) {
+            const int kj = i / (DQ / 4), c4 = (i - kj * (DQ / 4)) * 4;
+            const int tk = k0 + kj;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (tk < p.T) {
+                const size_t tok = (size_t)b * p.T + tk;
+                v = c4 < p.d1 ? *reinterpret_cast<const float4*>(p.k1 + tok * p.ldk1 + head * p.d1 + c4)
+                              : *reinterpret_cast<const float4*>(p.k2 + tok * p.ldk2 + head * p.d2 + (c4 - p.d1));
+            } else if (tk < S) {
+                const size_t tok = (size_t)b * p.Tx + (tk - p.T);
+                v = c4 < p.d1 ? *reinterpret_cast<const float4*>(p.xk1 + tok * p.ldx + head * p.d1 + c4)
+                              : *reinterpret_cast<const float4*>(p.xk2 + tok * p.ldx + head * p.d2 + (c4 - p.d1));
+            }
+            sK[(c4 + 0) * FA_PAD + kj] = v.x; sK[(c4 + 1) * FA_PAD + kj] = v.y;
+            sK[(c4 + 2) * FA_PAD + kj] = v.z; sK[(c4 + 3) * FA_PAD + kj] = v.w;
+        }
+        for (int i = tid; i < FA_BK * (DV / 4); i += FA_THREADS) {
+            const int kj = i / (DV / 4), c4 = (i - kj * (DV / 4)) * 4;
+            const int tk = k0 + kj;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (tk < p.T) v = *reinterpret_cast<const float4*>(p.v + ((size_t)b * p.T + tk) * p.ldv + head * DV + c4);
+            else if (tk < S) v = *reinterpret_cast<const float4*>(p.xv + ((size_t)b * p.Tx + (tk - p.T)) * p.ldx + head * DV + c4);
+            *reinterpret_cast<float4*>(sV + kj * DV + c4) = v;
+        }
+        __syncthreads();
+        // ---- S = Q K^T for this thread's 4 queries x 4 keys ----
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < DQ; ++d) {
+            const float4 qv = *reinterpret_cast<const float4*>(sQ + d * FA_PAD + ty * 4);
+            const float4 kv = *reinterpret_cast<const float4*>(sK + d * FA_PAD + tx * 4);
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+        }
+        // mask keys past the end
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + tx * 4 + j >= S)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[i][j] = -INFINITY;
+        // ---- online softmax: row max over the 16 threads (tx) sharing the same queries ----
+        float alpha[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = fmaxf(fmaxf(s[i][0], s[i][1]), fmaxf(s[i][2], s[i][3]));
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float m_new = fmaxf(m_run[i], mx);
+            alpha[i] = __expf(m_run[i] - m_new);      // exp(-inf) = 0 on the first tile
+            m_run[i] = m_new;
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float e = __expf(s[i][j] - m_new);
+                s[i][j] = e;
+                rs += e;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            l_run[i] = l_run[i] * alpha[i] + rs;
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) o[i][j] *= alpha[i];
+        }
+        // P -> smem (key-major so that 4 queries are contiguous)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(sP + (tx * 4 + j) * FA_PAD + ty * 4) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+        __syncthreads();
+        // ---- O += P V : this thread's 4 queries x DPT value dims (dims tx*DPT ..) ----
+#pragma unroll 8
+        for (int k = 0; k < FA_BK; ++k) {
+            const float4 pv = *reinterpret_cast<const float4*>(sP + k * FA_PAD + ty * 4);
+            const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+            float va[DPT];
+            if constexpr (DPT == 4) {
+                const float4 vv = *reinterpret_cast<const float4*>(sV + k * DV + tx * 4);
+                va[0] = vv.x; va[1] = vv.y; va[2] = vv.z; va[3] = vv.w;
+            } else {
+                const float2 vv = *reinterpret_cast<const float2*>(sV + k * DV + tx * 2);
+                va[0] = vv.x; va[1] = vv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < DPT; ++j) o[i][j] = fmaf(pa[i], va[j], o[i][j]);
+        }
+    }
+    // ---- normalise and store (fp16 hi [+ lo], slab-major conv operand) ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int tq = q0 + ty * 4 + i;
+        if (tq >= p.T) continue;
+        const float inv = 1.f / l_run[i];
+        const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
+        const int ch = head * DV + tx * DPT;
+        __half* op = p.out + ((((size_t)b * (p.T / p.Wimg) + hh) * (p.C / 8) + ch / 8) * p.Wimg + ww) * 8 + (ch & 7);
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const float val = o[i][j] * inv;
+            const __half hi = __float2half_rn(val);
+            op[j] = hi;
+            if (p.lo_off) op[p.lo_off + j] = __float2half_rn(val - __half2float(hi));
+        }
+    }
+}
+
+template <int DQ, int DV>
+static int launch_fa(const FAParams& p, int B, int heads, cudaStream_t st) {
+    const size_t smem = ((size_t)2 * DQ * FA_PAD + FA_BK * DV + FA_BK * FA_PAD) * sizeof(float);
+    static bool attr = false;
+    if (!attr && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DQ, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("flash_attn: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return B200_E_CUDA;
+        }
+        attr = true;
+    }
+    dim3 grid(cdiv(p.T, FA_BQ), heads, B);
+    flash_attn_kernel<DQ, DV><<<grid, FA_THREADS, smem, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_flash_attention(const float* qkv, int E, void* out, int out_w, int parts, int B, int heads, int T,
+                                    float scale, void* stream) {
+    // self-attention on the fused in-projection output qkv fp32 [B,T,3E] (q | k | v, head-major)
+    B200_CHECK_ARG(qkv && out && (parts == 1 || parts == 2) && heads > 0 && E % heads == 0);
+    B200_CHECK_ARG(out_w > 0 && T % out_w == 0);
+    const int d = E / heads;
+    FAParams p{qkv, nullptr, qkv + E, nullptr, qkv + 2 * E, nullptr, nullptr, nullptr, 3 * E, 0, 3 * E, 0, 3 * E, 0,
+               d, 0, d, T, 0, (__half*)out, parts == 2 ? (size_t)B * T * E : 0, E, out_w, scale};
+    if (d == 64) return launch_fa<64, 64>(p, B, heads, (cudaStream_t)stream);
+    if (d == 32) return launch_fa<32, 32>(p, B, heads, (cudaStream_t)stream);
+    set_error("flash_attention: head dim %d not supported (32 or 64)", d);
+    return B200_E_ARG;
+}
+
+extern "C" int b200_flash_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
+                                       const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
+                                       int L2, float scale2, void* stream) {
+    B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out && (parts == 1 || parts == 2));
+    B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32 && out_w > 0 && T % out_w == 0 && L2 >= 0);
+    FAParams p{qkv, pos_p, qkv + C, pos_p, qkv + 2 * C, kl, pos_l, vl, 3 * C, C, 3 * C, C, 3 * C, C,
+               32, 32, 32, T, L2, (__half*)out, parts == 2 ? (size_t)B * T * C : 0, C, out_w, scale2};
+    return launch_fa<64, 32>(p, B, heads, (cudaStream_t)stream);
+}

@@ -42,6 +42,13 @@ struct ConvParams {
 
 __device__ __align__(128) unsigned char g_zero_page[4096];  // source of zero-padding rows / pixels
 
+// Optional in-kernel profile (b200_conv_set_debug): per CTA 8 x u64 cycle counters
+//   [0] MMA thread total, [1] wait FULL_A, [2] wait FULL_B, [3] wait ACC_EMPTY,
+//   [4] epilogue warp 0 total, [5] epilogue wait ACC_FULL, [6] producer wait EMPTY_A, [7] producer wait EMPTY_B
+__device__ unsigned long long* g_conv_dbg = nullptr;
+#define DBG_T0() const long long t0__ = dbg ? clock64() : 0
+#define DBG_ACC(slot) do { if (dbg) dbg_acc[slot] += clock64() - t0__; } while (0)
+
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
 constexpr int CONV_THREADS = 192;
 
@@ -128,6 +135,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     if (warp == 4) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
         uint32_t ia = 0, ib = 0;
+        unsigned long long* dbg = g_conv_dbg;
+        unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             int t = tile;
@@ -142,7 +151,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     const int s = ia % C::SA;
                     const uint32_t ph = (ia / C::SA) & 1;
                     if (lane == 0) {
+                        DBG_T0();
                         mbar_wait(EMPTY_A(s), ph ^ 1);
+                        DBG_ACC(6);
                         mbar_expect_tx(FULL_A(s), C::A_STAGE);
                     }
                     __syncwarp();
@@ -178,7 +189,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     for (int dy = 0; dy < C::TG; ++dy, ++ib) {
                         const int s = ib % C::SB;
                         const uint32_t ph = (ib / C::SB) & 1;
-                        mbar_wait(EMPTY_B(s), ph ^ 1);
+                        {
+                            DBG_T0();
+                            mbar_wait(EMPTY_B(s), ph ^ 1);
+                            DBG_ACC(7);
+                        }
                         mbar_expect_tx(FULL_B(s), C::B_STAGE);
                         bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE,
                                       wsrc + (size_t)(c * C::TG + dy) * (C::B_STAGE / 2), C::B_STAGE, FULL_B(s));
@@ -187,6 +202,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 __syncwarp();
             }
         }
+        if (dbg && lane == 0) {
+            dbg[blockIdx.x * 8 + 6] = dbg_acc[6];
+            dbg[blockIdx.x * 8 + 7] = dbg_acc[7];
+        }
     } else if (warp == 5) {
         // ------------------------------ MMA issuer: one thread ------------------------------
         if (lane == 0) {
@@ -194,18 +213,33 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * BN);
             constexpr uint32_t KGS = C::MERGE ? 2 * BN * 16 : BN * 16;   // byte stride between 8-channel groups of B
             uint32_t ia = 0, ib = 0, it = 0;
+            unsigned long long* dbg = g_conv_dbg;
+            unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long t_start = dbg ? clock64() : 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1;
-                mbar_wait(ACC_EMPTY(buf), ((it >> 1) & 1) ^ 1);
+                {
+                    DBG_T0();
+                    mbar_wait(ACC_EMPTY(buf), ((it >> 1) & 1) ^ 1);
+                    DBG_ACC(3);
+                }
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * C::ACC_COLS;
                 for (int c = 0; c < NCH; ++c, ++ia) {
                     const int sa = ia % C::SA;
-                    mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
+                    {
+                        DBG_T0();
+                        mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
+                        DBG_ACC(1);
+                    }
                     const uint32_t a_stage = sbase + C::OFF_A + sa * C::A_STAGE;
                     for (int dy = 0; dy < C::TG; ++dy, ++ib) {
                         const int sb = ib % C::SB;
-                        mbar_wait(FULL_B(sb), (ib / C::SB) & 1);
+                        {
+                            DBG_T0();
+                            mbar_wait(FULL_B(sb), (ib / C::SB) & 1);
+                            DBG_ACC(2);
+                        }
                         tc_fence_after();
                         const uint32_t b_stage = sbase + C::OFF_B + sb * C::B_STAGE;
 #pragma unroll
@@ -242,6 +276,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 }
                 tc_commit(ACC_FULL(buf));
             }
+            if (dbg) {
+                dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+                dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
+                dbg[blockIdx.x * 8 + 2] = dbg_acc[2];
+                dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
+            }
         }
     } else {
         // ------------------------------ epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ------------------------------
@@ -249,6 +289,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         const int col4 = lane & 7, rb = lane >> 3;
         const float scale = p.out_scale, winv = p.w_inv;
         uint32_t it = 0;
+        unsigned long long* dbg = g_conv_dbg;
+        unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long t_start = dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             int t = tile;
             const int nt = t % NT; t /= NT;
@@ -257,7 +300,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             const int b = t / HG;
             const int w0 = wt * PIX, h0 = hg * R, n0 = nt * BN;
             const uint32_t buf = it & 1;
-            mbar_wait(ACC_FULL(buf), (it >> 1) & 1);
+            {
+                DBG_T0();
+                mbar_wait(ACC_FULL(buf), (it >> 1) & 1);
+                DBG_ACC(5);
+            }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
             for (int o = 0; o < R; ++o) {
@@ -321,6 +368,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     __syncwarp();
                 }
             }
+        }
+        if (dbg && threadIdx.x == 0) {
+            dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+            dbg[blockIdx.x * 8 + 5] = dbg_acc[5];
         }
     }
 
@@ -499,6 +550,16 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_conv_set_debug(void* dbg_u64) {
+    unsigned long long* p = (unsigned long long*)dbg_u64;
+    cudaError_t e = cudaMemcpyToSymbol(g_conv_dbg, &p, sizeof(p));
+    if (e != cudaSuccess) {
+        set_error("conv_set_debug: %s", cudaGetErrorString(e));
+        return B200_E_CUDA;
+    }
+    return B200_OK;
+}
 
 extern "C" size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts) {
     return (size_t)Cout * Cin * taps * parts;

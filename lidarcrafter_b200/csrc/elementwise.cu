@@ -88,11 +88,19 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
     const int c8n = C / 8;
     const int p0 = blockIdx.x * pix_per_block;
     const int np = min(pix_per_block, HW - p0);
-    // consecutive threads -> consecutive pixels of one 8-channel group: 512 B contiguous stores per warp
-    for (int i = threadIdx.x; i < np * c8n; i += blockDim.x) {
-        const int c8 = i / np, pp = i - c8 * np;
+    // One warp item = 8 consecutive pixels x 32 consecutive channels: lane -> (pixel lane/4, 8-channel group lane%4).
+    // Reads: each pixel's 32 channels are one 128-byte line; writes: for each of the 4 channel groups the 8 pixels
+    // are 128 contiguous bytes of the slab-major output -> both directions move whole lines.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int px = lane >> 2, g = lane & 3;
+    const int cb_n = (C + 31) / 32, pb_n = np / 8;      // np is a multiple of 8 (W % 8 == 0)
+    const int Himg = HW / W;
+    for (int it = warp; it < pb_n * cb_n; it += nwarps) {
+        const int cb = it / pb_n, pb = it - cb * pb_n;
+        const int c8 = cb * 4 + g;
+        if (c8 >= c8n) continue;
         const int c = c8 * 8;
-        const int pl = p0 + pp;
+        const int pl = p0 + pb * 8 + px;
         const size_t pix = (size_t)b * HW + pl;
         const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
         const float4 v0 = *reinterpret_cast<const float4*>(src);
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
         const int hh = pl / W, ww = pl - hh * W;
-        const size_t oi = ((((size_t)b * (HW / W) + hh) * c8n + c8) * W + ww) * 8;
+        const size_t oi = ((((size_t)b * Himg + hh) * c8n + c8) * W + ww) * 8;
         *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
         if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
             __half2 l[4];
@@ -511,6 +519,7 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
                                int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
                                void* stream) {
     B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(W % 8 == 0);
     const int HW = H * W;
     B200_CHECK_ARG(x0 && y && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && (C1 == 0 || x1));
     const int C = C0 + C1;

@@ -245,6 +245,42 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
 
     p_sample_loop = sample
 
+    # ---- RePaint (continuous_time.py:262-319): same p_step kernels + q_step / mask blend ----
+    def _repaint_loop(self, p_step_fn, known, mask, num_steps, num_resample_steps, jump_length, progress, rng,
+                      return_all):
+        assert num_resample_steps > 0 and jump_length > 0
+        B = known.shape[0]
+        x_t = self.randn(B, *self.sampling_shape, rng=rng, device=self.device)
+        steps = torch.linspace(1, 0, num_steps + 1, device=self.device)[None].repeat_interleave(B, dim=0)
+        out = [x_t] if return_all else None
+        interp = torch.linspace(0, 1, jump_length + 1, device=self.device)
+        x_s = x_t
+        for i in range(num_steps):
+            r_steps = steps[:, [i]] + interp[None] * (steps[:, [i + 1]] - steps[:, [i]])
+            for j in range(num_resample_steps):
+                x = x_t
+                for k in range(jump_length):            # t -> s: reverse diffusion, known region re-noised
+                    known_s, _ = self.q_step_from_x_0(known, r_steps[:, k + 1], rng=rng)
+                    unknown_s = p_step_fn(x, r_steps[:, k], r_steps[:, k + 1], rng)
+                    x = mask * known_s + (1 - mask) * unknown_s
+                x_s = x
+                if return_all:
+                    out.append(x_s)
+                if i == num_steps - 1 or j == num_resample_steps - 1:
+                    x_t = x
+                    break
+                for k in range(jump_length, 0, -1):     # s -> t: forward diffusion (resampling jump)
+                    x = self.q_step(x, r_steps[:, k - 1], r_steps[:, k], rng=rng)
+                x_t = x
+        return torch.stack(out) if return_all else x_s
+
+    @torch.inference_mode()
+    def repaint(self, known: torch.Tensor, mask: torch.Tensor, num_steps: int, num_resample_steps: int = 1,
+                jump_length: int = 1, progress: bool = True, rng=None, return_all: bool = False):
+        """continuous_time.py:262-319 (RePaint, https://arxiv.org/abs/2201.09865); reverse steps are DDPM p_steps."""
+        return self._repaint_loop(lambda x, t, s, r: self.p_step(x, t, s, rng=r), known, mask, num_steps,
+                                  num_resample_steps, jump_length, progress, rng, return_all)
+
     def _sample_from(self, x, num_steps, progress, rng, return_all, mode, ddim_eta, plan=None):
         B = x.shape[0]
         dev = x.device
@@ -347,3 +383,18 @@ class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
         return self._sample_from(x, num_steps, progress, rng, return_all, mode, ddim_eta, plan=plan)
 
     p_sample_loop = sample
+
+    @torch.inference_mode()
+    def inpaint(self, known: torch.Tensor, mask: torch.Tensor, batch_dict: dict, num_steps: int,
+                num_resample_steps: int = 1, jump_length: int = 1, progress: bool = True, rng=None,
+                return_all: bool = False):
+        """continuous_time_cond.py:283-353: layout-conditioned RePaint.  (The reference passes ``condition_dict`` as
+        ``step_t`` to ``q_step`` in the resampling branch, :337 -- only reached for num_resample_steps > 1; here
+        q_step gets the step tensors it is declared with.)"""
+        cond = self.get_network_condition(input_dict=batch_dict, only_custom_condition=True)
+        return self._repaint_loop(lambda x, t, s, r: self.p_step(x, cond, t, s, rng=r), known, mask, num_steps,
+                                  num_resample_steps, jump_length, progress, rng, return_all)
+
+    @torch.inference_mode()
+    def repaint(self, known, mask, batch_dict, num_steps, **kw):
+        return self.inpaint(known, mask, batch_dict, num_steps, **kw)

@@ -347,9 +347,8 @@ class EfficientUNetPlan:
         qkv, _ = pb.conv(an, x.H, x.W, w_qkv, ab.attn.in_proj_bias, None, 1.0, False)
         att = self.plan.f16(self.B, T, E)
         d = E // nh
-        self.plan.add(self.lib.attention, _ptr(qkv), 3 * E, 0, _ptr(qkv), 3 * E, E, _ptr(qkv), 3 * E, 2 * E,
-                      _ptr(att), E, x.W, self.plan.parts, self.B, nh, T, T, d, d, 1.0 / math.sqrt(d), name="attention",
-                      flops=4.0 * self.B * nh * T * T * d)
+        self.plan.add(self.lib.flash_attention, _ptr(qkv), E, _ptr(att), x.W, self.plan.parts, self.B, nh, T,
+                      1.0 / math.sqrt(d), name="attention", flops=4.0 * self.B * nh * T * T * d)
         self.plan.flops += 4.0 * self.B * nh * T * T * d
         w_o = ab.attn.out_proj.weight.detach().reshape(E, E, 1, 1)
         out, st = pb.conv(att, x.H, x.W, w_o, ab.attn.out_proj.bias, x.t, float(ab.scale), True)

@@ -304,7 +304,7 @@ class LayoutUnetPlan:
         self.attn_consts.append((ab, res_key, bufs))
         att = plan.f16(B, T, C)
         d = C // nh
-        plan.add(self.lib.attention_oa, _ptr(qkv), _ptr(bufs["pos_p"]), _ptr(bufs["kl"]), _ptr(bufs["pos_l"]),
+        plan.add(self.lib.flash_attention_oa, _ptr(qkv), _ptr(bufs["pos_p"]), _ptr(bufs["kl"]), _ptr(bufs["pos_l"]),
                  _ptr(bufs["vl"]), _ptr(att), x.W, plan.parts, B, C, nh, T, L2, 1.0 / math.sqrt(2 * d), name="attention_oa",
                  flops=2.0 * B * nh * T * (T + L2) * (3 * d))
         plan.flops += 2.0 * B * nh * T * (T + L2) * (3 * d)

@@ -287,6 +287,14 @@ class EmulatedLib:
             to_slab(self._split(o, parts).view(parts, B, Tq // out_w, out_w, ldo)))
         return 0
 
+    def flash_attention(self, qkv, E, out, out_w, parts, B, heads, T, scale, stream):
+        d = E // heads
+        return self.attention(qkv, 3 * E, 0, qkv, 3 * E, E, qkv, 3 * E, 2 * E, out, E, out_w, parts, B, heads, T, T, d, d,
+                              scale, stream)
+
+    def flash_attention_oa(self, *a):
+        return self.attention_oa(*a)
+
     def sampler_update(self, x_t, pred, noise, coef, x_s, B, n, mode, objective, clip, stream):
         self._rec("sampler_update")
         xt, pr = f32(x_t, B, n).clone(), f32(pred, B, n)

@@ -306,3 +306,31 @@ def test_attention_oa(parts, C, T, W):
                             heads, T, L2, 1 / math.sqrt(64)])
     g, c = h.out(out)
     assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("E,heads,T,W", [(512, 8, 512, 128), (256, 8, 512, 128), (256, 8, 128, 128), (512, 8, 200, 40)])
+def test_flash_attention(parts, E, heads, T, W):
+    h = Both()
+    B = 2
+    d = E // heads
+    qkv = h.t(randn(B, T, 3 * E, seed=1))
+    out = h.t(torch.zeros(parts, B, T // W, E // 8, W, 8, dtype=torch.float16))
+    h.call("flash_attention", [("t", qkv), E, ("t", out), W, parts, B, heads, T, 1 / math.sqrt(d)])
+    g, c = h.out(out)
+    assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)
+
+
+@pytest.mark.parametrize("parts", [2, 1])
+@pytest.mark.parametrize("C,T,W", [(256, 2048, 256), (512, 512, 128)])
+def test_flash_attention_oa(parts, C, T, W):
+    h = Both()
+    B, L2 = 2, 13
+    qkv = h.t(randn(B, T, 3 * C, seed=1))
+    pos_p = h.t(randn(B, T, C, seed=2))
+    kl, pos_l, vl = h.t(randn(B, L2, C, seed=3)), h.t(randn(B, L2, C, seed=4)), h.t(randn(B, L2, C, seed=5))
+    out = h.t(torch.zeros(parts, B, T // W, C // 8, W, 8, dtype=torch.float16))
+    h.call("flash_attention_oa", [("t", qkv), ("t", pos_p), ("t", kl), ("t", pos_l), ("t", vl), ("t", out), W, parts, B,
+                                  C, C // 32, T, L2, 1 / math.sqrt(64)])
+    g, c = h.out(out)
+    assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)

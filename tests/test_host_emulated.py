@@ -101,3 +101,19 @@ def test_tile_picker_respects_kernel_limits():
                     bn, rows = pick_tile(B, H, W, C, taps, parts)
                     assert C % bn == 0 and H % rows == 0
                     assert rows * bn * (2 if (parts == 2 and bn == 64) else 1) <= 256
+
+
+@pytest.mark.parametrize("nres,jump", [(1, 1), (2, 2)])
+def test_repaint_matches_reference(emu, nres, jump):
+    """RePaint loop (continuous_time.py:262-319) against the reference run stored in tests/golden/repaint_mini.npz
+    (generated with the same CPU generator, so the whole noise stream is identical)."""
+    res, nres_blocks, _ = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres_blocks)
+    ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type="eps", noise_schedule="cosine")
+    g = torch.Generator().manual_seed(31)
+    known = torch.rand(2, 2, 8, 1024, generator=g) * 2 - 1
+    mask = (torch.rand(2, 1, 8, 1024, generator=g) > 0.5).float()
+    x = ddpm.repaint(known, mask, num_steps=2, num_resample_steps=nres, jump_length=jump, progress=False,
+                     rng=torch.Generator().manual_seed(55))
+    ref = torch.from_numpy(golden("repaint_mini")[f"repaint_{nres}_{jump}"])
+    assert rel_l2(x, ref) < 1e-3

@@ -75,7 +75,7 @@ def test_plan_matches_reference(emu, name, cin, autoreg):
     x, t = inputs()
     y = m(x, {"time_condition": t, "other_condition": cond})
     assert rel_l2(y, torch.from_numpy(GOLD[f"{name}_y"])) < 2e-5
-    assert emu.calls.count("attention_oa") == 11
+    assert emu.calls.count("attention_oa") == 11      # via flash_attention_oa
     assert abs(m.get_plan(1).plan.flops / 1e9 - 255.9) < 6.0       # 255.9 GFLOP / sample-step
 
 

@@ -101,6 +101,21 @@ def run_case(c):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     res["ms"] = ms
+    # in-kernel cycle breakdown (one extra launch with the debug counters on)
+    dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    lib.conv_set_debug(dbg.data_ptr())
+    lib.conv_tc(a.data_ptr(), wp.data_ptr(), 0, 0, 1.0, 1.0 / wscale, out.data_ptr(), 0, B, H, W, Cin, Cout, taps, 1,
+                bn, rows, parts, s)
+    torch.cuda.synchronize()
+    lib.conv_set_debug(0)
+    d = dbg.view(148, 8).double()
+    act = d[:, 0] > 0
+    if act.any():
+        d = d[act]
+        names = ["mma_total", "wait_full_a", "wait_full_b", "wait_acc_empty", "epi_total", "epi_wait_acc_full",
+                 "prod_wait_empty_a", "prod_wait_empty_b"]
+        res["cycles_mean"] = {n_: round(float(d[:, i].mean())) for i, n_ in enumerate(names)}
+        res["cycles_max_cta"] = {n_: round(float(d[:, i].max())) for i, n_ in enumerate(names)}
     res["tflops_algorithmic"] = 2.0 * B * H * W * taps * Cin * Cout / ms / 1e9
     print(json.dumps(res))
 
