@@ -79,3 +79,37 @@ def test_depth_to_xyz_vs_numpy():
     # the fused kernel equals the reference's three-call chain
     chain = lu.to_xyz(lu.revert_depth(lu.denormalize(x.cuda())))
     assert torch.allclose(chain, xyz, rtol=2e-5, atol=2e-4)
+
+
+def test_rollout_glue_on_device():
+    """delete_fg_points / extract_object_points / get_next_frame_points (pipe_related.py:54-68,243-288) against a
+    NumPy restatement built on the C oracle."""
+    from lidarcrafter_b200 import rollout
+    rs = np.random.RandomState(1)
+    boxes = _boxes(rs, 6)
+    pts = synth_sweep(4)
+    pts[:3000, :3] = (boxes[rs.randint(0, 6, 3000), :3] + rs.normal(0, 1.0, (3000, 3))).astype(np.float32)
+    tp, tb = torch.from_numpy(pts).cuda(), torch.from_numpy(boxes).cuda()
+    big = boxes.copy(); big[:, 3:6] += np.float32(0.2)
+    m = LO.points_in_boxes(pts[:, :3], big)
+    bg = rollout.delete_fg_points(tp, tb).cpu().numpy()
+    assert np.array_equal(bg, pts[m.sum(0) == 0])
+    objs, inten = rollout.extract_object_points(tp, tb)
+    for k in range(6):
+        sel = pts[m[k] > 0]
+        assert objs[k].shape[0] == sel.shape[0] and np.array_equal(inten[k].cpu().numpy(), sel[:, 3])
+        c, s = np.cos(-boxes[k, 6]), np.sin(-boxes[k, 6])
+        ref = (sel[:, :3] - boxes[k, :3]) @ np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]], np.float32)
+        assert np.allclose(objs[k].cpu().numpy(), ref, atol=1e-4)
+    T = rollout.compute_inter_frame_transforms(np.array([[0.02, 0.5]]))[0]
+    nxt = rollout.get_next_frame_points(torch.from_numpy(bg).cuda(), objs, inten, tb, T).cpu().numpy()
+    # oracle: warp in fp64, project with the C oracle, drop masked / empty pixels, paste the objects
+    h = np.concatenate([bg[:, :3].astype(np.float64), np.ones((len(bg), 1))], 1)
+    w = (T @ h.T).T
+    w[:, 3] = bg[:, 3]
+    img, _, _ = LO.range_project(w.astype(np.float32))
+    img = img * img[..., 5:6]
+    p = img[..., :4].reshape(-1, 4)
+    p = p[np.linalg.norm(p[:, :3], axis=1) > 1e-2]
+    assert nxt.shape[0] == p.shape[0] + sum(o.shape[0] for o in objs)
+    assert np.array_equal(nxt[:p.shape[0]], p)
