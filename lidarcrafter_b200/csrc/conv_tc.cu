@@ -21,7 +21,8 @@
 //     no im2col copies, no 9x re-reads, no swizzle.
 //   * B (weights): host-prepacked tiles in exactly the shared-memory image, one cp.async.bulk per (chunk, filter row).
 //   * warp roles: 0-3 epilogue (TMEM -> regs -> smem transpose -> coalesced fp32 store + residual + per-channel
-//     sum / sum-of-squares for the next GroupNorm), 4 producer (TMA bulk copies, mbarrier tx bytes),
+//     sum / sum-of-squares for the next GroupNorm), 4 activation producer and 6 weight producer (TMA bulk copies,
+//     mbarrier tx bytes; independent warps so a full weight ring never stalls the activation prefetch),
 //     5 MMA issuer (single thread, tcgen05.mma kind::f16, M=128 N=BN K=16) + TMEM owner.
 #include "common.cuh"
 
@@ -50,7 +51,7 @@ __device__ unsigned long long* g_conv_dbg = nullptr;
 #define DBG_ACC(slot) do { if (dbg) dbg_acc[slot] += clock64() - t0__; } while (0)
 
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 224;   // 4 epilogue warps + A producer + MMA issuer + B producer
 
 template <int BN, int R, int TAPS, int NP>
 struct ConvCfg {
@@ -70,14 +71,16 @@ struct ConvCfg {
     static constexpr int B_TAP = NP * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
     static constexpr int EPI = 4 * 32 * 36 * 4;
-    static constexpr int BUDGET = 227 * 1024 - EPI - 256;
-    static constexpr int SB = 4;
-    static constexpr int SA = (BUDGET - SB * B_STAGE) / A_STAGE >= 4 ? 4 : ((BUDGET - SB * B_STAGE) / A_STAGE >= 3 ? 3 : 2);
+    static constexpr int BUDGET = 227 * 1024 - EPI - 320;
+    static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= 3 ? 3 : 2;
+    static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
+    static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;   // weight ring: as deep as shared memory allows
+    static_assert(SB >= 3, "weight ring too shallow");
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI;
-    static constexpr int SMEM = OFF_BAR + 256;
+    static constexpr int SMEM = OFF_BAR + 320;
     // MERGE (fp16x3 with BN = 64): the weight tile keeps hi and lo rows adjacent ([KG][hi|lo][BN][8]) so that
     // a_hi x [w_hi ; w_lo] is ONE N = 128 MMA (A is fetched from shared memory once for 128 accumulator columns
     // instead of twice) and only a_lo x w_hi remains an N = 64 MMA: 64 + 48 instead of 3 x 48 tensor-pipe cycles.
@@ -98,13 +101,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + C::OFF_BAR;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 192);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 288);
 #define FULL_A(s) (bar0 + 8u * (s))
 #define EMPTY_A(s) (bar0 + 32u + 8u * (s))
 #define FULL_B(s) (bar0 + 64u + 8u * (s))
-#define EMPTY_B(s) (bar0 + 96u + 8u * (s))
-#define ACC_FULL(s) (bar0 + 128u + 8u * (s))
-#define ACC_EMPTY(s) (bar0 + 144u + 8u * (s))
+#define EMPTY_B(s) (bar0 + 160u + 8u * (s))
+#define ACC_FULL(s) (bar0 + 256u + 8u * (s))
+#define ACC_EMPTY(s) (bar0 + 272u + 8u * (s))
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.Cout / BN, WT = p.W / PIX, HG = p.H / R;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 
     if (warp == 4) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
-        uint32_t ia = 0, ib = 0;
+        uint32_t ia = 0;
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             const int hg = t % HG;
             const int b = t / HG;
             const int w0 = wt * PIX, h0 = hg * R;
-            const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (NP * BN * KC);
+            (void)nt;
             for (int c = 0; c < NCH; ++c) {
                 {
                     const int s = ia % C::SA;
@@ -185,26 +188,33 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     }
                     ++ia;
                 }
-                if (lane == 0) {
-                    for (int dy = 0; dy < C::TG; ++dy, ++ib) {
-                        const int s = ib % C::SB;
-                        const uint32_t ph = (ib / C::SB) & 1;
-                        {
-                            DBG_T0();
-                            mbar_wait(EMPTY_B(s), ph ^ 1);
-                            DBG_ACC(7);
-                        }
-                        mbar_expect_tx(FULL_B(s), C::B_STAGE);
-                        bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE,
-                                      wsrc + (size_t)(c * C::TG + dy) * (C::B_STAGE / 2), C::B_STAGE, FULL_B(s));
-                    }
-                }
                 __syncwarp();
             }
         }
-        if (dbg && lane == 0) {
-            dbg[blockIdx.x * 8 + 6] = dbg_acc[6];
-            dbg[blockIdx.x * 8 + 7] = dbg_acc[7];
+        if (dbg && lane == 0) dbg[blockIdx.x * 8 + 6] = dbg_acc[6];
+    } else if (warp == 6) {
+        // ------------------------------ weight producer: one thread, TMA-engine bulk copies ------------------------------
+        if (lane == 0) {
+            uint32_t ib = 0;
+            unsigned long long* dbg = g_conv_dbg;
+            unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int nt = tile % NT;
+                const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (NP * BN * KC);
+                for (int q = 0; q < NCH * C::TG; ++q, ++ib) {
+                    const int s = ib % C::SB;
+                    const uint32_t ph = (ib / C::SB) & 1;
+                    {
+                        DBG_T0();
+                        mbar_wait(EMPTY_B(s), ph ^ 1);
+                        DBG_ACC(7);
+                    }
+                    mbar_expect_tx(FULL_B(s), C::B_STAGE);
+                    bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE, wsrc + (size_t)q * (C::B_STAGE / 2), C::B_STAGE,
+                                  FULL_B(s));
+                }
+            }
+            if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[7];
         }
     } else if (warp == 5) {
         // ------------------------------ MMA issuer: one thread ------------------------------
