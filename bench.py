@@ -272,8 +272,11 @@ def main():
             if name == "conv_tc":      # args: a, w, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts
                 key = "conv %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (a[9], a[10], a[11], a[12], a[13], a[15], a[16])
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += 1
+            elif name == "gn_act_f16":  # args: x0, C0, x1, C1, st0, st1, g, b, ada, stride, groups, eps, silu, y, parts, B, H, W
+                key = "gn_act %2dx%-4d C%-4d norm%d" % (a[16], a[17], a[1] + a[3], 1 if a[4] else 0)
+                d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += by_k / 1e3; d[2] += 1
         for key, v in sorted(shapes.items(), key=lambda kv: -kv[1][0]):
-            print(f"    {key}  n={v[2]:2d} {v[0]:7.3f} ms  {v[1] / max(v[0], 1e-9) / 1e9:7.1f} TFLOP/s (algorithmic)", file=sys.stderr)
+            print(f"    {key}  n={v[2]:2d} {v[0]:7.3f} ms  {v[1] / max(v[0], 1e-9) / 1e9:7.1f} TFLOP/s | TB/s (algorithmic)", file=sys.stderr)
         for name, v in sorted(by.items(), key=lambda kv: -kv[1][0]):
             print(f"  {name:20s} n={v[3]:4d} {v[0]:8.3f} ms  {100 * v[0] / tot_ms:5.1f}%  "
                   f"{v[1] / max(v[0], 1e-9) / 1e9:8.1f} TFLOP/s  {v[2] / max(v[0], 1e-9) / 1e6:8.1f} GB/s", file=sys.stderr)

@@ -70,7 +70,8 @@ struct ConvCfg {
     static constexpr int B_PART = BN * KC * 2;
     static constexpr int B_TAP = NP * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
-    static constexpr int EPI = 4 * 32 * 36 * 4;
+    static constexpr int EPI_STG = 4 * 32 * 36 * 4;            // per-warp transpose staging
+    static constexpr int EPI = EPI_STG + 4 * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BUDGET = 227 * 1024 - EPI - 320;
     static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= 3 ? 3 : 2;
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
@@ -113,6 +114,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     const int NT = p.Cout / BN, WT = p.W / PIX, HG = p.H / R;
     const int NCH = p.Cin / KC;
     const int CG = p.Cin / 8;
+    // contiguous chunk of tiles per CTA (same image rows / same batch index: L2 locality, few statistic flushes)
+    const int tiles_per_cta = (p.n_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_lo = blockIdx.x * tiles_per_cta;
+    const int tile_hi = min(tile_lo + tiles_per_cta, p.n_tiles);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::SA; ++s) {
@@ -141,14 +146,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
             int t = tile;
-            const int nt = t % NT; t /= NT;
             const int wt = t % WT; t /= WT;
-            const int hg = t % HG;
-            const int b = t / HG;
+            const int hg = t % HG; t /= HG;
+            const int b = t / NT;
             const int w0 = wt * PIX, h0 = hg * R;
-            (void)nt;
             for (int c = 0; c < NCH; ++c) {
                 {
                     const int s = ia % C::SA;
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             uint32_t ib = 0;
             unsigned long long* dbg = g_conv_dbg;
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int nt = tile % NT;
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+                const int nt = (tile / (WT * HG)) % NT;
                 const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (NP * BN * KC);
                 for (int q = 0; q < NCH * C::TG; ++q, ++ib) {
                     const int s = ib % C::SB;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             unsigned long long* dbg = g_conv_dbg;
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const long long t_start = dbg ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
                 const uint32_t buf = it & 1;
                 {
                     DBG_T0();
@@ -302,13 +305,44 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_start = dbg ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        float* sst = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG) + warp * (2 * BN);   // [2][BN] of this warp
+        for (int i = lane; i < 2 * BN; i += 32) sst[i] = 0.f;
+        __syncwarp();
+        int cur_b = -1, cur_nt = -1;
+        // flush the CTA's per-channel partial sums: ONE fp64 atomic pair per channel per (batch, n-tile) change instead of
+        // one per warp x row x tile (same-address atomics serialise at L2: 1024 of them per address cost ~100 us)
+        auto flush_stats = [&]() {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (cur_b >= 0) {
+                float* all = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG);
+                for (int ch = threadIdx.x; ch < BN; ch += 128) {
+                    float a = 0.f, q = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        a += all[w * 2 * BN + ch];
+                        q += all[w * 2 * BN + BN + ch];
+                        all[w * 2 * BN + ch] = 0.f;
+                        all[w * 2 * BN + BN + ch] = 0.f;
+                    }
+                    double* st = p.stats + ((size_t)cur_b * p.Cout + cur_nt * BN + ch) * 2;
+                    atomicAdd(st, (double)a);
+                    atomicAdd(st + 1, (double)q);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             int t = tile;
-            const int nt = t % NT; t /= NT;
             const int wt = t % WT; t /= WT;
-            const int hg = t % HG;
-            const int b = t / HG;
+            const int hg = t % HG; t /= HG;
+            const int nt = t % NT;
+            const int b = t / NT;
             const int w0 = wt * PIX, h0 = hg * R, n0 = nt * BN;
+            if (p.stats && (b != cur_b || nt != cur_nt)) {
+                flush_stats();
+                cur_b = b;
+                cur_nt = nt;
+            }
             const uint32_t buf = it & 1;
             {
                 DBG_T0();
@@ -366,12 +400,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                             s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
                             s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                         }
-                        if (rb == 0) {
-                            double* st = p.stats + ((size_t)b * p.Cout + nb) * 2;
+                        if (rb == 0) {   // 8 lanes x 4 channels = the 32 channels of this slice; warp-private rows
+                            const int ch = sl * 32 + col4 * 4;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                atomicAdd(st + 2 * e, (double)s1[e]);
-                                atomicAdd(st + 2 * e + 1, (double)s2[e]);
+                                sst[ch + e] += s1[e];
+                                sst[BN + ch + e] += s2[e];
                             }
                         }
                     }
@@ -379,6 +413,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 }
             }
         }
+        if (p.stats) flush_stats();
         if (dbg && threadIdx.x == 0) {
             dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
             dbg[blockIdx.x * 8 + 5] = dbg_acc[5];
@@ -413,7 +448,9 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
         attr_set = true;
     }
     p.n_tiles = (p.W / PIX) * (p.H / R) * p.B * (p.Cout / BN);
-    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    const int tpc = (p.n_tiles + grid - 1) / grid;
+    grid = (p.n_tiles + tpc - 1) / tpc;     // no empty CTAs with contiguous chunks
     conv_tc_kernel<BN, R, TAPS, NP><<<grid, CONV_THREADS, C::SMEM, st>>>(p);
     B200_CHECK_LAUNCH();
     return B200_OK;
