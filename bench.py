@@ -275,7 +275,30 @@ def main():
             elif name == "gn_act_f16":  # args: x0, C0, x1, C1, st0, st1, g, b, ada, stride, groups, eps, silu, y, parts, B, H, W
                 key = "gn_act %2dx%-4d C%-4d norm%d" % (a[16], a[17], a[1] + a[3], 1 if a[4] else 0)
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += by_k / 1e3; d[2] += 1
+        # in-kernel wait breakdown of the conv launches inside the real plan (b200_conv_set_debug counters)
+        lib = plan.lib
+        dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+        waits = {}
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
+            if name != "conv_tc":
+                continue
+            dbg.zero_()
+            lib.conv_set_debug(dbg.data_ptr())
+            fn(*a, st)
+            torch.cuda.synchronize(dev)
+            lib.conv_set_debug(0)
+            d = dbg.view(148, 8).double()
+            d = d[d[:, 0] > 0]
+            key = "conv %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (a[9], a[10], a[11], a[12], a[13], a[15], a[16])
+            w = waits.setdefault(key, [0.0] * 5)
+            w[0] += float(d[:, 0].mean()); w[1] += float(d[:, 1].mean()); w[2] += float(d[:, 2].mean())
+            w[3] += float(d[:, 3].mean()); w[4] += float(d[:, 5].mean())
         for key, v in sorted(shapes.items(), key=lambda kv: -kv[1][0]):
+            if key in waits:
+                w = waits[key]
+                key = key + "  [mma-thread waits: A %.0f%% B %.0f%% acc %.0f%%; epi idle %.0f%%]" % (
+                    100 * w[1] / w[0], 100 * w[2] / w[0], 100 * w[3] / w[0], 100 * w[4] / w[0])
             print(f"    {key}  n={v[2]:2d} {v[0]:7.3f} ms  {v[1] / max(v[0], 1e-9) / 1e9:7.1f} TFLOP/s | TB/s (algorithmic)", file=sys.stderr)
         for name, v in sorted(by.items(), key=lambda kv: -kv[1][0]):
             print(f"  {name:20s} n={v[3]:4d} {v[0]:8.3f} ms  {100 * v[0] / tot_ms:5.1f}%  "

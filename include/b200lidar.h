@@ -77,11 +77,13 @@ int b200_conv_ffma(const void* a, const void* w16, const float* bias, const floa
  *   gamma/beta: [C0+C1] or NULL;  ada: fp32, scale at ada[b*ada_stride + c], shift at
  *               ada[b*ada_stride + (C0+C1) + c], NULL => none;  silu: 1 = apply x*sigmoid(x)
  *   y        : fp16 slab-major [parts][B][H][(C0+C1)/8][W][8] (the conv operand layout);
- *              parts = 2 also writes the residual lo = fp16(v - fp32(hi))                                */
+ *              parts = 2 also writes the residual lo = fp16(v - fp32(hi))
+ *   y_raw    : optional second output (same layout): the UN-normalised concatenated input as a conv operand
+ *              (input of the block's 1x1 skip conv, efficient_unet.py:92-96) -- one read of x feeds both     */
 int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                     const double* stats1, const float* gamma, const float* beta, const float* ada,
-                    int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
-                    void* stream);
+                    int ada_stride, int groups, float eps, int silu, void* y, void* y_raw, int parts, int B,
+                    int H, int W, void* stream);
 /* fp32 NHWC variant y = act(GroupNorm(x)) (no concat / AdaGN): feeds the FIR resampler of the up/down
  * ResBlocks (layout_unet_v1.py:229-235) and the final `out` head (layout_unet_v1.py:899-900)        */
 int b200_gn_act_f32(const float* x, const double* stats, const float* gamma, const float* beta, int groups,

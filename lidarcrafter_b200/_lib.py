@@ -28,7 +28,7 @@ PROTOTYPES = {
     "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, F, P]),
     "b200_pack_conv_weight_plain": (I, [P, P, I, I, I, I, F, P]),
     "b200_conv_ffma": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, P]),
-    "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, I, I, I, I, P]),
+    "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, I, I, I, I, P]),
     "b200_gn_act_f32": (I, [P, P, P, P, I, F, I, P, I, I, I, P]),
     "b200_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
     "b200_flash_attention": (I, [P, I, P, I, I, I, I, I, F, P]),

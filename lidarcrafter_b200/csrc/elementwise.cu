@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                                                      const double* __restrict__ st1, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const float* __restrict__ ada,
                                                      int ada_stride, int groups, float eps, int silu,
-                                                     __half* __restrict__ y, size_t lo_off, int HW, int W,
-                                                     int pix_per_block) {
+                                                     __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
+                                                     int HW, int W, int pix_per_block) {
     __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
     __shared__ double s_st[2 * GN_MAX_C];
     __shared__ float s_mean[64], s_rstd[64];
@@ -107,6 +107,22 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
         const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
         float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         __half2 h[4];
+        const int hh = pl / W, ww = pl - hh * W;
+        const size_t oi = ((((size_t)b * Himg + hh) * c8n + c8) * W + ww) * 8;
+        if (y_raw) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(y_raw + oi) = *reinterpret_cast<const uint4*>(h);
+            if (lo_off) {
+                __half2 l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 hf = __half22float2(h[e]);
+                    l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                }
+                *reinterpret_cast<uint4*>(y_raw + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float t = fmaf(v[e], s_a[c + e], s_b[c + e]);
@@ -115,8 +131,6 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-        const int hh = pl / W, ww = pl - hh * W;
-        const size_t oi = ((((size_t)b * Himg + hh) * c8n + c8) * W + ww) * 8;
         *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
         if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
             __half2 l[4];
@@ -516,8 +530,8 @@ static bool c4_ok(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) ==
 
 extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                                const double* stats1, const float* gamma, const float* beta, const float* ada,
-                               int ada_stride, int groups, float eps, int silu, void* y, int parts, int B, int H, int W,
-                               void* stream) {
+                               int ada_stride, int groups, float eps, int silu, void* y, void* y_raw, int parts, int B,
+                               int H, int W, void* stream) {
     B200_CHECK_ARG(parts == 1 || parts == 2);
     B200_CHECK_ARG(W % 8 == 0);
     const int HW = H * W;
@@ -536,7 +550,7 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
     dim3 grid(cdiv(HW, ppb), B);
     gn_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
-                                                          groups, eps, silu, (__half*)y,
+                                                          groups, eps, silu, (__half*)y, (__half*)y_raw,
                                                           parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW, W, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;

@@ -324,15 +324,17 @@ class EfficientUNetPlan:
         pb, m = self.pb, self.m
         G, eps = m.gn_num_groups, m.gn_eps
         H, W = srcs[0].H, srcs[0].W
-        a1 = pb.gn_act(srcs, rb.norm1.weight, rb.norm1.bias, G, eps, True)
+        has_skip = not isinstance(rb.skip, nn.Identity)
+        a1 = pb.gn_act(srcs, rb.norm1.weight, rb.norm1.bias, G, eps, True, also_raw=has_skip)
+        if has_skip:
+            a1, x16 = a1
         hmid, st_h = pb.conv(a1, H, W, rb.conv1.weight, rb.conv1.bias, None, 1.0, True)
         a2 = pb.gn_act([Act(hmid, H, W, rb.cout, st_h)], None, None, G, eps, True, ada=self.ada, ada_stride=self.P,
                        ada_off=self.ada_off[id(rb)])
-        if isinstance(rb.skip, nn.Identity):
+        if not has_skip:
             assert len(srcs) == 1
             res = srcs[0].t
         else:
-            x16 = pb.cast16(srcs)
             res, _ = pb.conv(x16, H, W, rb.skip.weight, rb.skip.bias, None, 1.0, False)
         out, st = pb.conv(a2, H, W, rb.conv2.weight, rb.conv2.bias, res, float(rb.scale), True)
         return Act(out, H, W, rb.cout, st)

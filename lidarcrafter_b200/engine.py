@@ -206,12 +206,15 @@ class PlanBuilder:
 
     # ---- GroupNorm(+AdaGN)+SiLU -> fp16 operand ----
     def gn_act(self, srcs: list[Act], gamma, beta, groups: int, eps: float, silu: bool, ada=None, ada_stride=0,
-               ada_off=0, normalize: bool = True) -> torch.Tensor:
+               ada_off=0, normalize: bool = True, also_raw: bool = False):
+        """-> fp16 conv operand; with ``also_raw`` additionally the un-normalised input as a second operand
+        (returns (y, y_raw)): one pass over x feeds norm1->conv1 and the 1x1 skip conv."""
         a0 = srcs[0]
         a1 = srcs[1] if len(srcs) > 1 else None
         C = a0.C + (a1.C if a1 else 0)
         HW = a0.H * a0.W
         y = self.p.f16(self.B, HW, C)
+        y_raw = self.p.f16(self.B, HW, C) if also_raw else None
         g = None if gamma is None else gamma.detach().float().contiguous()
         b = None if beta is None else beta.detach().float().contiguous()
         self.p.bufs += [g, b]
@@ -220,9 +223,10 @@ class PlanBuilder:
         ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * ada_off
         self.p.add(self.lib.gn_act_f16, _ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0,
                    _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b),
-                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), self.p.parts, self.B, a0.H, a0.W,
-                   name="gn_act_f16", nbytes=self.B * HW * C * (4.0 + 2.0 * self.p.parts))
-        return y
+                   ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), _ptr(y_raw), self.p.parts, self.B,
+                   a0.H, a0.W, name="gn_act_f16",
+                   nbytes=self.B * HW * C * (4.0 + 2.0 * self.p.parts * (2 if also_raw else 1)))
+        return (y, y_raw) if also_raw else y
 
     def cast16(self, srcs: list[Act]) -> torch.Tensor:
         return self.gn_act(srcs, None, None, 1, 0.0, False, normalize=False)

@@ -276,7 +276,10 @@ class LayoutUnetPlan:
             H, W = tr.H, tr.W
             res = xr.t
         else:
-            a1 = pb.gn_act(srcs, n1.weight, n1.bias, GN_GROUPS, GN_EPS, True)
+            has_skip = not isinstance(rb.skip_connection, nn.Identity)
+            a1 = pb.gn_act(srcs, n1.weight, n1.bias, GN_GROUPS, GN_EPS, True, also_raw=has_skip)
+            if has_skip:
+                a1, x16 = a1
             res = None
         hmid, st_h = pb.conv(a1, H, W, conv1.weight, conv1.bias, None, 1.0, True)
         a2 = pb.gn_act([Act(hmid, H, W, rb.cout, st_h)], n2.weight, n2.bias, GN_GROUPS, GN_EPS, True, ada=self.ada,
@@ -286,7 +289,6 @@ class LayoutUnetPlan:
                 assert len(srcs) == 1
                 res = x0.t
             else:
-                x16 = pb.cast16(srcs)
                 res, _ = pb.conv(x16, H, W, rb.skip_connection.weight, rb.skip_connection.bias, None, 1.0, False)
         out, st = pb.conv(a2, H, W, conv2.weight, conv2.bias, res, 1.0, True)
         return Act(out, H, W, rb.cout, st)

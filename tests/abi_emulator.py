@@ -136,14 +136,16 @@ class EmulatedLib:
         return 0
 
     # ---- GN / stats ----
-    def gn_act_f16(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, y, parts, B, H, W,
-                   stream):
+    def gn_act_f16(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, y, y_raw, parts, B,
+                   H, W, stream):
         self._rec("gn_act_f16")
         HW = H * W
         x = f32(x0, B, HW, C0)
         if C1:
             x = torch.cat([x, f32(x1, B, HW, C1)], dim=-1)
         C = C0 + C1
+        if y_raw:
+            f16(y_raw, parts, B, H, C // 8, W, 8).copy_(to_slab(self._split(x, parts).view(parts, B, H, W, C)))
         if st0:
             st = f64(st0, B, C0, 2)
             if C1:

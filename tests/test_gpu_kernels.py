@@ -175,14 +175,19 @@ def test_gn_act(parts, C0, C1, groups, affine, ada, silu, norm):
     P = 2 * C + 24
     adat = h.t(0.3 * randn(B, P, seed=5))
     y = h.t(torch.zeros(parts, B, H, C // 8, W, 8, dtype=torch.float16))
+    yr = h.t(torch.zeros(parts, B, H, C // 8, W, 8, dtype=torch.float16))
     # ada pointer offset of 8 floats inside the row, as the planner does
     args = [("t", ix0), C0, ("t", ix1) if C1 else None, C1, ("t", s0) if norm else None,
             ("t", s1) if (norm and C1) else None, ("t", gam) if affine else None, ("t", bet) if affine else None,
-            ("t", adat) if ada else None, P, groups, 1e-6, 1 if silu else 0, ("t", y), parts, B, H, W]
+            ("t", adat) if ada else None, P, groups, 1e-6, 1 if silu else 0, ("t", y), ("t", yr) if C1 else None, parts,
+            B, H, W]
     h.call("gn_act_f16", args)
     g, c = h.out(y)
     full_g, full_c = g.float().sum(0), c.float().sum(0)
     assert rel(full_g, full_c) < (3e-6 if parts == 2 else 6e-4)
+    if C1:
+        g, c = h.out(yr)
+        assert torch.equal(g, c)           # raw operand: exact fp16 split of the concatenated input
 
 
 def test_channel_stats_and_fir():
