@@ -51,7 +51,8 @@ __device__ unsigned long long* g_conv_dbg = nullptr;
 #define DBG_ACC(slot) do { if (dbg) dbg_acc[slot] += clock64() - t0__; } while (0)
 
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
-constexpr int CONV_THREADS = 224;   // 4 epilogue warps + A producer + MMA issuer + B producer
+constexpr int CONV_THREADS = 384;   // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: A producer; 5: MMA; 6: B producer
+constexpr int EPI_WARPS = 8;
 
 template <int BN, int R, int TAPS, int NP>
 struct ConvCfg {
@@ -70,8 +71,8 @@ struct ConvCfg {
     static constexpr int B_PART = BN * KC * 2;
     static constexpr int B_TAP = NP * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
-    static constexpr int EPI_STG = 4 * 32 * 36 * 4;            // per-warp transpose staging
-    static constexpr int EPI = EPI_STG + 4 * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
+    static constexpr int EPI_STG = EPI_WARPS * 32 * 36 * 4;            // per-warp transpose staging
+    static constexpr int EPI = EPI_STG + EPI_WARPS * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BUDGET = 227 * 1024 - EPI - 320;
     static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= 3 ? 3 : 2;
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(ACC_FULL(s), 1);
-            mbar_init(ACC_EMPTY(s), 128);
+            mbar_init(ACC_EMPTY(s), EPI_WARPS * 32);
         }
         fence_barrier_init();
     }
@@ -296,29 +297,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
             }
         }
-    } else {
-        // ------------------------------ epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ------------------------------
-        float* stg = reinterpret_cast<float*>(smem + C::OFF_EPI) + warp * (32 * 36);
+    } else if (warp != 7) {
+        // ------------------------------ epilogue: warps 0-3 and 8-11; warp w reads TMEM lanes 32*(w%4) .. +31 ------------------------------
+        // the two warps of a lane quarter split the (row, 32-column slice) work items of a tile between them
+        const int ew = warp < 4 ? warp : warp - 4;       // 0..7: epilogue warp index
+        const int quarter = warp & 3, egroup = ew >> 2;  // TMEM lane quarter, work-item parity
+        float* stg = reinterpret_cast<float*>(smem + C::OFF_EPI) + ew * (32 * 36);
         const int col4 = lane & 7, rb = lane >> 3;
         const float scale = p.out_scale, winv = p.w_inv;
         uint32_t it = 0;
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_start = dbg ? clock64() : 0;
-        float* sst = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG) + warp * (2 * BN);   // [2][BN] of this warp
+        float* sst = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG) + ew * (2 * BN);   // [2][BN] of this warp
         for (int i = lane; i < 2 * BN; i += 32) sst[i] = 0.f;
         __syncwarp();
         int cur_b = -1, cur_nt = -1;
         // flush the CTA's per-channel partial sums: ONE fp64 atomic pair per channel per (batch, n-tile) change instead of
         // one per warp x row x tile (same-address atomics serialise at L2: 1024 of them per address cost ~100 us)
         auto flush_stats = [&]() {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (cur_b >= 0) {
                 float* all = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG);
-                for (int ch = threadIdx.x; ch < BN; ch += 128) {
+                for (int ch = ew * 32 + lane; ch < BN; ch += EPI_WARPS * 32) {
                     float a = 0.f, q = 0.f;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
+                    for (int w = 0; w < EPI_WARPS; ++w) {
                         a += all[w * 2 * BN + ch];
                         q += all[w * 2 * BN + BN + ch];
                         all[w * 2 * BN + ch] = 0.f;
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     atomicAdd(st + 1, (double)q);
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         };
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             int t = tile;
@@ -350,11 +354,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 DBG_ACC(5);
             }
             tc_fence_after();
-            const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
-            for (int o = 0; o < R; ++o) {
+            const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+            constexpr int NSL = BN / 32, NITEM = R * NSL;
+            for (int item = egroup; item < NITEM; item += 2) {
+                const int o = item / NSL, sl = item - o * NSL;
                 const int h = h0 + o;
-                const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + warp * 32) * p.Cout;
-                for (int sl = 0; sl < BN / 32; ++sl) {
+                const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + quarter * 32) * p.Cout;
+                {
                     float v[32];
                     tmem_ld_32x32(acc + o * C::ACC_ROW + sl * 32, v);
                     if (C::MERGE) {
@@ -363,8 +369,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += v2[j];
                     }
-                    if (o == R - 1 && sl == BN / 32 - 1) {
-                        // all TMEM reads of this accumulator set are done -> hand it back to the MMA warp
+                    if (item + 2 >= NITEM) {
+                        // this warp's TMEM reads of the accumulator set are done -> hand it back to the MMA warp
                         tc_fence_before();
                         mbar_arrive(ACC_EMPTY(buf));
                     }
