@@ -95,51 +95,67 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
     const int px = lane >> 2, g = lane & 3;
     const int cb_n = (C + 31) / 32, pb_n = np / 8;      // np is a multiple of 8 (W % 8 == 0)
     const int Himg = HW / W;
-    for (int it = warp; it < pb_n * cb_n; it += nwarps) {
-        const int cb = it / pb_n, pb = it - cb * pb_n;
-        const int c8 = cb * 4 + g;
-        if (c8 >= c8n) continue;
-        const int c = c8 * 8;
-        const int pl = p0 + pb * 8 + px;
-        const size_t pix = (size_t)b * HW + pl;
-        const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
-        const float4 v0 = *reinterpret_cast<const float4*>(src);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        __half2 h[4];
-        const int hh = pl / W, ww = pl - hh * W;
-        const size_t oi = ((((size_t)b * Himg + hh) * c8n + c8) * W + ww) * 8;
-        if (y_raw) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
+    const int n_items = pb_n * cb_n;
+    // two items per iteration: all four 16-byte loads are issued before any math (memory-level parallelism)
+    for (int it0 = warp; it0 < n_items; it0 += 2 * nwarps) {
+        float4 ld[2][2];
+        int c8s[2], pls[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * nwarps;
+            const int cb = it / pb_n, pb = it - cb * pb_n;
+            c8s[u] = cb * 4 + g;
+            pls[u] = p0 + pb * 8 + px;
+            ok[u] = it < n_items && c8s[u] < c8n;
+            if (ok[u]) {
+                const int c = c8s[u] * 8;
+                const size_t pix = (size_t)b * HW + pls[u];
+                const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
+                ld[u][0] = *reinterpret_cast<const float4*>(src);
+                ld[u][1] = *reinterpret_cast<const float4*>(src + 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const int c8 = c8s[u], c = c8 * 8, pl = pls[u];
+            float v[8] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w};
+            __half2 h[4];
+            const int hh = pl / W, ww = pl - hh * W;
+            const size_t oi = ((((size_t)b * Himg + hh) * c8n + c8) * W + ww) * 8;
+            if (y_raw) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                *reinterpret_cast<uint4*>(y_raw + oi) = *reinterpret_cast<const uint4*>(h);
+                if (lo_off) {
+                    __half2 l[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 hf = __half22float2(h[e]);
+                        l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                    }
+                    *reinterpret_cast<uint4*>(y_raw + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = fmaf(v[e], s_a[c + e], s_b[c + e]);
+                if (silu) t = silu_f(t);
+                v[e] = t;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-            *reinterpret_cast<uint4*>(y_raw + oi) = *reinterpret_cast<const uint4*>(h);
-            if (lo_off) {
+            *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
+            if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
                 __half2 l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 hf = __half22float2(h[e]);
                     l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
                 }
-                *reinterpret_cast<uint4*>(y_raw + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
+                *reinterpret_cast<uint4*>(y + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
             }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float t = fmaf(v[e], s_a[c + e], s_b[c + e]);
-            if (silu) t = silu_f(t);
-            v[e] = t;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-        *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
-        if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
-            __half2 l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 hf = __half22float2(h[e]);
-                l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-            }
-            *reinterpret_cast<uint4*>(y + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
         }
     }
 }

@@ -65,6 +65,21 @@ def weight_scale(weight: torch.Tensor) -> float:
     return float(2.0 ** (8 - math.floor(math.log2(m))))
 
 
+_TUNE_CACHE: dict = {}
+
+
+def tile_candidates(B: int, H: int, W: int, Cout: int, parts: int):
+    out = []
+    for bn in (128, 64):
+        if Cout % bn:
+            continue
+        merged = parts == 2 and bn == 64
+        for rows in (4, 2, 1):
+            if H % rows == 0 and rows * bn * (2 if merged else 1) <= 256:
+                out.append((bn, rows))
+    return out
+
+
 class PackedConv:
     """fp16 tile image of one conv's weights + fp32 bias (device)."""
 
@@ -186,7 +201,7 @@ class PlanBuilder:
         by = npix * (2.0 * self.p.parts * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
             + 2.0 * self.p.parts * taps * Cin * Cout
         if self.p.conv_impl == "tc":
-            bn, rows = pick_tile(self.B, H, W, Cout, taps, self.p.parts)
+            bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
             pc = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
             self.p.bufs.append(pc)
             self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
@@ -203,6 +218,38 @@ class PlanBuilder:
                        _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts,
                        name="conv_ffma", flops=fl, nbytes=by)
         return out, st
+
+    def tune_tile(self, a16, H, W, weight, bias, res, out):
+        """(bn, rows) of b200_conv_tc for this shape: measured once per shape on the device (CUDA events, best of the
+        candidate tiles), cached for the process; the analytic pick_tile() is only the no-GPU fallback of the planner
+        (emulator tests)."""
+        Cout, Cin, kh, kw = weight.shape
+        taps = kh * kw
+        key = (self.B, H, W, Cin, Cout, taps, self.p.parts, res is not None)
+        if key in _TUNE_CACHE:
+            return _TUNE_CACHE[key]
+        if self.p.device.type != "cuda":
+            return pick_tile(self.B, H, W, Cout, taps, self.p.parts)
+        best = None
+        packed = {}
+        for bn, rows in tile_candidates(self.B, H, W, Cout, self.p.parts):
+            if bn not in packed:
+                packed[bn] = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
+            pc = packed[bn]
+            args = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), 1.0, 1.0 / pc.wscale, _ptr(out), 0, self.B, H, W,
+                    Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
+            self.lib.conv_tc(*args)                      # warm-up (function attributes, caches)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                self.lib.conv_tc(*args)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if best is None or ms < best[0]:
+                best = (ms, bn, rows)
+        _TUNE_CACHE[key] = (best[1], best[2])
+        return _TUNE_CACHE[key]
 
     # ---- GroupNorm(+AdaGN)+SiLU -> fp16 operand ----
     def gn_act(self, srcs: list[Act], gamma, beta, groups: int, eps: float, silu: bool, ada=None, ada_stride=0,
