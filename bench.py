@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,6 +216,8 @@ def main():
         clk.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(K):
         one_step(W + i)
@@ -222,6 +226,8 @@ def main():
         dist.all_gather(out, plan.x_in)
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clocks = clk.stop() if rank == 0 else None
     if world > 1:
@@ -273,7 +279,7 @@ def main():
                 key = "conv %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (a[9], a[10], a[11], a[12], a[13], a[15], a[16])
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += 1
             elif name == "gn_act_f16":  # args: x0, C0, x1, C1, st0, st1, g, b, ada, stride, groups, eps, silu, y, parts, B, H, W
-                key = "gn_act %2dx%-4d C%-4d norm%d" % (a[16], a[17], a[1] + a[3], 1 if a[4] else 0)
+                key = "gn_act %2dx%-4d C%-4d norm%d raw%d" % (a[17], a[18], a[1] + a[3], 1 if a[4] else 0, 1 if a[14] else 0)
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += by_k / 1e3; d[2] += 1
         # in-kernel wait breakdown of the conv launches inside the real plan (b200_conv_set_debug counters)
         lib = plan.lib

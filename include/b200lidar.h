@@ -56,9 +56,13 @@ int b200_conv_set_debug(void* dbg_u64);
 /* number of fp16 elements of the packed weight image (== parts*taps*Cout*Cin) */
 size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
 /* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
- * packed fp16 tiles [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8], KC = 32 (parts 1) or 16 (parts 2) */
-int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int parts,
-                          float wscale, void* stream);
+ * packed fp16 tiles [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8] (merged mode: [..][KC/8][parts][bn][8]),
+ * KC = 32 (parts 1) or 16 (parts 2)                                                               */
+int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int rows,
+                          int parts, float wscale, void* stream);
+/* 1 if b200_conv_tc runs (bn, rows, parts) in merged mode (hi/lo weight rows adjacent: the packed image and the
+ * tile must be created with the same (bn, rows, parts))                                              */
+int b200_conv_merged(int bn, int rows, int parts);
 /* plain fp16 copy w16[parts][tap][Cout][Cin] for the CUDA-core checking kernel */
 int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, int Cin, int taps, int parts,
                                 float wscale, void* stream);

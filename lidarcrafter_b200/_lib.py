@@ -25,7 +25,8 @@ PROTOTYPES = {
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b200_conv_set_debug": (I, [P]),
     "b200_packed_weight_elems": (SZ, [I, I, I, I]),
-    "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, F, P]),
+    "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, F, P]),
+    "b200_conv_merged": (I, [I, I, I]),
     "b200_pack_conv_weight_plain": (I, [P, P, I, I, I, I, F, P]),
     "b200_conv_ffma": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, P]),
     "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, I, I, I, I, P]),
@@ -48,7 +49,7 @@ PROTOTYPES = {
     "b200_depth_to_xyz": (I, [P, P, P, P, I, I, I, F, F, P]),
 }
 
-_NO_STATUS = {"b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems"}
+_NO_STATUS = {"b200_conv_merged", "b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems"}
 
 
 class B200LidarError(RuntimeError):

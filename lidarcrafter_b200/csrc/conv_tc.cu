@@ -83,11 +83,11 @@ struct ConvCfg {
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI;
     static constexpr int SMEM = OFF_BAR + 320;
-    // MERGE (fp16x3 with BN = 64): the weight tile keeps hi and lo rows adjacent ([KG][hi|lo][BN][8]) so that
-    // a_hi x [w_hi ; w_lo] is ONE N = 128 MMA (A is fetched from shared memory once for 128 accumulator columns
-    // instead of twice) and only a_lo x w_hi remains an N = 64 MMA: 64 + 48 instead of 3 x 48 tensor-pipe cycles.
-    // The two partial accumulators (columns [0,64) and [64,128)) are added in the epilogue.
-    static constexpr bool MERGE = (NP == 2 && BN == 64);
+    // MERGE (fp16x3 whenever 2 x R x BN accumulator columns fit twice in TMEM): the weight tile keeps hi and lo rows
+    // adjacent ([KG][hi|lo][BN][8]) so that a_hi x [w_hi ; w_lo] is ONE N = 2 BN MMA (A is fetched from shared memory
+    // once for 2 BN accumulator columns instead of twice) and only a_lo x w_hi remains an N = BN MMA.  The two partial
+    // accumulators (columns [0,BN) and [BN,2BN)) are added in the epilogue.
+    static constexpr bool MERGE = (NP == 2 && 2 * R * BN <= 256);
     static constexpr int ACC_ROW = MERGE ? 2 * BN : BN;
     static constexpr int ACC_COLS = R * ACC_ROW;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -468,7 +468,7 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
 //   by `wscale` (a power of two chosen on the host so max|w|*wscale is in [256, 512)).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin, int taps,
-                                   int bn, int parts, float wscale) {
+                                   int bn, int parts, int merged, float wscale) {
     const int kc = parts == 2 ? 16 : 32, kg = kc / 8;
     const size_t total = (size_t)Cout * Cin * taps * parts;
     const int nch = Cin / kc;
@@ -477,7 +477,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
         const int e = r % 8; r /= 8;
         const int n = r % bn; r /= bn;
         int j, part;
-        if (parts == 2 && bn == 64) {   // merged layout [KG][hi|lo][bn][8] (see ConvCfg::MERGE)
+        if (merged) {   // merged layout [KG][hi|lo][bn][8] (see ConvCfg::MERGE)
             part = r % parts; r /= parts;
             j = r % kg; r /= kg;
         } else {
@@ -620,16 +620,18 @@ extern "C" size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int part
 
 static int pack_blocks(size_t total) { return (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256); }
 
-extern "C" int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int parts,
-                                     float wscale, void* stream) {
+extern "C" int b200_conv_merged(int bn, int rows, int parts) { return (parts == 2 && 2 * rows * bn <= 256) ? 1 : 0; }
+
+extern "C" int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int rows,
+                                     int parts, float wscale, void* stream) {
     B200_CHECK_ARG(w && wpacked);
     B200_CHECK_ARG(taps == 9 || taps == 1);
     B200_CHECK_ARG(bn == 64 || bn == 128);
     B200_CHECK_ARG(parts == 1 || parts == 2);
     B200_CHECK_ARG(Cout % bn == 0 && Cin % 32 == 0);
     const size_t total = (size_t)Cout * Cin * taps * parts;
-    pack_weight_kernel<<<pack_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpacked, Cout, Cin, taps, bn,
-                                                                             parts, wscale);
+    pack_weight_kernel<<<pack_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+        w, (__half*)wpacked, Cout, Cin, taps, bn, parts, b200_conv_merged(bn, rows, parts), wscale);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -656,7 +658,7 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(W % PIX == 0 && Cin % 32 == 0 && Cin >= 32);
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
     B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
-    B200_CHECK_ARG(rows * bn * ((parts == 2 && bn == 64) ? 2 : 1) <= 256);   // two TMEM accumulator sets <= 512 columns
+    B200_CHECK_ARG(rows * bn <= 256);   // two TMEM accumulator sets <= 512 columns (merged mode is chosen when 2x fits)
     ConvParams p{(const __half*)a, (const __half*)wpacked, bias, res, out, stats, out_scale, w_inv,
                  B, H, W, Cin, Cout, ring, 0};
     cudaStream_t st = (cudaStream_t)stream;
@@ -677,6 +679,7 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CONV_CASE(128, 2, 1)
     B200_CONV_CASE(64, 1, 2)
     B200_CONV_CASE(64, 2, 2)
+    B200_CONV_CASE(64, 4, 2)
     B200_CONV_CASE(128, 1, 2)
     B200_CONV_CASE(128, 2, 2)
 #undef B200_CONV_CASE

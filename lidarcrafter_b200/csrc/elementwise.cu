@@ -74,10 +74,13 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                                                      int ada_stride, int groups, float eps, int silu,
                                                      __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
                                                      int HW, int W, int pix_per_block) {
-    __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
-    __shared__ double s_st[2 * GN_MAX_C];
-    __shared__ float s_mean[64], s_rstd[64];
+    // dynamic shared memory sized by the channel count (24 B / channel): keeps 8 blocks resident per SM
+    extern __shared__ __align__(16) unsigned char gn_smem[];
     const int C = C0 + C1;
+    double* s_st = reinterpret_cast<double*>(gn_smem);            // [2C]
+    float* s_a = reinterpret_cast<float*>(gn_smem + 16 * C);      // [C]
+    float* s_b = s_a + C;                                         // [C]
+    __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y;
     if (st0 != nullptr) {
         gn_coefficients(st0, C0, st1, C1, gamma, beta, ada, ada_stride, groups, eps, HW, b, s_a, s_b, s_st, s_mean, s_rstd);
@@ -167,8 +170,10 @@ __global__ void __launch_bounds__(256) gn_act_f32_kernel(const float* __restrict
                                                          const float* __restrict__ beta, int groups, float eps, int silu,
                                                          float* __restrict__ y, double* __restrict__ stats_out, int HW,
                                                          int pix_per_block) {
-    __shared__ float s_a[GN_MAX_C], s_b[GN_MAX_C];
-    __shared__ double s_st[2 * GN_MAX_C];
+    extern __shared__ __align__(16) unsigned char gn_smem[];
+    double* s_st = reinterpret_cast<double*>(gn_smem);
+    float* s_a = reinterpret_cast<float*>(gn_smem + 16 * C);
+    float* s_b = s_a + C;
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y;
     gn_coefficients(st, C, nullptr, 0, gamma, beta, nullptr, 0, groups, eps, HW, b, s_a, s_b, s_st, s_mean, s_rstd);
@@ -493,6 +498,72 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const TIn* __restrict__ a
     for (int co = 0; co < Cout; ++co) pred[((size_t)b * Cout + co) * HW + pp] = acc[co] + bias[co];
 }
 
+// out_conv, row-tiled: one block = 128 consecutive pixels of one image row.  Stage 1 reads every input pixel of the
+// three halo rows ONCE (coalesced 256 B per pixel) and reduces its Cin channels to the 3 x Cout partial sums of the
+// filter row it feeds; stage 2 adds the 9 partial sums of each output pixel.  (The thread-per-pixel kernel above
+// re-reads every input pixel 9 times from L1/L2.)
+constexpr int OC_PIX = 128, OC_THREADS = 256;
+
+__global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, float* __restrict__ pred,
+                                                                   int H, int W, int Cin, int Cout, int ring) {
+    extern __shared__ float osm[];
+    float* sw = osm;                                   // [3 dy][Cin][12]  (dx*4 + co, zero padded)
+    float* st = osm + 3 * Cin * 12;                    // [3 rows][130 px][12]
+    for (int i = threadIdx.x; i < 3 * Cin * 12; i += OC_THREADS) {
+        const int q = i % 12, ci = (i / 12) % Cin, dy = i / (12 * Cin);
+        const int dx = q >> 2, co = q & 3;
+        sw[i] = co < Cout ? w[((size_t)co * Cin + ci) * 9 + dy * 3 + dx] : 0.f;
+    }
+    __syncthreads();
+    const int wt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int w0 = wt * OC_PIX;
+    for (int item = threadIdx.x; item < 3 * (OC_PIX + 2); item += OC_THREADS) {
+        const int r = item / (OC_PIX + 2), j = item - r * (OC_PIX + 2);
+        const int gh = h + r - 1;
+        int gw = w0 + j - 1;
+        bool ok = gh >= 0 && gh < H;
+        if (gw < 0) { if (ring) gw += W; else ok = false; }
+        else if (gw >= W) { if (ring) gw -= W; else ok = false; }
+        float acc[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+        if (ok) {
+            const float* ap = a + ((size_t)(b * H + gh) * W + gw) * Cin;
+            const float* wr = sw + r * Cin * 12;
+            for (int ci = 0; ci < Cin; ci += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(ap + ci);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 w0v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12);
+                    const float4 w1v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12 + 4);
+                    const float4 w2v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12 + 8);
+                    acc[0] = fmaf(vv[e], w0v.x, acc[0]); acc[1] = fmaf(vv[e], w0v.y, acc[1]);
+                    acc[2] = fmaf(vv[e], w0v.z, acc[2]); acc[3] = fmaf(vv[e], w0v.w, acc[3]);
+                    acc[4] = fmaf(vv[e], w1v.x, acc[4]); acc[5] = fmaf(vv[e], w1v.y, acc[5]);
+                    acc[6] = fmaf(vv[e], w1v.z, acc[6]); acc[7] = fmaf(vv[e], w1v.w, acc[7]);
+                    acc[8] = fmaf(vv[e], w2v.x, acc[8]); acc[9] = fmaf(vv[e], w2v.y, acc[9]);
+                    acc[10] = fmaf(vv[e], w2v.z, acc[10]); acc[11] = fmaf(vv[e], w2v.w, acc[11]);
+                }
+            }
+        }
+        float* o = st + (size_t)(r * (OC_PIX + 2) + j) * 12;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) o[q] = acc[q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OC_PIX * Cout; i += OC_THREADS) {
+        const int co = i / OC_PIX, px = i - co * OC_PIX;     // consecutive threads -> consecutive pixels (NCHW store)
+        float acc = bias[co];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) acc += st[(size_t)(r * (OC_PIX + 2) + px + dx) * 12 + dx * 4 + co];
+        pred[((size_t)(b * Cout + co) * H + h) * W + w0 + px] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // sampler update (continuous_time.py:205-231)
 // ---------------------------------------------------------------------------------------------------------
@@ -565,7 +636,7 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     int ppb = 256;
     while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
     dim3 grid(cdiv(HW, ppb), B);
-    gn_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
+    gn_act_kernel<<<grid, 256, (size_t)24 * C, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
                                                           groups, eps, silu, (__half*)y, (__half*)y_raw,
                                                           parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW, W, ppb);
     B200_CHECK_LAUNCH();
@@ -580,7 +651,7 @@ extern "C" int b200_gn_act_f32(const float* x, const double* stats, const float*
     int ppb = 256;
     while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
     dim3 grid(cdiv(HW, ppb), B);
-    gn_act_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, stats, gamma, beta, groups, eps, silu, y, nullptr, HW,
+    gn_act_f32_kernel<<<grid, 256, (size_t)24 * C, (cudaStream_t)stream>>>(x, C, stats, gamma, beta, groups, eps, silu, y, nullptr, HW,
                                                               ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
@@ -650,6 +721,16 @@ extern "C" int b200_out_conv(const void* a, int a_is_f16, const float* w, const 
                              int W, int Cin, int Cout, int ring, void* stream) {
     B200_CHECK_ARG(a && w && bias && pred && Cout >= 1 && Cout <= 4);
     B200_CHECK_ARG(Cin % 8 == 0);
+    if (!a_is_f16 && W % OC_PIX == 0) {
+        const size_t sm = ((size_t)3 * Cin * 12 + 3 * (OC_PIX + 2) * 12) * sizeof(float);
+        if (sm <= 48 * 1024) {
+            dim3 grid(W / OC_PIX, H, B);
+            out_conv_rows_kernel<<<grid, OC_THREADS, sm, (cudaStream_t)stream>>>((const float*)a, w, bias, pred, H, W, Cin,
+                                                                               Cout, ring);
+            B200_CHECK_LAUNCH();
+            return B200_OK;
+        }
+    }
     const size_t smem = (size_t)4 * 9 * Cin * sizeof(float);
     B200_CHECK_ARG(smem <= 48 * 1024);
     dim3 grid(cdiv(H * W, 128), B);

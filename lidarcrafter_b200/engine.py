@@ -31,6 +31,11 @@ class Act:
     stats: dict | None = None  # stats slot from Plan.new_stats(): [B, C, 2] fp64 view into the arena
 
 
+def conv_merged(bn: int, rows: int, parts: int) -> bool:
+    """mirror of b200_conv_merged(): hi/lo weight rows adjacent when 2 x rows x bn accumulator columns fit twice in TMEM"""
+    return parts == 2 and 2 * rows * bn <= 256
+
+
 def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, parts: int = 2, sms: int = NUM_SMS):
     """Choose (bn, rows) for b200_conv_tc: maximise (SM fill) x min(L2-feed, MMA-shape) efficiency."""
     best = None
@@ -38,8 +43,7 @@ def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, parts: int = 2, sms:
         if Cout % bn:
             continue
         for rows in (4, 2, 1):
-            merged = parts == 2 and bn == 64      # conv_tc ConvCfg::MERGE: 2 x BN accumulator columns per row
-            if H % rows or rows * bn * (2 if merged else 1) > 256:
+            if H % rows or rows * bn > 256:
                 continue
             tiles = B * (H // rows) * (W // 128) * (Cout // bn)
             waves = math.ceil(tiles / sms)
@@ -73,9 +77,8 @@ def tile_candidates(B: int, H: int, W: int, Cout: int, parts: int):
     for bn in (128, 64):
         if Cout % bn:
             continue
-        merged = parts == 2 and bn == 64
         for rows in (4, 2, 1):
-            if H % rows == 0 and rows * bn * (2 if merged else 1) <= 256:
+            if H % rows == 0 and rows * bn <= 256:
                 out.append((bn, rows))
     return out
 
@@ -83,13 +86,13 @@ def tile_candidates(B: int, H: int, W: int, Cout: int, parts: int):
 class PackedConv:
     """fp16 tile image of one conv's weights + fp32 bias (device)."""
 
-    def __init__(self, lib, weight: torch.Tensor, bias: torch.Tensor | None, bn: int, parts: int, stream: int):
+    def __init__(self, lib, weight: torch.Tensor, bias: torch.Tensor | None, bn: int, rows: int, parts: int, stream: int):
         Cout, Cin, kh, kw = weight.shape
-        self.Cout, self.Cin, self.taps, self.bn, self.parts = Cout, Cin, kh * kw, bn, parts
+        self.Cout, self.Cin, self.taps, self.bn, self.rows, self.parts = Cout, Cin, kh * kw, bn, rows, parts
         w = weight.detach().float().contiguous()
         self.wscale = weight_scale(w)
         self.packed = torch.empty(Cout * Cin * self.taps * parts, dtype=torch.float16, device=w.device)
-        lib.pack_conv_weight(_ptr(w), _ptr(self.packed), Cout, Cin, self.taps, bn, parts, self.wscale, stream)
+        lib.pack_conv_weight(_ptr(w), _ptr(self.packed), Cout, Cin, self.taps, bn, rows, parts, self.wscale, stream)
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self._keep = w
 
@@ -202,7 +205,7 @@ class PlanBuilder:
             + 2.0 * self.p.parts * taps * Cin * Cout
         if self.p.conv_impl == "tc":
             bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
-            pc = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
+            pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             self.p.bufs.append(pc)
             self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
                        1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
@@ -233,9 +236,10 @@ class PlanBuilder:
         best = None
         packed = {}
         for bn, rows in tile_candidates(self.B, H, W, Cout, self.p.parts):
-            if bn not in packed:
-                packed[bn] = PackedConv(self.lib, weight, bias, bn, self.p.parts, self.stream)
-            pc = packed[bn]
+            pk = (bn, conv_merged(bn, rows, self.p.parts))
+            if pk not in packed:
+                packed[pk] = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
+            pc = packed[pk]
             args = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), 1.0, 1.0 / pc.wscale, _ptr(out), 0, self.B, H, W,
                     Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
             self.lib.conv_tc(*args)                      # warm-up (function attributes, caches)

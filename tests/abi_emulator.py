@@ -81,13 +81,18 @@ class EmulatedLib:
             return hi[None]
         return torch.stack([hi, (v - hi.float()).half()])
 
-    def pack_conv_weight(self, w, out, Cout, Cin, taps, bn, parts, wscale, stream):
+    @staticmethod
+    def conv_merged(bn, rows, parts):
+        return 1 if (parts == 2 and 2 * rows * bn <= 256) else 0
+
+    def pack_conv_weight(self, w, out, Cout, Cin, taps, bn, rows, parts, wscale, stream):
         self._rec("pack_conv_weight")
+        merged = self.conv_merged(bn, rows, parts)
         kc = 16 if parts == 2 else 32
         W = self._split(f32(w, Cout, Cin, taps) * wscale, parts)        # [parts, Cout, Cin, taps]
         # -> [Cout/bn][Cin/kc][taps][parts][kc/8][bn][8]   (merged mode, parts == 2 and bn == 64: [..][kc/8][parts][bn][8])
         t = W.view(parts, Cout // bn, bn, Cin // kc, kc // 8, 8, taps)
-        t = (t.permute(1, 3, 6, 4, 0, 2, 5) if (parts == 2 and bn == 64) else t.permute(1, 3, 6, 0, 4, 2, 5)).contiguous()
+        t = (t.permute(1, 3, 6, 4, 0, 2, 5) if merged else t.permute(1, 3, 6, 0, 4, 2, 5)).contiguous()
         f16(out, Cout * Cin * taps * parts).copy_(t.reshape(-1))
         return 0
 
@@ -119,8 +124,8 @@ class EmulatedLib:
         assert W % 128 == 0 and Cin % KC == 0 and Cout % bn == 0 and H % rows == 0 and rows * bn <= 256
         k = 3 if taps == 9 else 1
         kc = 16 if parts == 2 else 32
-        assert rows * bn * (2 if (parts == 2 and bn == 64) else 1) <= 256
-        if parts == 2 and bn == 64:
+        assert rows * bn <= 256
+        if self.conv_merged(bn, rows, parts):
             t = f16(wpacked, Cout // bn, Cin // kc, taps, kc // 8, parts, bn, 8).float().sum(4)
         else:
             t = f16(wpacked, Cout // bn, Cin // kc, taps, parts, kc // 8, bn, 8).float().sum(3)

@@ -64,6 +64,7 @@ def split(v, parts):
 @pytest.mark.parametrize("taps", [9, 1])
 @pytest.mark.parametrize("bn,rows,Cin,Cout,H,W,B", [
     (64, 2, 64, 64, 8, 256, 2),
+    (64, 4, 64, 64, 8, 256, 2),
     (64, 2, 64, 64, 32, 1024, 3),        # > 148 tiles: persistent loop + TMEM double buffering
     (64, 2, 96, 64, 4, 128, 1),
     (64, 1, 32, 128, 3, 128, 2),
@@ -83,7 +84,7 @@ def test_conv_tc_matches_contract(parts, taps, bn, rows, Cin, Cout, H, W, B):
     out = h.t(torch.zeros(B, H, W, Cout))
     st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
     wscale = 64.0
-    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, parts, wscale])
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, rows, parts, wscale])
     g, c = h.out(wp)
     assert torch.equal(g, c), "packed weight image differs"
     h.call("conv_tc", [("t", a), ("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out), ("t", st),
@@ -101,7 +102,7 @@ def test_conv_tc_zero_pad_no_bias_no_res():
     a = h.t(split(randn(B, H, W, Cin, seed=2), 2))
     wp = h.t(torch.zeros(Cout * Cin * 9 * 2, dtype=torch.float16))
     out = h.t(torch.zeros(B, H, W, Cout))
-    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 64, 2, 128.0])
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 64, 2, 2, 128.0])
     h.call("conv_tc", [("t", a), ("t", wp), None, None, 1.0, 1.0 / 128.0, ("t", out), None, B, H, W, Cin, Cout, 9, 0, 64,
                        2, 2])  # ring = 0: zero padding in W as well
     g, c = h.out(out)
@@ -124,7 +125,7 @@ def test_conv_tc_split_reaches_fp32_accuracy():
         wp = h.t(torch.zeros(Cout * Cin * 9 * parts, dtype=torch.float16))
         out = h.t(torch.zeros(B, H, W, Cout))
         ws = 2.0 ** (8 - math.floor(math.log2(float(w32.abs().max()))))
-        h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 128, parts, ws])
+        h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, 9, 128, 2, parts, ws])
         h.call("conv_tc", [("t", a), ("t", wp), None, None, 1.0, 1.0 / ws, ("t", out), None, B, H, W, Cin, Cout, 9, 1,
                            128, 2, parts])
         errs[parts] = rel(h.out(out)[0], ref)
@@ -339,3 +340,16 @@ def test_flash_attention_oa(parts, C, T, W):
                                   C, C // 32, T, L2, 1 / math.sqrt(64)])
     g, c = h.out(out)
     assert rel(g.float().sum(0), c.float().sum(0)) < (2e-5 if parts == 2 else 6e-4)
+
+
+@pytest.mark.parametrize("ring", [1, 0])
+def test_out_conv_row_tiled(ring):
+    """W % 128 == 0 fp32 input takes the row-tiled kernel (one read of every input pixel)."""
+    h = Both()
+    B, H, W = 2, 6, 256
+    a = h.t(randn(B, H, W, 64, seed=4))
+    w = h.t(randn(2, 64, 3, 3, seed=5, scale=0.1))
+    b = h.t(randn(2, seed=6))
+    pred = h.t(torch.zeros(B, 2, H, W))
+    h.call("out_conv", [("t", a), 0, ("t", w), ("t", b), ("t", pred), B, H, W, 64, 2, ring])
+    assert rel(*h.out(pred)) < 1e-6

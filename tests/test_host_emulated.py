@@ -100,7 +100,7 @@ def test_tile_picker_respects_kernel_limits():
                 for parts in (1, 2):
                     bn, rows = pick_tile(B, H, W, C, taps, parts)
                     assert C % bn == 0 and H % rows == 0
-                    assert rows * bn * (2 if (parts == 2 and bn == 64) else 1) <= 256
+                    assert rows * bn <= 256
 
 
 @pytest.mark.parametrize("nres,jump", [(1, 1), (2, 2)])

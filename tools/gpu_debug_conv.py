@@ -58,7 +58,7 @@ def run_case(c):
     out = torch.full((B, H, W, Cout), float("nan"), device=dev)
     st = torch.zeros(B, Cout, 2, dtype=torch.float64, device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    lib.pack_conv_weight(w.data_ptr(), wp.data_ptr(), Cout, Cin, taps, bn, parts, wscale, s)
+    lib.pack_conv_weight(w.data_ptr(), wp.data_ptr(), Cout, Cin, taps, bn, rows, parts, wscale, s)
     lib.conv_tc(a.data_ptr(), wp.data_ptr(), 0, 0, 1.0, 1.0 / wscale, out.data_ptr(), st.data_ptr(), B, H, W, Cin, Cout,
                 taps, 1, bn, rows, parts, s)
     torch.cuda.synchronize()

@@ -17,13 +17,13 @@ cat gpurun_out/bench.json | head -c 600
 timeout 300 python bench.py --steps 20 --warmup 3 --precision fp16 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err
 timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
 if [ "${NCU:-0}" = "1" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_bench.log 2>&1
   echo "ncu launches rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 12 -c 3 -f -o gpurun_out/prof_conv \
-      python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_conv.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc -s 4 -c 4 -f -o gpurun_out/prof_conv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_conv.log 2>&1
   echo "ncu conv rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gn_act|in_conv|out_conv|fir_|flash_attn' -s 4 -c 8 -f -o gpurun_out/prof_elem \
-      python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_elem.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'gn_act|in_conv|out_conv|fir_|flash_attn|sampler' -c 12 -f -o gpurun_out/prof_elem \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_elem.log 2>&1
   echo "ncu elem rc=$?"
 fi
