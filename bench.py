@@ -311,13 +311,35 @@ def main():
                   f"{v[1] / max(v[0], 1e-9) / 1e9:8.1f} TFLOP/s  {v[2] / max(v[0], 1e-9) / 1e6:8.1f} GB/s", file=sys.stderr)
     c = by.get("conv_tc", [1e-9, 0, 0, 1])
     mma_per_product = 3 if args.precision == "fp16x3" else 1
-    ach = c[1] / (c[0] / 1e3) / 1e12
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 ring conv, all launches of one step)",
-            "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
-            "peak_source": pk["src"] + " bf16 dense burst", "share_of_step": c[0] / tot_ms,
-            "tensor_work_multiplier": mma_per_product,
-            "note": "achieved = algorithmic conv FLOPs (2*B*H*W*taps*Cin*Cout); the fp16x3 mode issues 3 fp16 MMAs per "
-                    "algorithmic product, so tensor-pipe utilisation = frac * tensor_work_multiplier"}
+    # dominant kernel = the conv shape with the largest share of the step (per-launch numbers)
+    dom = {}
+    for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
+        if name == "conv_tc":
+            key = (a[9], a[10], a[11], a[12], a[13])
+            d = dom.setdefault(key, [0.0, 0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += by_k; d[3] += 1
+    dk, dv = max(dom.items(), key=lambda kv: kv[1][0])
+    d_ms, d_fl, d_by = dv[0] / dv[3], dv[1] / dv[3], dv[2] / dv[3]
+    t_tensor = d_fl / (pk["tf"] * 1e12) * 1e3          # ms at the measured bf16 peak (1 MMA / product)
+    t_hbm = d_by / (pk["hbm_gbs"] * 1e9) * 1e3         # ms at the measured HBM peak
+    bound = "hbm" if t_hbm >= t_tensor else "tensor"
+    ach = (d_by / (d_ms / 1e3) / 1e9) if bound == "hbm" else (d_fl / (d_ms / 1e3) / 1e12)
+    peak = pk["hbm_gbs"] if bound == "hbm" else pk["tf"]
+    # DRAM traffic of this shape from the committed ncu --set full capture (profiles/), per launch; None if unknown
+    ncu_traffic = {(32, 1024, 64, 64, 9): 2.53e8}.get(dk)
+    roof = {"bound": bound, "kernel": "conv_tc_kernel %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
+                dk + (dv[3], 100 * dv[0] / tot_ms)),
+            "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
+            "traffic": ncu_traffic, "peak_source": pk["src"],
+            "per_launch": {"ms": d_ms, "algorithmic_gflop": d_fl / 1e9, "algorithmic_mb": d_by / 1e6,
+                           "ms_at_tensor_peak": t_tensor, "ms_at_hbm_peak": t_hbm,
+                           "tflops_algorithmic": d_fl / (d_ms / 1e3) / 1e12,
+                           "tensor_pipe_tflops": mma_per_product * d_fl / (d_ms / 1e3) / 1e12},
+            "all_conv_launches": {"n": c[3], "ms": c[0], "share_of_step": c[0] / tot_ms,
+                                  "tflops_algorithmic": c[1] / (c[0] / 1e3) / 1e12,
+                                  "frac_of_bf16_peak_algorithmic": c[1] / (c[0] / 1e3) / 1e12 / pk["tf"],
+                                  "tensor_work_multiplier": mma_per_product},
+            "note": "bound = max(algorithmic FLOPs / measured bf16 peak, algorithmic bytes / measured HBM peak) per launch "
+                    "(SURVEY 8d); the fp16x3 mode issues 3 fp16 MMAs per algorithmic product (tensor_pipe_tflops)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16x3 split tensor-core MMAs, fp32 accumulate)" if args.precision == "fp16x3" else "f16 operands, f32 accumulate",

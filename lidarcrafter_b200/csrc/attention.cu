@@ -322,6 +322,8 @@ struct FAParams {
 template <int DQ, int DV>
 __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const FAParams p) {
     extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     float* sQ = sm;                       // [DQ][FA_PAD]   (d-major: 4 consecutive queries = one LDS.128)
     float* sK = sQ + DQ * FA_PAD;         // [DQ][FA_PAD]
     float* sV = sK + DQ * FA_PAD;         // [FA_BK][DV]
@@ -482,7 +484,7 @@ static int launch_fa(const FAParams& p, int B, int heads, cudaStream_t st) {
         attr = true;
     }
     dim3 grid(cdiv(p.T, FA_BQ), heads, B);
-    flash_attn_kernel<DQ, DV><<<grid, FA_THREADS, smem, st>>>(p);
+    launch_pdl(flash_attn_kernel<DQ, DV>, grid, dim3(FA_THREADS), smem, st, p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

@@ -135,11 +135,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         }
         fence_barrier_init();
     }
+    pdl_launch_dependents();   // let the next kernel's CTAs be scheduled while this grid drains
     if (warp == 5) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                // everything above (barriers, TMEM) overlapped the previous kernel's tail
 
     if (warp == 4) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
@@ -457,7 +459,7 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     const int tpc = (p.n_tiles + grid - 1) / grid;
     grid = (p.n_tiles + tpc - 1) / tpc;     // no empty CTAs with contiguous chunks
-    conv_tc_kernel<BN, R, TAPS, NP><<<grid, CONV_THREADS, C::SMEM, st>>>(p);
+    launch_pdl(conv_tc_kernel<BN, R, TAPS, NP>, dim3(grid), dim3(CONV_THREADS), (size_t)C::SMEM, st, p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

@@ -1,12 +1,22 @@
 // HBM-bound kernels of the denoiser step: GroupNorm apply + SiLU + fp16 cast (+concat), channel statistics,
 // FIR resampling, time embedding, first/last convs on CUDA cores, sampler update.  All NHWC fp32.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace b200 {
 
 static thread_local char g_err[512] = "";
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -76,6 +86,8 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                                                      int HW, int W, int pix_per_block) {
     // dynamic shared memory sized by the channel count (24 B / channel): keeps 8 blocks resident per SM
     extern __shared__ __align__(16) unsigned char gn_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int C = C0 + C1;
     double* s_st = reinterpret_cast<double*>(gn_smem);            // [2C]
     float* s_a = reinterpret_cast<float*>(gn_smem + 16 * C);      // [C]
@@ -171,6 +183,8 @@ __global__ void __launch_bounds__(256) gn_act_f32_kernel(const float* __restrict
                                                          float* __restrict__ y, double* __restrict__ stats_out, int HW,
                                                          int pix_per_block) {
     extern __shared__ __align__(16) unsigned char gn_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
     double* s_st = reinterpret_cast<double*>(gn_smem);
     float* s_a = reinterpret_cast<float*>(gn_smem + 16 * C);
     float* s_b = s_a + C;
@@ -249,6 +263,8 @@ __global__ void __launch_bounds__(256) fir_kernel(const float* __restrict__ x, f
                                                   double* __restrict__ stats, int H, int W, int C, int ring,
                                                   int pix_per_block) {
     __shared__ float red[256 * 8];
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = UP ? 2 * H : H / 2, Wo = UP ? 2 * W : W / 2;
     const int b = blockIdx.y;
     const int c4n = C / 4;
@@ -306,6 +322,8 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
                                                    const float* __restrict__ b2, const float* __restrict__ add,
                                                    float* __restrict__ temb, int Cs, int E) {
     extern __shared__ float sm[];
+    pdl_launch_dependents();
+    pdl_wait();
     float* e0 = sm;        // [Cs]
     float* h1 = sm + Cs;   // [E]
     const int b = blockIdx.x;
@@ -342,6 +360,8 @@ __global__ void __launch_bounds__(256) ada_proj_kernel(const float* __restrict__
                                                        const float* __restrict__ bp, float* __restrict__ ada, int B,
                                                        int E, int P) {
     extern __shared__ float sm[];  // silu(temb) [B][E]
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = threadIdx.x; i < B * E; i += blockDim.x) sm[i] = silu_f(temb[i]);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,6 +397,8 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
                                                       int Cx, int Cout, int ring) {
     __shared__ float red[256 * 8];
     __shared__ float sw[4 * 9 * 256];  // [ci][tap][co] , Cout <= 256
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < Cx * 9 * Cout; i += blockDim.x) {
         const int co = i % Cout, r = i / Cout;
@@ -508,6 +530,8 @@ __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* 
                                                                    const float* __restrict__ bias, float* __restrict__ pred,
                                                                    int H, int W, int Cin, int Cout, int ring) {
     extern __shared__ float osm[];
+    pdl_launch_dependents();
+    pdl_wait();
     float* sw = osm;                                   // [3 dy][Cin][12]  (dx*4 + co, zero padded)
     float* st = osm + 3 * Cin * 12;                    // [3 rows][130 px][12]
     for (int i = threadIdx.x; i < 3 * Cin * 12; i += OC_THREADS) {
@@ -570,6 +594,8 @@ __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* 
 __global__ void sampler_update_kernel(const float* __restrict__ x_t, const float* __restrict__ pred,
                                       const float* __restrict__ noise, const float* __restrict__ coef,
                                       float* __restrict__ x_s, int n, int mode, int objective, float clip) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const float a_t = coef[b * 8 + 0], s_t = coef[b * 8 + 1], a_s = coef[b * 8 + 2], s_s = coef[b * 8 + 3];
     const float c1 = coef[b * 8 + 4], c2 = coef[b * 8 + 5], cc = coef[b * 8 + 6];
@@ -636,9 +662,9 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     int ppb = 256;
     while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
     dim3 grid(cdiv(HW, ppb), B);
-    gn_act_kernel<<<grid, 256, (size_t)24 * C, (cudaStream_t)stream>>>(x0, C0, x1, C1, stats0, stats1, gamma, beta, ada, ada_stride,
-                                                          groups, eps, silu, (__half*)y, (__half*)y_raw,
-                                                          parts == 2 ? (size_t)B * HW * (C0 + C1) : 0, HW, W, ppb);
+    launch_pdl(gn_act_kernel, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1, gamma,
+               beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
+               parts == 2 ? (size_t)B * HW * (C0 + C1) : (size_t)0, HW, W, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -651,8 +677,8 @@ extern "C" int b200_gn_act_f32(const float* x, const double* stats, const float*
     int ppb = 256;
     while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
     dim3 grid(cdiv(HW, ppb), B);
-    gn_act_f32_kernel<<<grid, 256, (size_t)24 * C, (cudaStream_t)stream>>>(x, C, stats, gamma, beta, groups, eps, silu, y, nullptr, HW,
-                                                              ppb);
+    launch_pdl(gn_act_f32_kernel, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x, C, stats, gamma, beta, groups,
+               eps, silu, y, (double*)nullptr, HW, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -674,8 +700,8 @@ extern "C" int b200_fir_resample(const float* x, float* y, double* stats, int B,
     const int pmin = 256 / (C / 4) > 8 ? 256 / (C / 4) : 8;   // at least one pixel per thread row
     while (ppb > pmin && (long long)cdiv(npo, ppb) * B < 4 * 148) ppb >>= 1;
     dim3 grid(cdiv(npo, ppb), B);
-    if (up) fir_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring, ppb);
-    else fir_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, stats, H, W, C, ring, ppb);
+    if (up) launch_pdl(fir_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, stats, H, W, C, ring, ppb);
+    else launch_pdl(fir_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, stats, H, W, C, ring, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -685,13 +711,14 @@ extern "C" int b200_time_embed(const float* t, const float* w1, const float* b1,
                                int Cs, int E, int P, void* stream) {
     B200_CHECK_ARG(t && w1 && b1 && w2 && b2 && temb);
     B200_CHECK_ARG(B > 0 && B <= ADA_MAX_B && Cs % 2 == 0 && Cs >= 4);
-    temb_kernel<<<B, 256, (Cs + E) * sizeof(float), (cudaStream_t)stream>>>(t, w1, b1, w2, b2, temb_add, temb, Cs, E);
+    launch_pdl(temb_kernel, dim3(B), dim3(256), (Cs + E) * sizeof(float), (cudaStream_t)stream, t, w1, b1, w2, b2, temb_add,
+               temb, Cs, E);
     B200_CHECK_LAUNCH();
     if (P > 0) {
         B200_CHECK_ARG(wp && bp && ada);
         B200_CHECK_ARG((size_t)B * E * sizeof(float) <= 48 * 1024);
-        ada_proj_kernel<<<cdiv(P, ADA_ROWS_PER_BLOCK), 256, (size_t)B * E * sizeof(float), (cudaStream_t)stream>>>(
-            temb, wp, bp, ada, B, E, P);
+        launch_pdl(ada_proj_kernel, dim3(cdiv(P, ADA_ROWS_PER_BLOCK)), dim3(256), (size_t)B * E * sizeof(float),
+                   (cudaStream_t)stream, (const float*)temb, wp, bp, ada, B, E, P);
         B200_CHECK_LAUNCH();
     }
     return B200_OK;
@@ -702,7 +729,8 @@ extern "C" int b200_in_conv(const float* x, const float* w, const float* cst, in
     B200_CHECK_ARG(x && w && cst && out);
     B200_CHECK_ARG(Cx >= 1 && Cx <= 4 && Cout <= 256 && c4_ok(Cout));
     dim3 grid(cdiv(H * W, ST_PIX_PER_BLOCK), B);
-    in_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, cst, cst_batched, out, stats, H, W, Cx, Cout, ring);
+    launch_pdl(in_conv_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, w, cst, cst_batched, out, stats, H, W, Cx, Cout,
+               ring);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -725,8 +753,8 @@ extern "C" int b200_out_conv(const void* a, int a_is_f16, const float* w, const 
         const size_t sm = ((size_t)3 * Cin * 12 + 3 * (OC_PIX + 2) * 12) * sizeof(float);
         if (sm <= 48 * 1024) {
             dim3 grid(W / OC_PIX, H, B);
-            out_conv_rows_kernel<<<grid, OC_THREADS, sm, (cudaStream_t)stream>>>((const float*)a, w, bias, pred, H, W, Cin,
-                                                                               Cout, ring);
+            launch_pdl(out_conv_rows_kernel, grid, dim3(OC_THREADS), sm, (cudaStream_t)stream, (const float*)a, w, bias, pred,
+                       H, W, Cin, Cout, ring);
             B200_CHECK_LAUNCH();
             return B200_OK;
         }
@@ -749,8 +777,8 @@ extern "C" int b200_sampler_update(const float* x_t, const float* pred, const fl
                                    void* stream) {
     B200_CHECK_ARG(x_t && pred && coef && x_s && (mode == 0 || (mode == 1 && noise)));
     dim3 grid(cdiv(n_per_sample, 256 * 4), B);
-    sampler_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_t, pred, noise, coef, x_s, n_per_sample, mode,
-                                                                  objective, clip);
+    launch_pdl(sampler_update_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x_t, pred, noise, coef, x_s, n_per_sample,
+               mode, objective, clip);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
