@@ -39,7 +39,15 @@ const char* b200_last_error(void);
  *              shared-memory image, so the TMA engine stages it with plain bulk copies), already
  *              normalised/activated by b200_gn_act_f16;
  *              parts = 1: plain fp16;  parts = 2: a = a[0] (hi) + a[1] (lo), the error-compensated split
- *              (3 tensor-core MMAs per product, ~fp32 accuracy -- the mode that meets the 1e-3 tolerance)
+ *              (3 tensor-core MMAs per product, ~fp32 accuracy: ~2e-6 through the UNet);
+ *              parts = 3 ("fp16 + fp8 correction", ~5e-5 through the UNet, inside the 1e-3 tolerance): plane 0 =
+ *              fp16 hi as above; plane 1 (same byte size) = e4m3 pairs [B][H][Cin/16][2][W][16 bytes]: for every
+ *              16-channel chunk and pixel one 16-byte unit L8 = e4m3((a - hi) * 2^11) and one unit A8 = e4m3(a).
+ *              The kernel evaluates  hi x w16  with kind::f16 and BOTH cross terms a_lo*w_hi + a_hi*w_lo with ONE
+ *              kind::f8f6f4 MMA (K = 32 = [L8 | A8] x [e4m3(w 2^-11) | e4m3(w - w16)]): 2 MMA time units instead
+ *              of 3.  wscale must put max|w * wscale| in [2^14, 2^15) (both e4m3 weight planes in normal range).
+ *              parts = 4: as 3 with the correction MMAs accumulating into their own TMEM columns (added in the
+ *              epilogue) -- diagnostic variant, needs 2*rows*bn <= 256.
  *   wpacked  : fp16 image from b200_pack_conv_weight (same bn, same parts), pre-scaled by wscale = 1/w_inv
  *   out      : fp32 [B,H,W,Cout] = (conv(a)*w_inv + bias + res) * out_scale   (res may be NULL / == out)
  *   stats    : fp64 [B,Cout,2] += {sum, sum of squares} of `out` over H*W  (may be NULL)
@@ -53,17 +61,19 @@ int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const fl
 /* profiling aid: device buffer of [#CTAs][8] uint64 cycle counters filled by b200_conv_tc (NULL disables; see
  * conv_tc.cu g_conv_dbg for the slot meaning).  Not used on the product path.                          */
 int b200_conv_set_debug(void* dbg_u64);
-/* number of fp16 elements of the packed weight image (== parts*taps*Cout*Cin) */
+/* number of fp16-sized elements of the packed weight image (== planes*taps*Cout*Cin, planes = 1 for parts 1 else 2) */
 size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
 /* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
  * packed fp16 tiles [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8] (merged mode: [..][KC/8][parts][bn][8]),
- * KC = 32 (parts 1) or 16 (parts 2)                                                               */
+ * KC = 32 (parts 1) or 16 (parts 2);  parts 3/4: per (n-tile, 16-channel chunk, tap) [2][bn][8] fp16(w*wscale)
+ * followed by [2][bn][16] e4m3 {w*wscale*2^-11, w*wscale - fp16(w*wscale)}                          */
 int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int rows,
                           int parts, float wscale, void* stream);
 /* 1 if b200_conv_tc runs (bn, rows, parts) in merged mode (hi/lo weight rows adjacent: the packed image and the
  * tile must be created with the same (bn, rows, parts))                                              */
 int b200_conv_merged(int bn, int rows, int parts);
-/* plain fp16 copy w16[parts][tap][Cout][Cin] for the CUDA-core checking kernel */
+/* plain fp16 copy w16[parts][tap][Cout][Cin] for the CUDA-core checking kernel (parts 3: planes 1, 2 hold the
+ * fp16 images of the two e4m3 weight planes) */
 int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, int Cin, int taps, int parts,
                                 float wscale, void* stream);
 /* CUDA-core (FFMA) implementation of exactly the same contract as b200_conv_tc, weights from
@@ -81,7 +91,8 @@ int b200_conv_ffma(const void* a, const void* w16, const float* bias, const floa
  *   gamma/beta: [C0+C1] or NULL;  ada: fp32, scale at ada[b*ada_stride + c], shift at
  *               ada[b*ada_stride + (C0+C1) + c], NULL => none;  silu: 1 = apply x*sigmoid(x)
  *   y        : fp16 slab-major [parts][B][H][(C0+C1)/8][W][8] (the conv operand layout);
- *              parts = 2 also writes the residual lo = fp16(v - fp32(hi))
+ *              parts = 2 also writes the residual lo = fp16(v - fp32(hi)); parts = 3 writes the e4m3 pair plane
+ *              (see b200_conv_tc; needs (C0+C1) % 32 == 0)
  *   y_raw    : optional second output (same layout): the UN-normalised concatenated input as a conv operand
  *              (input of the block's 1x1 skip conv, efficient_unet.py:92-96) -- one read of x feeds both     */
 int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,

@@ -12,7 +12,8 @@ constexpr int ATT_THREADS = 128;
 struct AttnParams {
     const float *q, *k, *v;
     __half* out;
-    size_t lo_off;
+    size_t lo_off;   // fp16 elements per operand plane
+    int parts;
     int ldq, qoff, ldk, koff, ldv, voff, ldo, Wimg;
     int heads, Tq, Tk, dqk, dv;
     float scale;
@@ -99,13 +100,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
         const int tq = q0 + qi;
         const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
         const int ch = head * p.dv + dc * dper;
-        __half* o = p.out + ((((size_t)b * (p.Tq / p.Wimg) + hh) * (p.ldo / 8) + ch / 8) * p.Wimg + ww) * 8 + (ch & 7);
-        for (int e = 0; e < dper; ++e) {
-            const float val = acc[e] * inv;
-            const __half hi = __float2half_rn(val);
-            o[e] = hi;
-            if (p.lo_off) o[p.lo_off + e] = __float2half_rn(val - __half2float(hi));
-        }
+        for (int e = 0; e < dper; ++e)
+            store_operand_elem(p.out, p.lo_off, p.parts, (size_t)b * (p.Tq / p.Wimg) + hh, p.ldo, p.Wimg, ww, ch + e,
+                               acc[e] * inv);
     }
 }
 
@@ -116,12 +113,12 @@ using namespace b200;
 extern "C" int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
                               int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq, int Tk,
                               int dqk, int dv, float scale, void* stream) {
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(out_w > 0 && Tq % out_w == 0 && ldo % 8 == 0);
     B200_CHECK_ARG(q && k && v && out);
     B200_CHECK_ARG(dqk % 4 == 0 && (dv == 32 || dv == 64));
     B200_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && qoff % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
-    AttnParams p{q, k, v, (__half*)out, parts == 2 ? (size_t)B * Tq * ldo : 0, ldq, qoff, ldk, koff, ldv, voff, ldo, out_w, heads, Tq, Tk, dqk, dv, scale};
+    AttnParams p{q, k, v, (__half*)out, (size_t)B * Tq * ldo, parts, ldq, qoff, ldk, koff, ldv, voff, ldo, out_w, heads, Tq, Tk, dqk, dv, scale};
     const size_t smem = ((size_t)ATT_QT * dqk + (size_t)ATT_QT * (Tk + 1) + ATT_QT) * sizeof(float);
     B200_CHECK_ARG(smem <= 200 * 1024);
     static size_t smem_set = 0;
@@ -153,7 +150,8 @@ namespace b200 {
 struct OAParams {
     const float *qkv, *pos_p, *kl, *pos_l, *vl;
     __half* out;
-    size_t lo_off;
+    size_t lo_off;   // fp16 elements per operand plane
+    int parts;
     int C, heads, T, L2, d, Wimg;
     float scale2;
 };
@@ -255,14 +253,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_oa_kernel(const OAParam
         const int tq = q0 + qi;
         const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
         const int ch = head * d + dc * 4;
-        __half* o = p.out + ((((size_t)b * (p.T / p.Wimg) + hh) * (p.C / 8) + ch / 8) * p.Wimg + ww) * 8 + (ch & 7);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float val = acc[e] * inv;
-            const __half hi = __float2half_rn(val);
-            o[e] = hi;
-            if (p.lo_off) o[p.lo_off + e] = __float2half_rn(val - __half2float(hi));
-        }
+        for (int e = 0; e < 4; ++e)
+            store_operand_elem(p.out, p.lo_off, p.parts, (size_t)b * (p.T / p.Wimg) + hh, p.C, p.Wimg, ww, ch + e,
+                               acc[e] * inv);
     }
 }
 
@@ -272,10 +266,10 @@ extern "C" int b200_attention_oa(const float* qkv, const float* pos_p, const flo
                                  const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                                  int L2, float scale2, void* stream) {
     B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out);
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32);   // num_head_channels = 32 in every config
     B200_CHECK_ARG(out_w > 0 && T % out_w == 0 && L2 >= 0);
-    OAParams p{qkv, pos_p, kl, pos_l, vl, (__half*)out, parts == 2 ? (size_t)B * T * C : 0, C, heads, T, L2, C / heads,
+    OAParams p{qkv, pos_p, kl, pos_l, vl, (__half*)out, (size_t)B * T * C, parts, C, heads, T, L2, C / heads,
                out_w, scale2};
     const size_t smem = ((size_t)ATT_QT * 2 * p.d + (size_t)ATT_QT * (T + L2 + 1) + ATT_QT) * sizeof(float);
     B200_CHECK_ARG(smem <= 200 * 1024);
@@ -314,7 +308,8 @@ struct FAParams {
     int d1, d2, dv;                          // per-head dims of source 1 / 2 and of v
     int T, Tx;                               // #queries == #main keys, #extra keys
     __half* out;
-    size_t lo_off;
+    size_t lo_off;   // fp16 elements per operand plane
+    int parts;
     int C, Wimg;                             // output channels (heads * dv) and image width for the slab-major store
     float scale;                             // applied to q (full softmax scale)
 };
@@ -460,14 +455,10 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const FAParams p
         const float inv = 1.f / l_run[i];
         const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
         const int ch = head * DV + tx * DPT;
-        __half* op = p.out + ((((size_t)b * (p.T / p.Wimg) + hh) * (p.C / 8) + ch / 8) * p.Wimg + ww) * 8 + (ch & 7);
 #pragma unroll
-        for (int j = 0; j < DPT; ++j) {
-            const float val = o[i][j] * inv;
-            const __half hi = __float2half_rn(val);
-            op[j] = hi;
-            if (p.lo_off) op[p.lo_off + j] = __float2half_rn(val - __half2float(hi));
-        }
+        for (int j = 0; j < DPT; ++j)
+            store_operand_elem(p.out, p.lo_off, p.parts, (size_t)b * (p.T / p.Wimg) + hh, p.C, p.Wimg, ww, ch + j,
+                               o[i][j] * inv);
     }
 }
 
@@ -494,11 +485,11 @@ static int launch_fa(const FAParams& p, int B, int heads, cudaStream_t st) {
 extern "C" int b200_flash_attention(const float* qkv, int E, void* out, int out_w, int parts, int B, int heads, int T,
                                     float scale, void* stream) {
     // self-attention on the fused in-projection output qkv fp32 [B,T,3E] (q | k | v, head-major)
-    B200_CHECK_ARG(qkv && out && (parts == 1 || parts == 2) && heads > 0 && E % heads == 0);
+    B200_CHECK_ARG(qkv && out && (parts >= 1 && parts <= 3) && heads > 0 && E % heads == 0);
     B200_CHECK_ARG(out_w > 0 && T % out_w == 0);
     const int d = E / heads;
     FAParams p{qkv, nullptr, qkv + E, nullptr, qkv + 2 * E, nullptr, nullptr, nullptr, 3 * E, 0, 3 * E, 0, 3 * E, 0,
-               d, 0, d, T, 0, (__half*)out, parts == 2 ? (size_t)B * T * E : 0, E, out_w, scale};
+               d, 0, d, T, 0, (__half*)out, (size_t)B * T * E, parts, E, out_w, scale};
     if (d == 64) return launch_fa<64, 64>(p, B, heads, (cudaStream_t)stream);
     if (d == 32) return launch_fa<32, 32>(p, B, heads, (cudaStream_t)stream);
     set_error("flash_attention: head dim %d not supported (32 or 64)", d);
@@ -508,9 +499,9 @@ extern "C" int b200_flash_attention(const float* qkv, int E, void* out, int out_
 extern "C" int b200_flash_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
                                        const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                                        int L2, float scale2, void* stream) {
-    B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out && (parts == 1 || parts == 2));
+    B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out && (parts >= 1 && parts <= 3));
     B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32 && out_w > 0 && T % out_w == 0 && L2 >= 0);
     FAParams p{qkv, pos_p, qkv + C, pos_p, qkv + 2 * C, kl, pos_l, vl, 3 * C, C, 3 * C, C, 3 * C, C,
-               32, 32, 32, T, L2, (__half*)out, parts == 2 ? (size_t)B * T * C : 0, C, out_w, scale2};
+               32, 32, 32, T, L2, (__half*)out, (size_t)B * T * C, parts, C, out_w, scale2};
     return launch_fa<64, 32>(p, B, heads, (cudaStream_t)stream);
 }

@@ -2,6 +2,7 @@
 // mbarrier / cp.async / cp.async.bulk (TMA engine) / tcgen05 (tensor cores + TMEM).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -34,7 +35,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // Programmatic dependent launch (PDL): every kernel of the denoiser step is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, calls pdl_launch_dependents() first thing and pdl_wait() before
 // its first global-memory access.  The next kernel's CTAs are then scheduled (and run their prologue: barrier init,
-// TMEM allocation, coefficient setup) while the tail of the previous kernel is still draining.  B200_PDL=0 disables.
+// TMEM allocation, coefficient setup) while the tail of the previous kernel is still draining.  Opt-in with B200_PDL=1 (measured neutral-to-slightly-negative inside CUDA graphs).
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
@@ -143,6 +144,16 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, kind::f8f6f4 (here: E4M3 x E4M3, K = 32 per instruction, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 //   element (row r, k) lives at start + (r/8)*sbo + (r%8)*16 + (k/8)*lbo + (k%8)*2   [fp16]
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -153,7 +164,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
     return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
-// instruction descriptor: D fp32, A/B fp16, both K-major, M x N
+// instruction descriptor: D fp32, A/B fp16 (kind::f16) or E4M3 (kind::f8f6f4: format code 0 as well), K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -175,6 +186,39 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 
 // x * sigmoid(x); fast reciprocal (~2 ulp) -- the result is rounded to fp16 hi + lo right after
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// ---- "fp16 + fp8 correction" operand encoding (conv precision mode parts = 3) ----
+//   x = hi16 + lo,  lo ~ 2^-11 |x|:   plane 0 keeps hi16 (fp16);  plane 1 keeps, per 16-channel chunk, two 16-byte
+//   units per pixel: L8 = e4m3(lo * 2^11) and A8 = e4m3(x).  The conv then computes
+//   hi16 x w16  (kind::f16)  +  [L8 | A8] x [e4m3(w 2^-11) | e4m3(w - w16)]  (ONE kind::f8f6f4 MMA, K = 32).
+constexpr float F8_LO_SCALE = 2048.f;
+__device__ __forceinline__ uint32_t f8x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ uint8_t f8x1(float a) {
+    return (uint8_t)__nv_cvt_float_to_fp8(a, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float f8_to_float(uint8_t v) {
+    const __half_raw h = __nv_cvt_fp8_to_halfraw(v, __NV_E4M3);
+    return __half2float(__half(h));
+}
+// scalar store of channel `ch` of pixel (bh = b*H + h, ww) into a slab-major conv operand (parts = 1, 2 or 3);
+// plane_elems = B*H*W*C (fp16 elements per plane)
+__device__ __forceinline__ void store_operand_elem(__half* out, size_t plane_elems, int parts, size_t bh, int C, int W,
+                                                   int ww, int ch, float val) {
+    const __half hi = __float2half_rn(val);
+    out[((bh * (C / 8) + ch / 8) * W + ww) * 8 + (ch & 7)] = hi;
+    if (parts == 2) {
+        out[plane_elems + ((bh * (C / 8) + ch / 8) * W + ww) * 8 + (ch & 7)] = __float2half_rn(val - __half2float(hi));
+    } else if (parts == 3) {
+        uint8_t* p1 = reinterpret_cast<uint8_t*>(out + plane_elems);
+        const size_t unit = ((bh * (C / 16) + ch / 16) * 2) * (size_t)W + ww;   // 16-byte units; + W for the A8 slab
+        p1[unit * 16 + (ch & 15)] = f8x1((val - __half2float(hi)) * F8_LO_SCALE);
+        p1[(unit + W) * 16 + (ch & 15)] = f8x1(val);
+    }
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

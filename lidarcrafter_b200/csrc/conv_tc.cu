@@ -13,6 +13,11 @@
 //                NP = 2 -> error-compensated split a = a_hi + a_lo, w = w_hi + w_lo (all fp16):
 //                a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (3 MMAs, ~2^-22 relative) -- the mode that meets the
 //                reference's 1e-3 fp32 tolerance.  Weights are pre-scaled by a power of two (w_inv undoes it).
+//                NP = 3 -> fp16 main term + fp8 correction: the two small cross terms a_lo*w_hi + a_hi*w_lo (2^-11 of
+//                the result) only need ~3 significant bits, so they are evaluated by ONE kind::f8f6f4 MMA (K = 32 =
+//                [e4m3(a_lo 2^11) | e4m3(a)] x [e4m3(w 2^-11) | e4m3(w_lo)]) at twice the fp16 rate: 2 MMA time
+//                units per product instead of 3, ~5e-5 relative through the whole UNet.  (NP = 4: same operands,
+//                corrections in their own accumulator columns, added in the epilogue.)
 //   * A (activations) live in HBM "slab-major": [part][b][h][C/8][w][8] fp16, i.e. for one image row and one
 //     8-channel group all pixels are contiguous at a 16-byte pitch -- which IS the canonical no-swizzle K-major
 //     shared-memory layout of a tcgen05 operand.  For every K chunk the R+2 halo rows are staged ONCE by the TMA
@@ -56,20 +61,23 @@ constexpr int EPI_WARPS = 8;
 
 template <int BN, int R, int TAPS, int NP>
 struct ConvCfg {
-    static constexpr int KC = NP == 2 ? 16 : 32;  // channels per K chunk
+    static constexpr int PL = NP == 1 ? 1 : 2;    // operand planes (hi | lo or fp8 pair)
+    static constexpr bool F8 = NP >= 3;
+    static constexpr bool SEP = NP == 4;
+    static constexpr int KC = NP == 1 ? 32 : 16;  // channels per K chunk
     static constexpr int KG = KC / 8;             // 8-channel groups (slabs) per row
     static constexpr int KS = KC / 16;            // MMA K steps per chunk
     static constexpr int HALO = TAPS == 9 ? 1 : 0;
     static constexpr int NPX = PIX + 2 * HALO;
     static constexpr int SLAB = NPX * 16;  // bytes: one 8-channel group of one staged row
     static constexpr int RA = R + 2 * HALO;
-    static constexpr int NSLAB = NP * RA * KG;
+    static constexpr int NSLAB = PL * RA * KG;
     static constexpr int A_PART = RA * KG * SLAB;
-    static constexpr int A_STAGE = NP * A_PART;
+    static constexpr int A_STAGE = PL * A_PART;
     static constexpr int TW = TAPS == 9 ? 3 : 1;  // taps per B stage (one filter row)
     static constexpr int TG = TAPS == 9 ? 3 : 1;  // B stages per chunk
     static constexpr int B_PART = BN * KC * 2;
-    static constexpr int B_TAP = NP * B_PART;
+    static constexpr int B_TAP = PL * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
     static constexpr int EPI_STG = EPI_WARPS * 32 * 36 * 4;            // per-warp transpose staging
     static constexpr int EPI = EPI_STG + EPI_WARPS * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
@@ -88,7 +96,7 @@ struct ConvCfg {
     // once for 2 BN accumulator columns instead of twice) and only a_lo x w_hi remains an N = BN MMA.  The two partial
     // accumulators (columns [0,BN) and [BN,2BN)) are added in the epilogue.
     static constexpr bool MERGE = (NP == 2 && 2 * R * BN <= 256);
-    static constexpr int ACC_ROW = MERGE ? 2 * BN : BN;
+    static constexpr int ACC_ROW = (MERGE || SEP) ? 2 * BN : BN;
     static constexpr int ACC_COLS = R * ACC_ROW;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
                 const int nt = (tile / (WT * HG)) % NT;
-                const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (NP * BN * KC);
+                const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (C::PL * BN * KC);
                 for (int q = 0; q < NCH * C::TG; ++q, ++ib) {
                     const int s = ib % C::SB;
                     const uint32_t ph = (ib / C::SB) & 1;
@@ -270,7 +278,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                                     const uint64_t a_hi = make_smem_desc(a_addr, C::SLAB, 128);
                                     const uint64_t b_hi = make_smem_desc(b_addr, KGS, 128);
                                     const uint32_t first = (uint32_t)((c | dy | dx | ks) != 0);
-                                    if (C::MERGE) {
+                                    if (C::F8) {
+                                        // plane 1 of both operands: [L8 | A8] x [e4m3(w 2^-11) | e4m3(w_lo)], K = 32
+                                        const uint64_t a_f8 = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
+                                        const uint64_t b_f8 = make_smem_desc(b_addr + C::B_PART, KGS, 128);
+                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc, first);
+                                        tc_mma_f8(acc + o * C::ACC_ROW + (C::SEP ? BN : 0), a_f8, b_f8, idesc,
+                                                  C::SEP ? first : 1u);
+                                    } else if (C::MERGE) {
                                         const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
                                         tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc2, first);   // [hi*hi | hi*lo]
                                         tc_mma_f16(acc + o * C::ACC_ROW, a_lo, b_hi, idesc, 1u);       // += lo*hi
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 {
                     float v[32];
                     tmem_ld_32x32(acc + o * C::ACC_ROW + sl * 32, v);
-                    if (C::MERGE) {
+                    if (C::MERGE || C::SEP) {
                         float v2[32];
                         tmem_ld_32x32(acc + o * C::ACC_ROW + BN + sl * 32, v2);
 #pragma unroll
@@ -497,6 +512,32 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
     }
 }
 
+// parts = 3 ("fp16 + fp8 correction"): per (n-tile, 16-channel chunk, tap) the B stage image is
+//   plane 0: [2 (8-channel groups)][bn][8] fp16(w*s)         plane 1: [2][bn][16] e4m3: {w*s*2^-11, w*s - fp16(w*s)}
+// with s a power of two such that max|w*s| is in [2^14, 2^15).
+__global__ void pack_weight_f8_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin, int taps,
+                                      int bn, float wscale) {
+    const size_t total = (size_t)Cout * Cin * taps;
+    const int nch = Cin / 16;
+    uint8_t* out8 = reinterpret_cast<uint8_t*>(out);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e16 = r % 16; r /= 16;
+        const int n = r % bn; r /= bn;
+        const int tap = r % taps; r /= taps;
+        const int c = r % nch; r /= nch;
+        const int nt = (int)r;
+        const int k = c * 16 + e16, co = nt * bn + n;
+        const float v = w[((size_t)co * Cin + k) * taps + tap] * wscale;
+        const __half hi = __float2half_rn(v);
+        const size_t tap_base = (((size_t)nt * nch + c) * taps + tap) * (size_t)(bn * 32);   // halves per tap image
+        out[tap_base + ((size_t)(e16 / 8) * bn + n) * 8 + (e16 & 7)] = hi;
+        const size_t p1 = (tap_base + (size_t)bn * 16) * 2;                                   // byte offset of plane 1
+        out8[p1 + (size_t)n * 16 + e16] = f8x1(v * (1.f / F8_LO_SCALE));
+        out8[p1 + ((size_t)bn + n) * 16 + e16] = f8x1(v - __half2float(hi));
+    }
+}
+
 // plain layout for the cross-check kernel: [parts][tap][Cout][Cin]
 __global__ void pack_weight_plain_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
                                          int taps, int parts, float wscale) {
@@ -510,7 +551,11 @@ __global__ void pack_weight_plain_kernel(const float* __restrict__ w, __half* __
         const int tap = (int)r;
         const float v = w[((size_t)co * Cin + k) * taps + tap] * wscale;
         const __half hi = __float2half_rn(v);
-        out[i] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+        if (parts == 3)   // fp16 images of the e4m3 values the tensor-core path multiplies with
+            out[i] = part == 0 ? hi
+                               : __float2half_rn(f8_to_float(f8x1(part == 1 ? v * (1.f / F8_LO_SCALE) : v - __half2float(hi))));
+        else
+            out[i] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
     }
 }
 
@@ -551,7 +596,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
         const __half* ap = p.a + (((size_t)(b * p.H + gh) * (p.Cin / 8)) * p.W + gw) * 8;
         const __half* wp = p.w + ((size_t)tap * p.Cout + co0) * p.Cin;
         for (int k = 0; k < p.Cin; k += 8) {
-            float av[8];
+            float av[8], l8v[8], a8v[8];
             if (ok) {
                 const __half* apk = ap + (size_t)(k / 8) * p.W * 8;
                 load8h(apk, av);
@@ -560,10 +605,21 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
                     load8h(apk + a_part, lo);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) av[e] += lo[e];
+                } else if (parts == 3) {
+                    // plane 1: per 16-channel chunk {L8 slab, A8 slab}, 16 bytes per pixel each
+                    const uint8_t* p1 = reinterpret_cast<const uint8_t*>(p.a + a_part);
+                    const size_t unit = (((size_t)(b * p.H + gh) * (p.Cin / 16) + k / 16) * 2) * p.W + gw;
+                    const uint2 l8 = *reinterpret_cast<const uint2*>(p1 + unit * 16 + (k & 8));
+                    const uint2 a8 = *reinterpret_cast<const uint2*>(p1 + (unit + p.W) * 16 + (k & 8));
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        l8v[e] = f8_to_float((uint8_t)(((e < 4 ? l8.x : l8.y) >> (8 * (e & 3))) & 0xff));
+                        a8v[e] = f8_to_float((uint8_t)(((e < 4 ? a8.x : a8.y) >> (8 * (e & 3))) & 0xff));
+                    }
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) av[e] = 0.f;
+                for (int e = 0; e < 8; ++e) av[e] = l8v[e] = a8v[e] = 0.f;
             }
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
@@ -577,6 +633,13 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
                 }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[n] = fmaf(av[e], wv[e], acc[n]);
+                if (parts == 3) {   // the same two fp8 cross terms the tensor-core path adds
+                    float w1[8], w2[8];
+                    load8h(wp + w_part + (size_t)n * p.Cin + k, w1);
+                    load8h(wp + 2 * w_part + (size_t)n * p.Cin + k, w2);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[n] = fmaf(l8v[e], w1[e], fmaf(a8v[e], w2[e], acc[n]));
+                }
             }
         }
     }
@@ -617,7 +680,7 @@ extern "C" int b200_conv_set_debug(void* dbg_u64) {
 }
 
 extern "C" size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts) {
-    return (size_t)Cout * Cin * taps * parts;
+    return (size_t)Cout * Cin * taps * (parts >= 3 ? 2 : parts);   // fp16-sized elements (parts 3: fp16 + 2 x e4m3)
 }
 
 static int pack_blocks(size_t total) { return (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256); }
@@ -629,8 +692,15 @@ extern "C" int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, in
     B200_CHECK_ARG(w && wpacked);
     B200_CHECK_ARG(taps == 9 || taps == 1);
     B200_CHECK_ARG(bn == 64 || bn == 128);
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 4);
     B200_CHECK_ARG(Cout % bn == 0 && Cin % 32 == 0);
+    if (parts >= 3) {
+        const size_t n = (size_t)Cout * Cin * taps;
+        pack_weight_f8_kernel<<<pack_blocks(n), 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpacked, Cout, Cin, taps, bn,
+                                                                                wscale);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     const size_t total = (size_t)Cout * Cin * taps * parts;
     pack_weight_kernel<<<pack_blocks(total), 256, 0, (cudaStream_t)stream>>>(
         w, (__half*)wpacked, Cout, Cin, taps, bn, parts, b200_conv_merged(bn, rows, parts), wscale);
@@ -642,7 +712,7 @@ extern "C" int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, 
                                            float wscale, void* stream) {
     B200_CHECK_ARG(w && w16);
     B200_CHECK_ARG(taps == 9 || taps == 1);
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 3);
     const size_t total = (size_t)Cout * Cin * taps * parts;
     pack_weight_plain_kernel<<<pack_blocks(total), 256, 0, (cudaStream_t)stream>>>(w, (__half*)w16, Cout, Cin, taps,
                                                                                    parts, wscale);
@@ -656,7 +726,7 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(a && wpacked && out);
     B200_CHECK_ARG(B > 0 && H > 0 && W > 0);
     B200_CHECK_ARG(taps == 9 || taps == 1);
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 4);
     B200_CHECK_ARG(W % PIX == 0 && Cin % 32 == 0 && Cin >= 32);
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
     B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
@@ -684,6 +754,14 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CONV_CASE(64, 4, 2)
     B200_CONV_CASE(128, 1, 2)
     B200_CONV_CASE(128, 2, 2)
+    B200_CONV_CASE(64, 1, 3)
+    B200_CONV_CASE(64, 2, 3)
+    B200_CONV_CASE(64, 4, 3)
+    B200_CONV_CASE(128, 1, 3)
+    B200_CONV_CASE(128, 2, 3)
+    B200_CONV_CASE(64, 1, 4)
+    B200_CONV_CASE(64, 2, 4)
+    B200_CONV_CASE(128, 1, 4)
 #undef B200_CONV_CASE
     set_error("conv_tc: unsupported tile bn=%d rows=%d (need rows*bn <= 256)", bn, rows);
     return B200_E_ARG;
@@ -694,8 +772,8 @@ extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias,
                               int ring, int parts, void* stream) {
     B200_CHECK_ARG(a && w16 && out);
     B200_CHECK_ARG(taps == 9 || taps == 1);
-    B200_CHECK_ARG(parts == 1 || parts == 2);
-    B200_CHECK_ARG(Cin % 8 == 0 && Cout % 32 == 0);
+    B200_CHECK_ARG(parts >= 1 && parts <= 3);
+    B200_CHECK_ARG(Cin % (parts == 3 ? 16 : 8) == 0 && Cout % 32 == 0);
     B200_CHECK_ARG(!stats || (H * W) % 32 == 0);
     ConvParams p{(const __half*)a, (const __half*)w16, bias, res, out, stats, out_scale, w_inv,
                  B, H, W, Cin, Cout, ring, 0};

@@ -12,7 +12,7 @@ bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("B200_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;   // measured on B200 inside the step graphs: no gain (4.90 vs 4.78 ms), so opt-in
     }
     return v == 1;
 }
@@ -75,6 +75,38 @@ __device__ __forceinline__ void gn_coefficients(const double* __restrict__ st0, 
     }
 }
 
+// second operand plane of one lane's 8 channels (v = fp32 values, h = their fp16 roundings), 16 bytes at `dst`:
+//   parts == 2: lo = fp16(x - hi)  (error-compensation term of the fp16x3 split)
+//   parts == 3: per 16-channel chunk the even 8-channel slab position holds L8 = e4m3((x - hi) * 2^11) of all 16
+//               channels and the odd one A8 = e4m3(x) (see common.cuh); the two lanes of a chunk swap halves.
+__device__ __forceinline__ void store_plane1(__half* dst, const float* v, const __half2* h, int parts, int lane) {
+    float lo[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(h[e]);
+        lo[2 * e] = v[2 * e] - hf.x;
+        lo[2 * e + 1] = v[2 * e + 1] - hf.y;
+    }
+    if (parts == 2) {
+        __half2 l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l[e] = __floats2half2_rn(lo[2 * e], lo[2 * e + 1]);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(l);
+    } else {
+        uint2 l8, a8;
+        l8.x = f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE, lo[3] * F8_LO_SCALE);
+        l8.y = f8x4(lo[4] * F8_LO_SCALE, lo[5] * F8_LO_SCALE, lo[6] * F8_LO_SCALE, lo[7] * F8_LO_SCALE);
+        a8.x = f8x4(v[0], v[1], v[2], v[3]);
+        a8.y = f8x4(v[4], v[5], v[6], v[7]);
+        const bool odd = lane & 1;
+        const uint2 send = odd ? l8 : a8;
+        uint2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        *reinterpret_cast<uint4*>(dst) = odd ? make_uint4(recv.x, recv.y, a8.x, a8.y) : make_uint4(l8.x, l8.y, recv.x, recv.y);
+    }
+}
+
 // output layout ("slab-major", the tcgen05 no-swizzle K-major operand image of one image row):
 //   y[part][b][h][C/8][w][8]  -- for a fixed (row, 8-channel group) all pixels are contiguous at a 16 B pitch
 __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
@@ -83,7 +115,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, const float* __restrict__ ada,
                                                      int ada_stride, int groups, float eps, int silu,
                                                      __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
-                                                     int HW, int W, int pix_per_block) {
+                                                     int parts, int HW, int W, int pix_per_block) {
     // dynamic shared memory sized by the channel count (24 B / channel): keeps 8 blocks resident per SM
     extern __shared__ __align__(16) unsigned char gn_smem[];
     pdl_launch_dependents();
@@ -143,15 +175,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
 #pragma unroll
                 for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                 *reinterpret_cast<uint4*>(y_raw + oi) = *reinterpret_cast<const uint4*>(h);
-                if (lo_off) {
-                    __half2 l[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 hf = __half22float2(h[e]);
-                        l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                    }
-                    *reinterpret_cast<uint4*>(y_raw + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
-                }
+                if (parts >= 2) store_plane1(y_raw + lo_off + oi, v, h, parts, lane);
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -162,15 +186,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x
 #pragma unroll
             for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
             *reinterpret_cast<uint4*>(y + oi) = *reinterpret_cast<const uint4*>(h);
-            if (lo_off) {  // error-compensation term: lo = fp16(x - fp32(hi))
-                __half2 l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 hf = __half22float2(h[e]);
-                    l[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                }
-                *reinterpret_cast<uint4*>(y + lo_off + oi) = *reinterpret_cast<const uint4*>(l);
-            }
+            if (parts >= 2) store_plane1(y + lo_off + oi, v, h, parts, lane);
         }
     }
 }
@@ -645,11 +661,12 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
                                const double* stats1, const float* gamma, const float* beta, const float* ada,
                                int ada_stride, int groups, float eps, int silu, void* y, void* y_raw, int parts, int B,
                                int H, int W, void* stream) {
-    B200_CHECK_ARG(parts == 1 || parts == 2);
+    B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(W % 8 == 0);
     const int HW = H * W;
     B200_CHECK_ARG(x0 && y && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && (C1 == 0 || x1));
     const int C = C0 + C1;
+    B200_CHECK_ARG(parts != 3 || C % 32 == 0);   // fp8 plane: whole warps per 32-channel item
     B200_CHECK_ARG(C <= GN_MAX_C);
     if (stats0) {
         B200_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0);
@@ -664,7 +681,7 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     dim3 grid(cdiv(HW, ppb), B);
     launch_pdl(gn_act_kernel, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1, gamma,
                beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
-               parts == 2 ? (size_t)B * HW * (C0 + C1) : (size_t)0, HW, W, ppb);
+               (size_t)B * HW * (C0 + C1), parts, HW, W, ppb);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

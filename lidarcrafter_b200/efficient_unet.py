@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .engine import Act, Plan, PlanBuilder, _ptr, _sp
+from .engine import Act, Plan, PlanBuilder, _ptr, _sp, precision_parts
 
 
 def _n_tuple(x, n):
@@ -207,11 +207,10 @@ class EfficientUNet(nn.Module):
         super().__setattr__(name, value)
 
     def get_plan(self, B: int) -> "EfficientUNetPlan":
-        if self.precision not in ("fp16x3", "fp16"):
-            raise ValueError(f"precision must be 'fp16x3' or 'fp16', got {self.precision!r}")
+        parts = precision_parts(self.precision)
         key = (B, self.conv_impl, self.precision)
         if key not in self._plans:
-            self._plans[key] = EfficientUNetPlan(self, B, self.conv_impl, 2 if self.precision == "fp16x3" else 1)
+            self._plans[key] = EfficientUNetPlan(self, B, self.conv_impl, parts)
         return self._plans[key]
 
     @torch.no_grad()

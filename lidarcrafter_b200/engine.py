@@ -60,13 +60,33 @@ def pick_tile(B: int, H: int, W: int, Cout: int, taps: int, parts: int = 2, sms:
     return best[1], best[2]
 
 
-def weight_scale(weight: torch.Tensor) -> float:
-    """Power of two s with max|w| * s in [256, 512): keeps the fp16 hi/lo split of small weights out of
-    the subnormal range; undone exactly in the conv epilogue (w_inv = 1 / s)."""
+def weight_scale(weight: torch.Tensor, parts: int = 2) -> float:
+    """Power of two s, undone exactly in the conv epilogue (w_inv = 1 / s).
+    parts 1/2: max|w| * s in [256, 512) -- keeps the fp16 hi/lo split of small weights out of the subnormal range.
+    parts 3 (fp16 + fp8 correction): max|w| * s in [2^14, 2^15) so that BOTH fp8 correction operands, e4m3(w s 2^-11)
+    (max in [8, 16)) and e4m3(w s - fp16(w s)) (|.| <= 8), sit in the normal e4m3 range."""
     m = float(weight.detach().abs().max())
     if not (m > 0.0) or not math.isfinite(m):
         return 1.0
-    return float(2.0 ** (8 - math.floor(math.log2(m))))
+    return float(2.0 ** ((14 if parts >= 3 else 8) - math.floor(math.log2(m))))
+
+
+# conv precision modes (the ``precision`` attribute of the UNet mirrors) -> ``parts`` of the C-ABI
+#   fp16x3: error-compensated fp16 split, 3 fp16 MMAs / product, ~2e-6 relative through the UNet (fp32-grade)
+#   fp16f8: fp16 main term + ONE fp8 (e4m3) MMA for both correction cross terms, ~5e-5 relative (tolerance 1e-3)
+#   fp16  : single fp16 pass, ~1.7e-3 (outside the 1e-3 tolerance; kept for measurement only)
+PRECISION_PARTS = {"fp16x3": 2, "fp16f8": 3, "fp16": 1}
+
+
+def precision_parts(precision: str) -> int:
+    if precision not in PRECISION_PARTS:
+        raise ValueError(f"precision must be one of {sorted(PRECISION_PARTS)}, got {precision!r}")
+    return PRECISION_PARTS[precision]
+
+
+def planes(parts: int) -> int:
+    """fp16-sized planes of a conv operand: parts 1 -> 1; 2 (hi, lo) -> 2; 3 (fp16 hi + e4m3 pair) -> 2"""
+    return 1 if parts == 1 else 2
 
 
 _TUNE_CACHE: dict = {}
@@ -90,8 +110,8 @@ class PackedConv:
         Cout, Cin, kh, kw = weight.shape
         self.Cout, self.Cin, self.taps, self.bn, self.rows, self.parts = Cout, Cin, kh * kw, bn, rows, parts
         w = weight.detach().float().contiguous()
-        self.wscale = weight_scale(w)
-        self.packed = torch.empty(Cout * Cin * self.taps * parts, dtype=torch.float16, device=w.device)
+        self.wscale = weight_scale(w, parts)
+        self.packed = torch.empty(Cout * Cin * self.taps * planes(parts), dtype=torch.float16, device=w.device)
         lib.pack_conv_weight(_ptr(w), _ptr(self.packed), Cout, Cin, self.taps, bn, rows, parts, self.wscale, stream)
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self._keep = w
@@ -104,7 +124,8 @@ class Plan:
         self.lib = lib
         self.device = device
         self.B = B
-        self.parts = parts            # 2 = error-compensated fp16 split (meets 1e-3), 1 = single fp16 pass
+        # 2 = error-compensated fp16 split (fp32-grade), 3 = fp16 + fp8 correction terms (~5e-5), 1 = single fp16 pass
+        self.parts = parts
         self.ops = []                 # list of (callable, args-without-stream)
         self.meta = []                # (kernel name, algorithmic flops, algorithmic bytes) per op
         self.bufs = []                # keep-alive
@@ -120,8 +141,8 @@ class Plan:
         return t
 
     def f16(self, *shape):
-        """fp16 conv operand [parts][*shape]"""
-        t = torch.empty(self.parts, *shape, dtype=torch.float16, device=self.device)
+        """conv operand [planes][*shape] (fp16-sized elements; plane 1 of parts 3 holds e4m3 pairs)"""
+        t = torch.empty(planes(self.parts), *shape, dtype=torch.float16, device=self.device)
         self.bufs.append(t)
         return t
 
@@ -201,8 +222,8 @@ class PlanBuilder:
         fl = 2.0 * self.B * H * W * taps * Cin * Cout
         self.p.flops += fl
         npix = self.B * H * W
-        by = npix * (2.0 * self.p.parts * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
-            + 2.0 * self.p.parts * taps * Cin * Cout
+        by = npix * (2.0 * planes(self.p.parts) * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
+            + 2.0 * planes(self.p.parts) * taps * Cin * Cout
         if self.p.conv_impl == "tc":
             bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
             pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
@@ -212,7 +233,7 @@ class PlanBuilder:
                        self.p.parts, name="conv_tc", flops=fl, nbytes=by)
         else:
             w = weight.detach().float().contiguous()
-            ws = weight_scale(w)
+            ws = weight_scale(w, self.p.parts)
             w16 = torch.empty(Cout * Cin * taps * self.p.parts, dtype=torch.float16, device=w.device)
             self.lib.pack_conv_weight_plain(_ptr(w), _ptr(w16), Cout, Cin, taps, self.p.parts, ws, self.stream)
             b32 = None if bias is None else bias.detach().float().contiguous()
@@ -276,7 +297,7 @@ class PlanBuilder:
                    _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b),
                    ada_ptr, ada_stride, groups, float(eps), 1 if silu else 0, _ptr(y), _ptr(y_raw), self.p.parts, self.B,
                    a0.H, a0.W, name="gn_act_f16",
-                   nbytes=self.B * HW * C * (4.0 + 2.0 * self.p.parts * (2 if also_raw else 1)))
+                   nbytes=self.B * HW * C * (4.0 + 2.0 * planes(self.p.parts) * (2 if also_raw else 1)))
         return (y, y_raw) if also_raw else y
 
     def cast16(self, srcs: list[Act]) -> torch.Tensor:

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib
 from .efficient_unet import _ConvP, _FourierP, _KernelBuf, _n_tuple, _zero, fourier_features, generate_polar_coords
-from .engine import Act, Plan, PlanBuilder, _ptr, _sp
+from .engine import Act, Plan, PlanBuilder, _ptr, _sp, precision_parts
 
 GN_GROUPS = 32
 GN_EPS = 1e-5
@@ -143,11 +143,10 @@ class LayoutUnetV1(nn.Module):
         super().__setattr__(name, value)
 
     def get_plan(self, B: int) -> "LayoutUnetPlan":
-        if self.precision not in ("fp16x3", "fp16"):
-            raise ValueError(f"precision must be 'fp16x3' or 'fp16', got {self.precision!r}")
+        parts = precision_parts(self.precision)
         key = (B, self.conv_impl, self.precision)
         if key not in self._plans:
-            self._plans[key] = LayoutUnetPlan(self, B, self.conv_impl, 2 if self.precision == "fp16x3" else 1)
+            self._plans[key] = LayoutUnetPlan(self, B, self.conv_impl, parts)
         return self._plans[key]
 
     @torch.no_grad()

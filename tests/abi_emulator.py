@@ -45,6 +45,53 @@ def i32(ptr, *shape):
     return None if t is None else t.view(*shape)
 
 
+def u8(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_uint8, np.uint8)
+    return None if t is None else t.view(*shape)
+
+
+F8_LO_SCALE = 2048.0
+
+
+def e4m3(v):
+    """fp32 -> e4m3 (round to nearest even, saturate to +-448) as uint8 codes"""
+    return v.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def e4m3_value(codes):
+    return codes.view(torch.float8_e4m3fn).float()
+
+
+def n_planes(parts):
+    return 1 if parts == 1 else 2
+
+
+def store_operand(ptr, x, parts, B, H, W, C):
+    """x [B, H, W, C] fp32 -> conv operand at ``ptr`` (include/b200lidar.h, "conv operand layout")"""
+    x = x.reshape(B, H, W, C).float()
+    hi = x.half()
+    f16(ptr, B, H, C // 8, W, 8).copy_(to_slab(hi))
+    if parts == 2:
+        f16(ptr + 2 * B * H * W * C, B, H, C // 8, W, 8).copy_(to_slab((x - hi.float()).half()))
+    elif parts == 3:
+        l8 = e4m3((x - hi.float()) * F8_LO_SCALE).view(B, H, W, C // 16, 16)
+        a8 = e4m3(x).view(B, H, W, C // 16, 16)
+        pair = torch.stack([l8, a8], dim=0).permute(1, 2, 4, 0, 3, 5).contiguous()   # [B, H, C/16, 2, W, 16]
+        u8(ptr + 2 * B * H * W * C, B, H, C // 16, 2, W, 16).copy_(pair)
+
+
+def load_operand(ptr, parts, B, H, W, C):
+    """-> list of fp32 [B, H, W, C] tensors: [hi] / [hi, lo] / [hi, L8, A8]"""
+    out = [from_slab(f16(ptr, B, H, C // 8, W, 8)).float()]
+    if parts == 2:
+        out.append(from_slab(f16(ptr + 2 * B * H * W * C, B, H, C // 8, W, 8)).float())
+    elif parts == 3:
+        pair = e4m3_value(u8(ptr + 2 * B * H * W * C, B, H, C // 16, 2, W, 16))
+        for sub in range(2):
+            out.append(pair[:, :, :, sub].permute(0, 1, 3, 2, 4).reshape(B, H, W, C))
+    return out
+
+
 def to_slab(x):
     """[..., H, W, C] -> slab-major [..., H, C/8, W, 8] (the conv operand layout)"""
     *lead, H, W, C = x.shape
@@ -85,11 +132,33 @@ class EmulatedLib:
     def conv_merged(bn, rows, parts):
         return 1 if (parts == 2 and 2 * rows * bn <= 256) else 0
 
+    @staticmethod
+    def _wplanes(v, parts):
+        """scaled fp32 weights -> the planes the conv multiplies with (fp32 values):
+        parts 1: [fp16(v)]; 2: [hi, lo]; 3: [hi, e4m3(v 2^-11), e4m3(v - hi)]"""
+        hi = v.half().float()
+        if parts == 1:
+            return [hi]
+        if parts == 2:
+            return [hi, (v - hi).half().float()]
+        return [hi, e4m3_value(e4m3(v / F8_LO_SCALE)), e4m3_value(e4m3(v - hi))]
+
     def pack_conv_weight(self, w, out, Cout, Cin, taps, bn, rows, parts, wscale, stream):
         self._rec("pack_conv_weight")
+        v = f32(w, Cout, Cin, taps) * wscale
+        if parts >= 3:
+            # per (n-tile, 16-channel chunk, tap): plane 0 [2][bn][8] fp16, plane 1 [2 (hi8, lo8)][bn][16] e4m3
+            hi = v.half().view(Cout // bn, bn, Cin // 16, 2, 8, taps).permute(0, 2, 5, 3, 1, 4).contiguous()
+            w1 = e4m3(v / F8_LO_SCALE).view(Cout // bn, bn, Cin // 16, 16, taps)
+            w2 = e4m3(v - v.half().float()).view(Cout // bn, bn, Cin // 16, 16, taps)
+            p1 = torch.stack([w1, w2], dim=0).permute(1, 3, 5, 0, 2, 4).contiguous()   # [nt][c][tap][2][bn][16]
+            img = torch.cat([hi.view(torch.uint8).reshape(Cout // bn, Cin // 16, taps, -1),
+                             p1.reshape(Cout // bn, Cin // 16, taps, -1)], dim=-1)
+            u8(out, Cout * Cin * taps * 4).copy_(img.reshape(-1))
+            return 0
         merged = self.conv_merged(bn, rows, parts)
         kc = 16 if parts == 2 else 32
-        W = self._split(f32(w, Cout, Cin, taps) * wscale, parts)        # [parts, Cout, Cin, taps]
+        W = self._split(v, parts)        # [parts, Cout, Cin, taps]
         # -> [Cout/bn][Cin/kc][taps][parts][kc/8][bn][8]   (merged mode, parts == 2 and bn == 64: [..][kc/8][parts][bn][8])
         t = W.view(parts, Cout // bn, bn, Cin // kc, kc // 8, 8, taps)
         t = (t.permute(1, 3, 6, 4, 0, 2, 5) if merged else t.permute(1, 3, 6, 0, 4, 2, 5)).contiguous()
@@ -98,14 +167,17 @@ class EmulatedLib:
 
     def pack_conv_weight_plain(self, w, out, Cout, Cin, taps, parts, wscale, stream):
         self._rec("pack_conv_weight_plain")
-        W = self._split(f32(w, Cout, Cin, taps) * wscale, parts)
+        W = torch.stack(self._wplanes(f32(w, Cout, Cin, taps) * wscale, parts)).half()
         f16(out, parts, taps, Cout, Cin).copy_(W.permute(0, 3, 1, 2))
         return 0
 
-    def _conv(self, a, W4, bias, res, scale, w_inv, out, stats, B, H, Wd, Cin, Cout, taps, ring, parts):
+    def _conv(self, a, Wp, bias, res, scale, w_inv, out, stats, B, H, Wd, Cin, Cout, taps, ring, parts):
+        """Wp: list of [Cout, Cin, k, k] fp32 weight planes matching load_operand()'s activation planes"""
         k = 3 if taps == 9 else 1
-        x = from_slab(f16(a, parts, B, H, Cin // 8, Wd, 8)).float().sum(0).permute(0, 3, 1, 2)
-        y = F.conv2d(_ring_pad(x, k // 2, ring), W4.float()) * w_inv
+        xs = [t.permute(0, 3, 1, 2) for t in load_operand(a, parts, B, H, Wd, Cin)]
+        if parts == 2:      # (a_hi + a_lo) x (w_hi + w_lo)
+            xs, Wp = [xs[0] + xs[1]], [Wp[0] + Wp[1]]
+        y = sum(F.conv2d(_ring_pad(x, k // 2, ring), w) for x, w in zip(xs, Wp)) * w_inv
         y = y.permute(0, 2, 3, 1)
         if bias:
             y = y + f32(bias, Cout)
@@ -123,21 +195,29 @@ class EmulatedLib:
         self._rec("conv_tc")
         assert W % 128 == 0 and Cin % KC == 0 and Cout % bn == 0 and H % rows == 0 and rows * bn <= 256
         k = 3 if taps == 9 else 1
+        if parts >= 3:
+            img = u8(wpacked, Cout // bn, Cin // 16, taps, bn * 64)
+            hi = img[..., :bn * 32].contiguous().view(torch.float16).view(Cout // bn, Cin // 16, taps, 2, bn, 8)
+            Wp = [hi.float().permute(0, 4, 1, 3, 5, 2).reshape(Cout, Cin, k, k)]
+            p1 = e4m3_value(img[..., bn * 32:].contiguous()).view(Cout // bn, Cin // 16, taps, 2, bn, 16)
+            for sub in range(2):
+                Wp.append(p1[:, :, :, sub].permute(0, 3, 1, 4, 2).reshape(Cout, Cin, k, k))
+            self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, 3)
+            return 0
         kc = 16 if parts == 2 else 32
-        assert rows * bn <= 256
         if self.conv_merged(bn, rows, parts):
-            t = f16(wpacked, Cout // bn, Cin // kc, taps, kc // 8, parts, bn, 8).float().sum(4)
+            t = f16(wpacked, Cout // bn, Cin // kc, taps, kc // 8, parts, bn, 8).float().permute(4, 0, 1, 2, 3, 5, 6)
         else:
-            t = f16(wpacked, Cout // bn, Cin // kc, taps, parts, kc // 8, bn, 8).float().sum(3)
-        W4 = t.permute(0, 4, 1, 3, 5, 2).reshape(Cout, Cin, k, k)
-        self._conv(a, W4, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
+            t = f16(wpacked, Cout // bn, Cin // kc, taps, parts, kc // 8, bn, 8).float().permute(3, 0, 1, 2, 4, 5, 6)
+        Wp = [tp.permute(0, 4, 1, 3, 5, 2).reshape(Cout, Cin, k, k) for tp in t]
+        self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
         return 0
 
     def conv_ffma(self, a, w16, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts, stream):
         self._rec("conv_ffma")
         k = 3 if taps == 9 else 1
-        W4 = f16(w16, parts, taps, Cout, Cin).float().sum(0).permute(1, 2, 0).reshape(Cout, Cin, k, k)
-        self._conv(a, W4, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
+        Wp = [t.permute(1, 2, 0).reshape(Cout, Cin, k, k) for t in f16(w16, parts, taps, Cout, Cin).float()]
+        self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
         return 0
 
     # ---- GN / stats ----
@@ -150,7 +230,7 @@ class EmulatedLib:
             x = torch.cat([x, f32(x1, B, HW, C1)], dim=-1)
         C = C0 + C1
         if y_raw:
-            f16(y_raw, parts, B, H, C // 8, W, 8).copy_(to_slab(self._split(x, parts).view(parts, B, H, W, C)))
+            store_operand(y_raw, x, parts, B, H, W, C)
         if st0:
             st = f64(st0, B, C0, 2)
             if C1:
@@ -177,7 +257,7 @@ class EmulatedLib:
             x = x * a[:, None, :] + b[:, None, :]
         if silu:
             x = F.silu(x)
-        f16(y, parts, B, H, C // 8, W, 8).copy_(to_slab(self._split(x, parts).view(parts, B, H, W, C)))
+        store_operand(y, x, parts, B, H, W, C)
         return 0
 
     def gn_act_f32(self, x, st, gamma, beta, groups, eps, silu, y, B, HW, C, stream):
@@ -215,8 +295,7 @@ class EmulatedLib:
         vm = torch.cat([v, vlh], 2)
         att = torch.softmax(qm @ km.transpose(-1, -2) * scale2, dim=-1)
         o = (att @ vm).transpose(1, 2).reshape(B, T, C)
-        f16(out, parts, B, T // out_w, C // 8, out_w, 8).copy_(
-            to_slab(self._split(o, parts).view(parts, B, T // out_w, out_w, C)))
+        store_operand(out, o, parts, B, T // out_w, out_w, C)
         return 0
 
     def channel_stats(self, x, stats, B, HW, C, stream):
@@ -290,8 +369,7 @@ class EmulatedLib:
         att = torch.softmax(Q @ K.transpose(-1, -2) * scale, dim=-1)
         o = (att @ V).transpose(1, 2).reshape(B, Tq, heads * dv)
         assert ldo == heads * dv
-        f16(out, parts, B, Tq // out_w, ldo // 8, out_w, 8).copy_(
-            to_slab(self._split(o, parts).view(parts, B, Tq // out_w, out_w, ldo)))
+        store_operand(out, o, parts, B, Tq // out_w, out_w, ldo)
         return 0
 
     def flash_attention(self, qkv, E, out, out_w, parts, B, heads, T, scale, stream):

@@ -25,6 +25,32 @@ def test_unet_forward_vs_reference_golden(name):
     assert err < TOL
 
 
+@pytest.mark.parametrize("name", ["eunet_mini", "eunet_full"])
+def test_unet_fp16f8_mode_vs_reference_golden(name):
+    """fp16 main term + e4m3 correction MMA: ~5e-5 relative, 20x inside the 1e-3 tolerance"""
+    res, nres, B = CASES[name]
+    m, _ = make_unet(res, nres)
+    m = m.cuda()
+    m.precision = "fp16f8"
+    x, t, y_ref = golden_inputs(name)
+    err = rel_l2(m(x.cuda(), t.cuda()).cpu(), y_ref)
+    print(name, "fp16f8 rel-L2 vs reference golden:", err)
+    assert err < 2e-4
+
+
+def test_unet_fp16f8_tensor_core_path_equals_cuda_core_crosscheck():
+    """same e4m3 / fp16 operands through tcgen05 (kind::f16 + kind::f8f6f4) and through CUDA-core FMAs"""
+    res, nres, B = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres)
+    m = m.cuda()
+    m.precision = "fp16f8"
+    x, t, _ = golden_inputs("eunet_mini")
+    y_tc = m(x.cuda(), t.cuda()).cpu()
+    m.conv_impl = "ffma"
+    y_ff = m(x.cuda(), t.cuda()).cpu()
+    assert rel_l2(y_tc, y_ff) < 2e-5
+
+
 def test_unet_fp16_single_pass_mode_is_close_but_looser():
     res, nres, B = CASES["eunet_mini"]
     m, _ = make_unet(res, nres)
@@ -66,9 +92,11 @@ def test_unet_batch8_vs_oracle_and_batch_independence():
 
 
 @pytest.mark.parametrize("mode,steps,eta", [("ddim", 3, 0.0), ("ddim", 2, 0.5), ("ddpm", 2, 0.0)])
-def test_sampler_vs_reference_golden(mode, steps, eta):
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16f8"])
+def test_sampler_vs_reference_golden(mode, steps, eta, precision):
     res, nres, _ = CASES["eunet_mini"]
     m, _ = make_unet(res, nres)
+    m.precision = precision
     ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type="eps", noise_schedule="cosine").cuda()
     # CPU generator => bit-identical noise stream to the reference run (randn on the CPU, copied over)
     g = torch.Generator().manual_seed(77)

@@ -15,6 +15,9 @@ timeout 600 python bench.py --steps 20 --warmup 3 --profile-ops --no-cpu-baselin
 echo "bench rc=$?"
 cat gpurun_out/bench.json | head -c 600
 timeout 300 python bench.py --steps 20 --warmup 3 --precision fp16 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err
+timeout 600 python bench.py --steps 20 --warmup 3 --precision fp16f8 --profile-ops --no-cpu-baseline > gpurun_out/bench_fp16f8.json 2> gpurun_out/bench_fp16f8.err
+echo "bench fp16f8 rc=$?"
+cat gpurun_out/bench_fp16f8.json | head -c 400
 timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
 if [ "${NCU:-0}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv \
