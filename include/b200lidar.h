@@ -34,15 +34,17 @@ const char* b200_last_error(void);
  * replaces: F.pad(circular W / zero H) + nn.Conv2d  (models/unets/ops.py:32-49,149-173) together with
  *           the bias add, the residual add and the 1/sqrt(2) scale of ResidualBlock.forward
  *           (models/unets/efficient_unet.py:112-115), and the GroupNorm statistics of the NEXT norm.
- *   a        : fp16 conv operand in SLAB-MAJOR layout [parts][B][H][Cin/8][W][8] (for one image row and one
- *              8-channel group all pixels are contiguous at a 16 B pitch = the tcgen05 no-swizzle K-major
- *              shared-memory image, so the TMA engine stages it with plain bulk copies), already
- *              normalised/activated by b200_gn_act_f16;
+ *   a        : "conv operand layout" (tile-major slabs): [planes][B][H][W/128][Cin/8][130][8] fp16-sized elements.
+ *              For one image row, one 128-pixel tile and one 8-channel group: 130 pixels at a 16-byte pitch = the ring
+ *              neighbour (w0-1) mod W, the tile's 128 pixels, the ring neighbour (w0+128) mod W.  That IS the tcgen05
+ *              no-swizzle K-major shared-memory image of the tile with its 3x3 halo, and the slabs of consecutive
+ *              channel groups are contiguous, so the TMA engine stages one (row, plane, K chunk) with ONE bulk copy.
+ *              Written (halo duplicates included) by b200_gn_act_f16 / the attention kernels;
  *              parts = 1: plain fp16;  parts = 2: a = a[0] (hi) + a[1] (lo), the error-compensated split
  *              (3 tensor-core MMAs per product, ~fp32 accuracy: ~2e-6 through the UNet);
  *              parts = 3 ("fp16 + fp8 correction", ~5e-5 through the UNet, inside the 1e-3 tolerance): plane 0 =
- *              fp16 hi as above; plane 1 (same byte size) = e4m3 pairs [B][H][Cin/16][2][W][16 bytes]: for every
- *              16-channel chunk and pixel one 16-byte unit L8 = e4m3((a - hi) * 2^11) and one unit A8 = e4m3(a).
+ *              fp16 hi as above; plane 1 (same byte size) = e4m3 pairs [B][H][W/128][Cin/16][2][130][16 bytes]: for
+ *              every 16-channel chunk and pixel one 16-byte unit L8 = e4m3((a - hi) * 2^11) and one unit A8 = e4m3(a).
  *              The kernel evaluates  hi x w16  with kind::f16 and BOTH cross terms a_lo*w_hi + a_hi*w_lo with ONE
  *              kind::f8f6f4 MMA (K = 32 = [L8 | A8] x [e4m3(w 2^-11) | e4m3(w - w16)]): 2 MMA time units instead
  *              of 3.  wscale must put max|w * wscale| in [2^14, 2^15) (both e4m3 weight planes in normal range).
@@ -90,7 +92,7 @@ int b200_conv_ffma(const void* a, const void* w16, const float* bias, const floa
  *   stats0/1 : fp64 [B,C,2] per-channel {sum,sumsq} of the sources; NULL => no normalisation (cast only)
  *   gamma/beta: [C0+C1] or NULL;  ada: fp32, scale at ada[b*ada_stride + c], shift at
  *               ada[b*ada_stride + (C0+C1) + c], NULL => none;  silu: 1 = apply x*sigmoid(x)
- *   y        : fp16 slab-major [parts][B][H][(C0+C1)/8][W][8] (the conv operand layout);
+ *   y        : conv operand layout [planes][B][H][W/128][(C0+C1)/8][130][8] (see b200_conv_tc; W % 128 == 0);
  *              parts = 2 also writes the residual lo = fp16(v - fp32(hi)); parts = 3 writes the e4m3 pair plane
  *              (see b200_conv_tc; needs (C0+C1) % 32 == 0)
  *   y_raw    : optional second output (same layout): the UN-normalised concatenated input as a conv operand
@@ -138,7 +140,7 @@ int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias
 /* ---- K2: attention ---------------------------------------------------------------------------------
  * softmax(q k^T * scale) v per (batch, head); q/k/v are slices of fp32 token-major tensors
  *   q: [B,Tq,ldq] at column offset head*dqk (+qoff), k: [B,Tk,ldk], v: [B,Tk,ldv];
- *   out fp16 slab-major conv operand [parts][B][Tq/out_w][ldo/8][out_w][8] (token t = row t/out_w, col t%out_w)
+ *   out: conv operand layout for an image [B][Tq/out_w][out_w][ldo] (token t = row t/out_w, col t%out_w; out_w % 128 == 0)
  * replaces: nn.MultiheadAttention core (efficient_unet.py:39-53) / QKVAttentionLegacy einsum-softmax-einsum
  *           (layout_unet_v1.py:488-505)                                                              */
 int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
@@ -150,7 +152,7 @@ int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, i
  *   positional embedding), kl / pos_l / vl fp32 [B,L2,C] (layout key content, positional, value);
  *   per head (d = C/heads = 32): q = [q_c;pos_p], k = [[k_c;pos_p] | [k_l;pos_l]], v = [v_c | v_l];
  *   scale2 = 1/sqrt(2d) (the reference multiplies q and k each by (2d)^-1/4).
- *   out fp16 slab-major conv operand [parts][B][T/out_w][C/8][out_w][8]                              */
+ *   out: conv operand layout for an image [B][T/out_w][out_w][C] (out_w % 128 == 0)                    */
 int b200_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
                       const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                       int L2, float scale2, void* stream);

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     }
     if (qi < nq) {
         const float inv = sInv[qi];
-        // slab-major conv operand: token t = (h, w) of an image of width Wimg; [b][h][ldo/8][w][8]
+        // conv operand (common.cuh): token t = (h, w) of an image of width Wimg
         const int tq = q0 + qi;
         const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
         const int ch = head * p.dv + dc * dper;
@@ -114,11 +114,11 @@ extern "C" int b200_attention(const float* q, int ldq, int qoff, const float* k,
                               int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq, int Tk,
                               int dqk, int dv, float scale, void* stream) {
     B200_CHECK_ARG(parts >= 1 && parts <= 3);
-    B200_CHECK_ARG(out_w > 0 && Tq % out_w == 0 && ldo % 8 == 0);
+    B200_CHECK_ARG(out_w > 0 && out_w % OTW == 0 && Tq % out_w == 0 && ldo % 8 == 0);
     B200_CHECK_ARG(q && k && v && out);
     B200_CHECK_ARG(dqk % 4 == 0 && (dv == 32 || dv == 64));
     B200_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && qoff % 4 == 0 && koff % 4 == 0 && voff % 4 == 0);
-    AttnParams p{q, k, v, (__half*)out, (size_t)B * Tq * ldo, parts, ldq, qoff, ldk, koff, ldv, voff, ldo, out_w, heads, Tq, Tk, dqk, dv, scale};
+    AttnParams p{q, k, v, (__half*)out, (size_t)B * Tq / out_w * (out_w / OTW) * (ldo / 8) * OPX * 8, parts, ldq, qoff, ldk, koff, ldv, voff, ldo, out_w, heads, Tq, Tk, dqk, dv, scale};
     const size_t smem = ((size_t)ATT_QT * dqk + (size_t)ATT_QT * (Tk + 1) + ATT_QT) * sizeof(float);
     B200_CHECK_ARG(smem <= 200 * 1024);
     static size_t smem_set = 0;
@@ -268,8 +268,8 @@ extern "C" int b200_attention_oa(const float* qkv, const float* pos_p, const flo
     B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out);
     B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32);   // num_head_channels = 32 in every config
-    B200_CHECK_ARG(out_w > 0 && T % out_w == 0 && L2 >= 0);
-    OAParams p{qkv, pos_p, kl, pos_l, vl, (__half*)out, (size_t)B * T * C, parts, C, heads, T, L2, C / heads,
+    B200_CHECK_ARG(out_w > 0 && out_w % OTW == 0 && T % out_w == 0 && L2 >= 0);
+    OAParams p{qkv, pos_p, kl, pos_l, vl, (__half*)out, (size_t)B * T / out_w * (out_w / OTW) * (C / 8) * OPX * 8, parts, C, heads, T, L2, C / heads,
                out_w, scale2};
     const size_t smem = ((size_t)ATT_QT * 2 * p.d + (size_t)ATT_QT * (T + L2 + 1) + ATT_QT) * sizeof(float);
     B200_CHECK_ARG(smem <= 200 * 1024);
@@ -310,7 +310,7 @@ struct FAParams {
     __half* out;
     size_t lo_off;   // fp16 elements per operand plane
     int parts;
-    int C, Wimg;                             // output channels (heads * dv) and image width for the slab-major store
+    int C, Wimg;                             // output channels (heads * dv) and image width for the operand store
     float scale;                             // applied to q (full softmax scale)
 };
 
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const FAParams p
                 for (int j = 0; j < DPT; ++j) o[i][j] = fmaf(pa[i], va[j], o[i][j]);
         }
     }
-    // ---- normalise and store (fp16 hi [+ lo], slab-major conv operand) ----
+    // ---- normalise and store (conv operand layout, common.cuh) ----
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int tq = q0 + ty * 4 + i;
@@ -486,10 +486,10 @@ extern "C" int b200_flash_attention(const float* qkv, int E, void* out, int out_
                                     float scale, void* stream) {
     // self-attention on the fused in-projection output qkv fp32 [B,T,3E] (q | k | v, head-major)
     B200_CHECK_ARG(qkv && out && (parts >= 1 && parts <= 3) && heads > 0 && E % heads == 0);
-    B200_CHECK_ARG(out_w > 0 && T % out_w == 0);
+    B200_CHECK_ARG(out_w > 0 && out_w % OTW == 0 && T % out_w == 0);
     const int d = E / heads;
     FAParams p{qkv, nullptr, qkv + E, nullptr, qkv + 2 * E, nullptr, nullptr, nullptr, 3 * E, 0, 3 * E, 0, 3 * E, 0,
-               d, 0, d, T, 0, (__half*)out, (size_t)B * T * E, parts, E, out_w, scale};
+               d, 0, d, T, 0, (__half*)out, (size_t)B * T / out_w * (out_w / OTW) * (E / 8) * OPX * 8, parts, E, out_w, scale};
     if (d == 64) return launch_fa<64, 64>(p, B, heads, (cudaStream_t)stream);
     if (d == 32) return launch_fa<32, 32>(p, B, heads, (cudaStream_t)stream);
     set_error("flash_attention: head dim %d not supported (32 or 64)", d);
@@ -500,8 +500,8 @@ extern "C" int b200_flash_attention_oa(const float* qkv, const float* pos_p, con
                                        const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                                        int L2, float scale2, void* stream) {
     B200_CHECK_ARG(qkv && pos_p && kl && pos_l && vl && out && (parts >= 1 && parts <= 3));
-    B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32 && out_w > 0 && T % out_w == 0 && L2 >= 0);
+    B200_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads == 32 && out_w > 0 && out_w % OTW == 0 && T % out_w == 0 && L2 >= 0);
     FAParams p{qkv, pos_p, qkv + C, pos_p, qkv + 2 * C, kl, pos_l, vl, 3 * C, C, 3 * C, C, 3 * C, C,
-               32, 32, 32, T, L2, (__half*)out, (size_t)B * T * C, parts, C, out_w, scale2};
+               32, 32, 32, T, L2, (__half*)out, (size_t)B * T / out_w * (out_w / OTW) * (C / 8) * OPX * 8, parts, C, out_w, scale2};
     return launch_fa<64, 32>(p, B, heads, (cudaStream_t)stream);
 }

@@ -154,6 +154,46 @@ __device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (the warp keeps executing uniformly; tcgen05.mma / commit operands stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Descriptors split in 32-bit halves: the HIGH word (SBO = 128 B, version 1) is the same constant for every operand of
+// the conv kernel, the LOW word = (address >> 4) | (LBO >> 4) << 16, so stepping to another tap / row / K group is ONE
+// 32-bit add of a compile-time constant on a per-stage base (a single issuing thread is latency-bound: every
+// instruction between two MMAs counts).
+constexpr uint32_t DESC_HI_SBO128 = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SBO128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SBO128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 //   element (row r, k) lives at start + (r/8)*sbo + (r%8)*16 + (k/8)*lbo + (k%8)*2   [fp16]
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -204,19 +244,59 @@ __device__ __forceinline__ float f8_to_float(uint8_t v) {
     const __half_raw h = __nv_cvt_fp8_to_halfraw(v, __NV_E4M3);
     return __half2float(__half(h));
 }
-// scalar store of channel `ch` of pixel (bh = b*H + h, ww) into a slab-major conv operand (parts = 1, 2 or 3);
-// plane_elems = B*H*W*C (fp16 elements per plane)
+// ---- conv operand layout ("tile-major slabs") ----
+//   [plane][b][h][W/128][C/8][130][8] fp16-sized elements: for one image row, one 128-pixel tile and one 8-channel
+//   group, 130 pixels at a 16-byte pitch = the tile's 128 pixels preceded / followed by ONE halo pixel (the ring
+//   neighbours (w0-1) mod W and (w0+128) mod W).  This is exactly the tcgen05 no-swizzle K-major shared-memory image
+//   of the tile INCLUDING the 3x3 halo, and the KG slabs of a K chunk are contiguous, so the conv stages one
+//   (row, plane, chunk) with ONE cp.async.bulk (the TMA engine is request-rate bound: 3 copies per slab -- body plus
+//   two 16-byte halo pixels -- cost 18% of the kernel on B200).  Producers write the two duplicated halo pixels.
+constexpr int OPX = 130;    // pixels per slab
+constexpr int OTW = 128;    // tile width
+// 16-byte unit index of pixel position `pos` (0..129) of slab (bh, wt, cg)
+__host__ __device__ __forceinline__ size_t operand_unit(size_t bh, int WT, int CG, int wt, int cg, int pos) {
+    return ((bh * WT + wt) * CG + cg) * OPX + pos;
+}
+// home position of pixel ww and (if it is a tile-border pixel) its halo duplicate in the neighbouring tile
+struct OperandPos {
+    int wt, pos, wt2, pos2;   // wt2 < 0: no duplicate
+};
+__device__ __forceinline__ OperandPos operand_pos(int ww, int WT) {
+    OperandPos r;
+    r.wt = ww >> 7;
+    const int x = ww & (OTW - 1);
+    r.pos = x + 1;
+    r.wt2 = -1;
+    r.pos2 = 0;
+    if (x == 0) { r.wt2 = r.wt == 0 ? WT - 1 : r.wt - 1; r.pos2 = OPX - 1; }
+    else if (x == OTW - 1) { r.wt2 = r.wt == WT - 1 ? 0 : r.wt + 1; r.pos2 = 0; }
+    return r;
+}
+// scalar store of channel `ch` of pixel (bh = b*H + h, ww) into a conv operand (parts = 1, 2 or 3);
+// plane_elems = fp16-sized elements per plane = B*H*(W/128)*(C/8)*130*8
 __device__ __forceinline__ void store_operand_elem(__half* out, size_t plane_elems, int parts, size_t bh, int C, int W,
                                                    int ww, int ch, float val) {
+    const int WT = W / OTW;
+    const OperandPos op = operand_pos(ww, WT);
     const __half hi = __float2half_rn(val);
-    out[((bh * (C / 8) + ch / 8) * W + ww) * 8 + (ch & 7)] = hi;
-    if (parts == 2) {
-        out[plane_elems + ((bh * (C / 8) + ch / 8) * W + ww) * 8 + (ch & 7)] = __float2half_rn(val - __half2float(hi));
-    } else if (parts == 3) {
-        uint8_t* p1 = reinterpret_cast<uint8_t*>(out + plane_elems);
-        const size_t unit = ((bh * (C / 16) + ch / 16) * 2) * (size_t)W + ww;   // 16-byte units; + W for the A8 slab
-        p1[unit * 16 + (ch & 15)] = f8x1((val - __half2float(hi)) * F8_LO_SCALE);
-        p1[(unit + W) * 16 + (ch & 15)] = f8x1(val);
+    const __half lo = __float2half_rn(val - __half2float(hi));
+    const uint8_t l8 = parts == 3 ? f8x1((val - __half2float(hi)) * F8_LO_SCALE) : 0;
+    const uint8_t a8 = parts == 3 ? f8x1(val) : 0;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        const int wt = rep == 0 ? op.wt : op.wt2, pos = rep == 0 ? op.pos : op.pos2;
+        if (wt < 0) break;
+        const size_t u = operand_unit(bh, WT, C / 8, wt, ch / 8, pos);
+        out[u * 8 + (ch & 7)] = hi;
+        if (parts == 2) {
+            out[plane_elems + u * 8 + (ch & 7)] = lo;
+        } else if (parts == 3) {
+            // plane 1: slab (2*chunk) holds L8, slab (2*chunk + 1) holds A8 of the 16-channel chunk
+            uint8_t* p1 = reinterpret_cast<uint8_t*>(out + plane_elems);
+            const size_t u8 = operand_unit(bh, WT, C / 8, wt, (ch / 16) * 2, pos);
+            p1[u8 * 16 + (ch & 15)] = l8;
+            p1[(u8 + OPX) * 16 + (ch & 15)] = a8;
+        }
     }
 }
 

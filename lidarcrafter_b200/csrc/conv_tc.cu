@@ -18,17 +18,21 @@
 //                [e4m3(a_lo 2^11) | e4m3(a)] x [e4m3(w 2^-11) | e4m3(w_lo)]) at twice the fp16 rate: 2 MMA time
 //                units per product instead of 3, ~5e-5 relative through the whole UNet.  (NP = 4: same operands,
 //                corrections in their own accumulator columns, added in the epilogue.)
-//   * A (activations) live in HBM "slab-major": [part][b][h][C/8][w][8] fp16, i.e. for one image row and one
-//     8-channel group all pixels are contiguous at a 16-byte pitch -- which IS the canonical no-swizzle K-major
-//     shared-memory layout of a tcgen05 operand.  For every K chunk the R+2 halo rows are staged ONCE by the TMA
-//     engine (cp.async.bulk, 2 KB per slab + two 16-byte wrap-around halo pixels, zero rows from a zero page) and
-//     each of the 9 filter taps is just a different START ADDRESS of the same slab (dx*16 bytes, dy = other row):
-//     no im2col copies, no 9x re-reads, no swizzle.
+//   * A (activations) live in HBM "tile-major": [plane][b][h][W/128][C/8][130][8] fp16 (common.cuh): for one image
+//     row, one 128-pixel tile and one 8-channel group, 130 pixels (tile + its two ring-halo pixels) at a 16-byte
+//     pitch -- which IS the canonical no-swizzle K-major shared-memory layout of a tcgen05 operand, halo included.
+//     For every K chunk the R+2 halo rows are staged ONCE by the TMA engine, one cp.async.bulk per (row, plane)
+//     (zero rows from a zero page), and each of the 9 filter taps is just a different START ADDRESS of the same
+//     slab (dx*16 bytes, dy = other row): no im2col copies, no 9x re-reads, no swizzle.  (Measured on B200: the
+//     MMA rate does not depend on the 16-byte alignment of the start address -- profiles/r01_mma_probe.txt -- but
+//     the TMA engine is request-rate bound, hence few large copies.)
 //   * B (weights): host-prepacked tiles in exactly the shared-memory image, one cp.async.bulk per (chunk, filter row).
 //   * warp roles: 0-3 epilogue (TMEM -> regs -> smem transpose -> coalesced fp32 store + residual + per-channel
 //     sum / sum-of-squares for the next GroupNorm), 4 activation producer and 6 weight producer (TMA bulk copies,
 //     mbarrier tx bytes; independent warps so a full weight ring never stalls the activation prefetch),
 //     5 MMA issuer (single thread, tcgen05.mma kind::f16, M=128 N=BN K=16) + TMEM owner.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -46,7 +50,7 @@ struct ConvParams {
     int n_tiles;
 };
 
-__device__ __align__(128) unsigned char g_zero_page[4096];  // source of zero-padding rows / pixels
+__device__ __align__(128) unsigned char g_zero_page[16384];  // source of zero-padding rows / pixels
 
 // Optional in-kernel profile (b200_conv_set_debug): per CTA 8 x u64 cycle counters
 //   [0] MMA thread total, [1] wait FULL_A, [2] wait FULL_B, [3] wait ACC_EMPTY,
@@ -67,8 +71,9 @@ struct ConvCfg {
     static constexpr int KC = NP == 1 ? 32 : 16;  // channels per K chunk
     static constexpr int KG = KC / 8;             // 8-channel groups (slabs) per row
     static constexpr int KS = KC / 16;            // MMA K steps per chunk
-    static constexpr int HALO = TAPS == 9 ? 1 : 0;
-    static constexpr int NPX = PIX + 2 * HALO;
+    static constexpr int HALO = TAPS == 9 ? 1 : 0;   // halo ROWS above / below the tile
+    static constexpr int DX0 = TAPS == 9 ? 0 : 1;    // first pixel position read by tap dx = 0 (1x1: the body starts at 1)
+    static constexpr int NPX = OPX;                  // 128 pixels + the two halo pixels of the operand layout
     static constexpr int SLAB = NPX * 16;  // bytes: one 8-channel group of one staged row
     static constexpr int RA = R + 2 * HALO;
     static constexpr int NSLAB = PL * RA * KG;
@@ -101,7 +106,8 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static_assert(SLAB <= 4096, "zero page too small");
+    static constexpr int ROWB = KG * SLAB;   // bytes of one staged (row, plane): ONE bulk copy
+    static_assert(ROWB <= 16384, "zero page too small");
 };
 
 template <int BN, int R, int TAPS, int NP>
@@ -156,13 +162,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         uint32_t ia = 0;
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const size_t part_elems = (size_t)p.B * p.H * p.W * p.Cin;
+        const size_t part_elems = (size_t)p.B * p.H * WT * CG * OPX * 8;
         for (int tile = tile_lo; tile < tile_hi; ++tile) {
             int t = tile;
             const int wt = t % WT; t /= WT;
             const int hg = t % HG; t /= HG;
             const int b = t / NT;
-            const int w0 = wt * PIX, h0 = hg * R;
+            const int h0 = hg * R;
             for (int c = 0; c < NCH; ++c) {
                 {
                     const int s = ia % C::SA;
@@ -175,28 +181,31 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     }
                     __syncwarp();
                     const uint32_t dst0 = sbase + C::OFF_A + s * C::A_STAGE;
-                    for (int sl = lane; sl < C::NSLAB; sl += 32) {
-                        const int j = sl % C::KG;
-                        const int r2 = sl / C::KG;  // part * RA + row
+                    // one bulk copy per (plane, staged row): the KG slabs of this K chunk are contiguous in the
+                    // tile-major operand and already carry the two halo pixels
+                    for (int r2 = lane; r2 < C::PL * C::RA; r2 += 32) {
                         const int part = r2 / C::RA;
                         const int r = r2 - part * C::RA;
                         const int gh = h0 + r - C::HALO;
-                        const uint32_t dst = dst0 + sl * C::SLAB;
+                        const uint32_t dst = dst0 + r2 * C::ROWB;
                         if (gh < 0 || gh >= p.H) {
-                            bulk_copy_g2s(dst, g_zero_page, C::SLAB, FULL_A(s));
+                            bulk_copy_g2s(dst, g_zero_page, C::ROWB, FULL_A(s));
+                            continue;
+                        }
+                        const __half* src = p.a + part * part_elems +
+                                            operand_unit((size_t)b * p.H + gh, WT, CG, wt, c * C::KG, 0) * 8;
+                        const bool edge_l = !p.ring && wt == 0, edge_r = !p.ring && wt == WT - 1;
+                        if (!(edge_l || edge_r)) {
+                            bulk_copy_g2s(dst, src, C::ROWB, FULL_A(s));
                         } else {
-                            const __half* row = p.a + part * part_elems +
-                                                (((size_t)(b * p.H + gh) * CG + (size_t)c * C::KG + j) * p.W) * 8;
-                            bulk_copy_g2s(dst + C::HALO * 16, row + (size_t)w0 * 8, PIX * 16, FULL_A(s));
-                            if (C::HALO) {
-                                int wl = w0 - 1, wr = w0 + PIX;
-                                if (wl < 0) wl = p.ring ? p.W - 1 : -1;
-                                if (wr >= p.W) wr = p.ring ? 0 : -1;
-                                bulk_copy_g2s(dst, wl >= 0 ? (const void*)(row + (size_t)wl * 8) : (const void*)g_zero_page,
-                                              16, FULL_A(s));
-                                bulk_copy_g2s(dst + (PIX + 1) * 16,
-                                              wr >= 0 ? (const void*)(row + (size_t)wr * 8) : (const void*)g_zero_page, 16,
-                                              FULL_A(s));
+                            // zero padding in W (not on the hot path): per slab, zero halo pixel(s) + the rest
+                            for (int j = 0; j < C::KG; ++j) {
+                                const uint32_t d = dst + j * C::SLAB;
+                                const __half* sj = src + (size_t)j * OPX * 8;
+                                const int lo_px = edge_l ? 1 : 0, hi_px = edge_r ? OPX - 1 : OPX;
+                                if (edge_l) bulk_copy_g2s(d, g_zero_page, 16, FULL_A(s));
+                                bulk_copy_g2s(d + lo_px * 16, sj + lo_px * 8, (hi_px - lo_px) * 16, FULL_A(s));
+                                if (edge_r) bulk_copy_g2s(d + (OPX - 1) * 16, g_zero_page, 16, FULL_A(s));
                             }
                         }
                     }
@@ -231,13 +240,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[7];
         }
     } else if (warp == 5) {
-        // ------------------------------ MMA issuer: one thread ------------------------------
-        if (lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        // The whole warp runs the loop (uniform control flow, waits included); one elected lane issues the MMAs and
+        // commits.  Keeping the branch warp-uniform lets the descriptor arithmetic live in uniform registers: between
+        // two tcgen05.mma there is one 32-bit add per operand (see desc_lo / tc_mma_f16_lh).
+        {
             constexpr uint32_t idesc = make_idesc_f16(128, BN);
             constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * BN);
             constexpr uint32_t KGS = C::MERGE ? 2 * BN * 16 : BN * 16;   // byte stride between 8-channel groups of B
             uint32_t ia = 0, ib = 0, it = 0;
-            unsigned long long* dbg = g_conv_dbg;
+            unsigned long long* dbg = lane == 0 ? g_conv_dbg : nullptr;
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const long long t_start = dbg ? clock64() : 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
                         DBG_ACC(1);
                     }
-                    const uint32_t a_stage = sbase + C::OFF_A + sa * C::A_STAGE;
+                    const uint32_t a_lo0 = desc_lo(sbase + C::OFF_A + sa * C::A_STAGE, C::SLAB);
                     for (int dy = 0; dy < C::TG; ++dy, ++ib) {
                         const int sb = ib % C::SB;
                         {
@@ -265,47 +277,48 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                             DBG_ACC(2);
                         }
                         tc_fence_after();
-                        const uint32_t b_stage = sbase + C::OFF_B + sb * C::B_STAGE;
+                        const uint32_t b_lo0 = desc_lo(sbase + C::OFF_B + sb * C::B_STAGE, KGS);
+                        const uint32_t first_cd = (uint32_t)((c | dy) != 0);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int dx = 0; dx < C::TW; ++dx) {
+                            for (int dx = 0; dx < C::TW; ++dx) {
 #pragma unroll
-                            for (int o = 0; o < R; ++o) {
-                                const int ri = o + dy;  // staged input row feeding output row o through filter row dy
+                                for (int o = 0; o < R; ++o) {
 #pragma unroll
-                                for (int ks = 0; ks < C::KS; ++ks) {
-                                    const uint32_t a_addr = a_stage + (ri * C::KG + ks * 2) * C::SLAB + dx * 16;
-                                    const uint32_t b_addr = b_stage + dx * C::B_TAP + ks * 2 * KGS;
-                                    const uint64_t a_hi = make_smem_desc(a_addr, C::SLAB, 128);
-                                    const uint64_t b_hi = make_smem_desc(b_addr, KGS, 128);
-                                    const uint32_t first = (uint32_t)((c | dy | dx | ks) != 0);
-                                    if (C::F8) {
-                                        // plane 1 of both operands: [L8 | A8] x [e4m3(w 2^-11) | e4m3(w_lo)], K = 32
-                                        const uint64_t a_f8 = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
-                                        const uint64_t b_f8 = make_smem_desc(b_addr + C::B_PART, KGS, 128);
-                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc, first);
-                                        tc_mma_f8(acc + o * C::ACC_ROW + (C::SEP ? BN : 0), a_f8, b_f8, idesc,
-                                                  C::SEP ? first : 1u);
-                                    } else if (C::MERGE) {
-                                        const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
-                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc2, first);   // [hi*hi | hi*lo]
-                                        tc_mma_f16(acc + o * C::ACC_ROW, a_lo, b_hi, idesc, 1u);       // += lo*hi
-                                    } else {
-                                        tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_hi, idesc, first);
-                                        if (NP == 2) {
-                                            const uint64_t a_lo = make_smem_desc(a_addr + C::A_PART, C::SLAB, 128);
-                                            const uint64_t b_lo = make_smem_desc(b_addr + C::B_PART, KGS, 128);
-                                            tc_mma_f16(acc + o * C::ACC_ROW, a_lo, b_hi, idesc, 1u);
-                                            tc_mma_f16(acc + o * C::ACC_ROW, a_hi, b_lo, idesc, 1u);
+                                    for (int ks = 0; ks < C::KS; ++ks) {
+                                        // staged input row o + dy feeds output row o through filter row dy
+                                        const uint32_t a_hi = a_lo0 + ((uint32_t)(dy * C::KG * C::SLAB) >> 4) +
+                                                              (((o * C::KG + ks * 2) * C::SLAB + (dx + C::DX0) * 16) >> 4);
+                                        const uint32_t b_hi = b_lo0 + ((dx * C::B_TAP + ks * 2 * KGS) >> 4);
+                                        const uint32_t first = (dx | ks) != 0 ? 1u : first_cd;
+                                        const uint32_t d = acc + o * C::ACC_ROW;
+                                        if (C::F8) {
+                                            // plane 1 of both operands: [L8 | A8] x [e4m3(w 2^-11) | e4m3(w_lo)], K = 32
+                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
+                                            tc_mma_f8_lh(d + (C::SEP ? BN : 0), a_hi + (C::A_PART >> 4), b_hi + (C::B_PART >> 4),
+                                                         idesc, C::SEP ? first : 1u);
+                                        } else if (C::MERGE) {
+                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc2, first);                       // [hi*hi | hi*lo]
+                                            tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);        // += lo*hi
+                                        } else {
+                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
+                                            if (NP == 2) {
+                                                tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);
+                                                tc_mma_f16_lh(d, a_hi, b_hi + (C::B_PART >> 4), idesc, 1u);
+                                            }
                                         }
                                     }
                                 }
                             }
+                            tc_commit(EMPTY_B(sb));  // weights slot free once these MMAs retire
+                            if (dy == C::TG - 1) {
+                                tc_commit(EMPTY_A(sa));
+                                if (c == NCH - 1) tc_commit(ACC_FULL(buf));
+                            }
                         }
-                        tc_commit(EMPTY_B(sb));  // weights slot free once these MMAs retire
+                        __syncwarp();
                     }
-                    tc_commit(EMPTY_A(sa));
                 }
-                tc_commit(ACC_FULL(buf));
             }
             if (dbg) {
                 dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
@@ -583,7 +596,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
     const int h = valid ? (int)((pix / p.W) % p.H) : 0;
     const int b = valid ? (int)(pix / ((long long)p.W * p.H)) : 0;
     const int kside = taps == 9 ? 3 : 1, pad = taps == 9 ? 1 : 0;
-    const size_t a_part = (size_t)npix * p.Cin, w_part = (size_t)taps * p.Cout * p.Cin;
+    const size_t a_part = (size_t)p.B * p.H * (p.W / OTW) * (p.Cin / 8) * OPX * 8, w_part = (size_t)taps * p.Cout * p.Cin;
     float acc[4] = {0, 0, 0, 0};
     for (int tap = 0; tap < taps; ++tap) {
         const int dy = tap / kside - pad, dx = tap % kside - pad;
@@ -592,13 +605,15 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
         bool ok = valid && gh >= 0 && gh < p.H;
         if (gw < 0) { if (p.ring) gw += p.W; else ok = false; }
         else if (gw >= p.W) { if (p.ring) gw -= p.W; else ok = false; }
-        // slab-major operand: [part][b][h][C/8][w][8]
-        const __half* ap = p.a + (((size_t)(b * p.H + gh) * (p.Cin / 8)) * p.W + gw) * 8;
+        // tile-major operand (common.cuh): [plane][b][h][W/128][C/8][130][8]; the body pixel gw sits at position gw%128 + 1
+        const int WT = p.W / OTW, CG = p.Cin / 8;
+        const size_t bh = (size_t)b * p.H + gh;
+        const int twt = gw / OTW, tpos = gw % OTW + 1;
         const __half* wp = p.w + ((size_t)tap * p.Cout + co0) * p.Cin;
         for (int k = 0; k < p.Cin; k += 8) {
             float av[8], l8v[8], a8v[8];
             if (ok) {
-                const __half* apk = ap + (size_t)(k / 8) * p.W * 8;
+                const __half* apk = p.a + operand_unit(bh, WT, CG, twt, k / 8, tpos) * 8;
                 load8h(apk, av);
                 if (parts == 2) {
                     float lo[8];
@@ -608,9 +623,9 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvParams p, int 
                 } else if (parts == 3) {
                     // plane 1: per 16-channel chunk {L8 slab, A8 slab}, 16 bytes per pixel each
                     const uint8_t* p1 = reinterpret_cast<const uint8_t*>(p.a + a_part);
-                    const size_t unit = (((size_t)(b * p.H + gh) * (p.Cin / 16) + k / 16) * 2) * p.W + gw;
+                    const size_t unit = operand_unit(bh, WT, CG, twt, (k / 16) * 2, tpos);
                     const uint2 l8 = *reinterpret_cast<const uint2*>(p1 + unit * 16 + (k & 8));
-                    const uint2 a8 = *reinterpret_cast<const uint2*>(p1 + (unit + p.W) * 16 + (k & 8));
+                    const uint2 a8 = *reinterpret_cast<const uint2*>(p1 + (unit + OPX) * 16 + (k & 8));
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         l8v[e] = f8_to_float((uint8_t)(((e < 4 ? l8.x : l8.y) >> (8 * (e & 3))) & 0xff));
@@ -773,7 +788,7 @@ extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias,
     B200_CHECK_ARG(a && w16 && out);
     B200_CHECK_ARG(taps == 9 || taps == 1);
     B200_CHECK_ARG(parts >= 1 && parts <= 3);
-    B200_CHECK_ARG(Cin % (parts == 3 ? 16 : 8) == 0 && Cout % 32 == 0);
+    B200_CHECK_ARG(Cin % (parts == 3 ? 16 : 8) == 0 && Cout % 32 == 0 && W % OTW == 0);
     B200_CHECK_ARG(!stats || (H * W) % 32 == 0);
     ConvParams p{(const __half*)a, (const __half*)w16, bias, res, out, stats, out_scale, w_inv,
                  B, H, W, Cin, Cout, ring, 0};

@@ -346,7 +346,7 @@ class EfficientUNetPlan:
         an = pb.gn_act([x], ab.norm.weight, ab.norm.bias, m.gn_num_groups, m.gn_eps, False)
         w_qkv = ab.attn.in_proj_weight.detach().reshape(3 * E, E, 1, 1)
         qkv, _ = pb.conv(an, x.H, x.W, w_qkv, ab.attn.in_proj_bias, None, 1.0, False)
-        att = self.plan.f16(self.B, T, E)
+        att = self.plan.operand(x.H, x.W, E)
         d = E // nh
         self.plan.add(self.lib.flash_attention, _ptr(qkv), E, _ptr(att), x.W, self.plan.parts, self.B, nh, T,
                       1.0 / math.sqrt(d), name="attention", flops=4.0 * self.B * nh * T * T * d)

@@ -140,9 +140,13 @@ class Plan:
         self.bufs.append(t)
         return t
 
-    def f16(self, *shape):
-        """conv operand [planes][*shape] (fp16-sized elements; plane 1 of parts 3 holds e4m3 pairs)"""
-        t = torch.empty(planes(self.parts), *shape, dtype=torch.float16, device=self.device)
+    def operand(self, H: int, W: int, C: int):
+        """conv operand buffer, layout [planes][B][H][W/128][C/8][130][8] (fp16-sized elements; 128-pixel tiles with
+        their two ring-halo pixels -- csrc/common.cuh; plane 1 of parts 3 holds e4m3 pairs)"""
+        if W % 128 or C % 8:
+            raise ValueError(f"conv operands need W % 128 == 0 and C % 8 == 0 (got W={W}, C={C})")
+        t = torch.empty(planes(self.parts), self.B * H * (W // 128) * (C // 8) * 130 * 8, dtype=torch.float16,
+                        device=self.device)
         self.bufs.append(t)
         return t
 
@@ -285,8 +289,8 @@ class PlanBuilder:
         a1 = srcs[1] if len(srcs) > 1 else None
         C = a0.C + (a1.C if a1 else 0)
         HW = a0.H * a0.W
-        y = self.p.f16(self.B, HW, C)
-        y_raw = self.p.f16(self.B, HW, C) if also_raw else None
+        y = self.p.operand(a0.H, a0.W, C)
+        y_raw = self.p.operand(a0.H, a0.W, C) if also_raw else None
         g = None if gamma is None else gamma.detach().float().contiguous()
         b = None if beta is None else beta.detach().float().contiguous()
         self.p.bufs += [g, b]

@@ -303,7 +303,7 @@ class LayoutUnetPlan:
         bufs = dict(pos_p=plan.f32(B, T, C), kl=plan.f32(B, L2, C), pos_l=plan.f32(B, L2, C), vl=plan.f32(B, L2, C))
         res_key = f"image_patch_bbox_embedding_for_resolution{self.m.image_size // (self.H // x.H)}"
         self.attn_consts.append((ab, res_key, bufs))
-        att = plan.f16(B, T, C)
+        att = plan.operand(x.H, x.W, C)
         d = C // nh
         plan.add(self.lib.flash_attention_oa, _ptr(qkv), _ptr(bufs["pos_p"]), _ptr(bufs["kl"]), _ptr(bufs["pos_l"]),
                  _ptr(bufs["vl"]), _ptr(att), x.W, plan.parts, B, C, nh, T, L2, 1.0 / math.sqrt(2 * d), name="attention_oa",

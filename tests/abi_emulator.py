@@ -66,42 +66,60 @@ def n_planes(parts):
     return 1 if parts == 1 else 2
 
 
+OPX, OTW = 130, 128     # pixels per operand slab (128 + 2 ring-halo pixels), tile width
+
+
+def to_tiles(x, g=8):
+    """[..., H, W, C] -> conv operand layout [..., H, W/128, C/g, 130, g]: per 128-pixel tile and g-channel group 130
+    pixels = ring neighbour (w0-1) mod W, the 128 tile pixels, ring neighbour (w0+128) mod W  (csrc/common.cuh)"""
+    *lead, H, W, C = x.shape
+    WT = W // OTW
+
+    def tiles(t):
+        return t.reshape(*lead, H, WT, OTW, C // g, g)
+    left = tiles(torch.roll(x, 1, dims=-2))[..., 0:1, :, :]
+    right = tiles(torch.roll(x, -1, dims=-2))[..., OTW - 1:OTW, :, :]
+    return torch.cat([left, tiles(x), right], dim=-3).transpose(-3, -2).contiguous()
+
+
+def from_tiles(t):
+    """inverse of to_tiles (reads the tile bodies): [..., H, WT, C/g, 130, g] -> [..., H, W, C]"""
+    *lead, H, WT, G, P, g = t.shape
+    return t[..., 1:OTW + 1, :].transpose(-3, -2).reshape(*lead, H, WT * OTW, G * g)
+
+
+def operand_elems(B, H, W, C):
+    """fp16-sized elements of ONE operand plane"""
+    return B * H * (W // OTW) * (C // 8) * OPX * 8
+
+
 def store_operand(ptr, x, parts, B, H, W, C):
     """x [B, H, W, C] fp32 -> conv operand at ``ptr`` (include/b200lidar.h, "conv operand layout")"""
     x = x.reshape(B, H, W, C).float()
+    WT = W // OTW
     hi = x.half()
-    f16(ptr, B, H, C // 8, W, 8).copy_(to_slab(hi))
+    f16(ptr, B, H, WT, C // 8, OPX, 8).copy_(to_tiles(hi))
+    plane = 2 * operand_elems(B, H, W, C)
     if parts == 2:
-        f16(ptr + 2 * B * H * W * C, B, H, C // 8, W, 8).copy_(to_slab((x - hi.float()).half()))
+        f16(ptr + plane, B, H, WT, C // 8, OPX, 8).copy_(to_tiles((x - hi.float()).half()))
     elif parts == 3:
-        l8 = e4m3((x - hi.float()) * F8_LO_SCALE).view(B, H, W, C // 16, 16)
-        a8 = e4m3(x).view(B, H, W, C // 16, 16)
-        pair = torch.stack([l8, a8], dim=0).permute(1, 2, 4, 0, 3, 5).contiguous()   # [B, H, C/16, 2, W, 16]
-        u8(ptr + 2 * B * H * W * C, B, H, C // 16, 2, W, 16).copy_(pair)
+        l8 = to_tiles(e4m3((x - hi.float()) * F8_LO_SCALE), 16)       # [B, H, WT, C/16, 130, 16]
+        a8 = to_tiles(e4m3(x), 16)
+        u8(ptr + plane, B, H, WT, C // 16, 2, OPX, 16).copy_(torch.stack([l8, a8], dim=4))
 
 
 def load_operand(ptr, parts, B, H, W, C):
-    """-> list of fp32 [B, H, W, C] tensors: [hi] / [hi, lo] / [hi, L8, A8]"""
-    out = [from_slab(f16(ptr, B, H, C // 8, W, 8)).float()]
+    """-> list of fp32 [B, H, W, C] tensors: [hi] / [hi, lo] / [hi, L8, A8]  (tile bodies)"""
+    WT = W // OTW
+    plane = 2 * operand_elems(B, H, W, C)
+    out = [from_tiles(f16(ptr, B, H, WT, C // 8, OPX, 8)).float()]
     if parts == 2:
-        out.append(from_slab(f16(ptr + 2 * B * H * W * C, B, H, C // 8, W, 8)).float())
+        out.append(from_tiles(f16(ptr + plane, B, H, WT, C // 8, OPX, 8)).float())
     elif parts == 3:
-        pair = e4m3_value(u8(ptr + 2 * B * H * W * C, B, H, C // 16, 2, W, 16))
+        pair = e4m3_value(u8(ptr + plane, B, H, WT, C // 16, 2, OPX, 16))
         for sub in range(2):
-            out.append(pair[:, :, :, sub].permute(0, 1, 3, 2, 4).reshape(B, H, W, C))
+            out.append(from_tiles(pair[:, :, :, :, sub]))
     return out
-
-
-def to_slab(x):
-    """[..., H, W, C] -> slab-major [..., H, C/8, W, 8] (the conv operand layout)"""
-    *lead, H, W, C = x.shape
-    return x.reshape(*lead, H, W, C // 8, 8).transpose(-3, -2).contiguous()
-
-
-def from_slab(x):
-    """slab-major [..., H, C/8, W, 8] -> [..., H, W, C]"""
-    *lead, H, G, W, E = x.shape
-    return x.transpose(-3, -2).reshape(*lead, H, W, G * E)
 
 
 def _ring_pad(x, pad, ring):

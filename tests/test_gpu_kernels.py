@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from abi_emulator import EmulatedLib, from_slab, load_operand, n_planes, store_operand, to_slab
+from abi_emulator import OPX, OTW, EmulatedLib, load_operand, n_planes, operand_elems, store_operand
 
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
@@ -55,12 +55,12 @@ def randn(*shape, seed=0, scale=1.0):
 
 
 def operand_zeros(parts, B, H, W, C):
-    """empty conv operand: [planes][B][H][C/8][W][8] fp16-sized elements (plane 1 of parts 3: e4m3 pairs)"""
-    return torch.zeros(n_planes(parts), B, H, C // 8, W, 8, dtype=torch.float16)
+    """empty conv operand: [planes][B][H][W/128][C/8][130][8] fp16-sized elements (plane 1 of parts 3: e4m3 pairs)"""
+    return torch.zeros(n_planes(parts), operand_elems(B, H, W, C), dtype=torch.float16)
 
 
 def split(v, parts):
-    """fp32 [B,H,W,C] -> conv operand (slab-major; include/b200lidar.h "conv operand layout")"""
+    """fp32 [B,H,W,C] -> conv operand (include/b200lidar.h "conv operand layout")"""
     B, H, W, C = v.shape
     t = operand_zeros(parts, B, H, W, C)
     store_operand(t.data_ptr(), v, parts, B, H, W, C)
@@ -70,6 +70,10 @@ def split(v, parts):
 def operand_close(g, c, parts, B, H, W, C):
     """compare two conv operands by VALUE: hi (+ lo) reconstruct the fp32 input; for parts 3 additionally the A8 plane"""
     pg, pc = load_operand(g.data_ptr(), parts, B, H, W, C), load_operand(c.data_ptr(), parts, B, H, W, C)
+    # halo pixels of every slab duplicate the ring neighbours' body pixels, bit for bit (all planes)
+    raw = g.view(torch.int16).view(n_planes(parts), B, H, W // OTW, C // 8, OPX, 8)
+    assert torch.equal(raw[..., 0, :], torch.roll(raw, 1, dims=3)[..., OTW, :])
+    assert torch.equal(raw[..., OPX - 1, :], torch.roll(raw, -1, dims=3)[..., 1, :])
     if parts == 1:
         assert rel(pg[0], pc[0]) < 6e-4
     elif parts == 2:
@@ -162,7 +166,7 @@ def test_conv_tc_split_reaches_fp32_accuracy():
 @pytest.mark.parametrize("parts", [2, 1, 3])
 def test_conv_ffma_matches_contract(parts):
     h = Both()
-    B, H, W, Cin, Cout, taps = 2, 4, 64, 48, 64, 9
+    B, H, W, Cin, Cout, taps = 2, 4, 128, 48, 64, 9
     w = h.t(randn(Cout, Cin, 3, 3, seed=1, scale=0.05))
     a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
     bias = h.t(randn(Cout, seed=3, scale=0.1))
@@ -191,7 +195,7 @@ def test_conv_ffma_matches_contract(parts):
 ])
 def test_gn_act(parts, C0, C1, groups, affine, ada, silu, norm):
     h = Both()
-    B, H, W = 3, 5, 40
+    B, H, W = 3, 5, 256
     HW = H * W
     C = C0 + C1
     x0 = randn(B, HW, C0, seed=1) * 2 + 0.3
@@ -252,16 +256,18 @@ def test_time_embed():
 
 
 def test_in_conv_out_conv_direct():
-    h = Both()
-    B, H, W, Cx, Cout = 2, 5, 64, 2, 64
-    x = h.t(randn(B, Cx, H, W, seed=1))
-    w = h.t(randn(Cout, Cx, 3, 3, seed=2, scale=0.2))
-    cst = h.t(randn(1, H, W, Cout, seed=3))
-    out = h.t(torch.zeros(B, H, W, Cout))
-    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
-    h.call("in_conv", [("t", x), ("t", w), ("t", cst), 0, ("t", out), ("t", st), B, H, W, Cx, Cout, 1])
-    assert rel(*h.out(out)) < 1e-6
-    assert rel(*h.out(st)) < 1e-6
+    B, H, Cx, Cout = 2, 5, 2, 64
+    for W, ring in ((64, 1), (256, 1), (128, 0)):        # generic kernel / row-tiled kernel (W % 128 == 0)
+        h = Both()
+        x = h.t(randn(B, Cx, H, W, seed=1))
+        w = h.t(randn(Cout, Cx, 3, 3, seed=2, scale=0.2))
+        cst = h.t(randn(1, H, W, Cout, seed=3))
+        out = h.t(torch.zeros(B, H, W, Cout))
+        st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+        h.call("in_conv", [("t", x), ("t", w), ("t", cst), 0, ("t", out), ("t", st), B, H, W, Cx, Cout, ring])
+        assert rel(*h.out(out)) < 1e-6
+        assert rel(*h.out(st)) < 1e-6
+    W = 64
 
     h = Both()
     Cin, Co = 30, 64
@@ -340,7 +346,7 @@ def test_attention_oa(parts, C, T, W):
 
 
 @pytest.mark.parametrize("parts", [2, 1, 3])
-@pytest.mark.parametrize("E,heads,T,W", [(512, 8, 512, 128), (256, 8, 512, 128), (256, 8, 128, 128), (512, 8, 200, 40)])
+@pytest.mark.parametrize("E,heads,T,W", [(512, 8, 512, 128), (256, 8, 512, 128), (256, 8, 128, 128), (512, 8, 384, 128)])
 def test_flash_attention(parts, E, heads, T, W):
     h = Both()
     B = 2
