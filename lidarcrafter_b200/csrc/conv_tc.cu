@@ -378,6 +378,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 cur_nt = nt;
             }
             const uint32_t buf = it & 1;
+            constexpr int NSL = BN / 32, NITEM = R * NSL;
+            // residual rows of an item: 8 x 16 bytes per lane, requested BEFORE the accumulator wait / the TMEM read of the
+            // item so that the (HBM) latency of the skip tensor overlaps the MMAs instead of extending the epilogue
+            auto res_ptr = [&](int item) {
+                const int o = item / NSL, sl = item - o * NSL;
+                return p.res + ((size_t)(b * p.H + h0 + o) * p.W + w0 + quarter * 32 + rb) * p.Cout + n0 + sl * 32 + col4 * 4;
+            };
+            float4 rv[8];
+            if (p.res && egroup < NITEM) {
+                const float* rp = res_ptr(egroup);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
+            }
             {
                 DBG_T0();
                 mbar_wait(ACC_FULL(buf), (it >> 1) & 1);
@@ -385,7 +398,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-            constexpr int NSL = BN / 32, NITEM = R * NSL;
             for (int item = egroup; item < NITEM; item += 2) {
                 const int o = item / NSL, sl = item - o * NSL;
                 const int h = h0 + o;
@@ -398,6 +410,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         tmem_ld_32x32(acc + o * C::ACC_ROW + BN + sl * 32, v2);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                    }
+                    float4 rn[8];      // next item's residual: in flight during this item's transpose / stores
+                    if (p.res && item + 2 < NITEM) {
+                        const float* rp = res_ptr(item + 2);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
                     }
                     if (item + 2 >= NITEM) {
                         // this warp's TMEM reads of the accumulator set are done -> hand it back to the MMA warp
@@ -419,10 +437,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         const size_t gi = row_base + (size_t)row * p.Cout + nb;
                         tv.x = fmaf(tv.x, winv, bi.x); tv.y = fmaf(tv.y, winv, bi.y);
                         tv.z = fmaf(tv.z, winv, bi.z); tv.w = fmaf(tv.w, winv, bi.w);
-                        if (p.res) {
-                            const float4 rv = *reinterpret_cast<const float4*>(p.res + gi);
-                            tv.x += rv.x; tv.y += rv.y; tv.z += rv.z; tv.w += rv.w;
-                        }
+                        if (p.res) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
                         tv.x *= scale; tv.y *= scale; tv.z *= scale; tv.w *= scale;
                         *reinterpret_cast<float4*>(p.out + gi) = tv;
                         s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
@@ -446,6 +461,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         }
                     }
                     __syncwarp();
+                    if (p.res && item + 2 < NITEM) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rv[i] = rn[i];
+                    }
                 }
             }
         }

@@ -107,7 +107,185 @@ __device__ __forceinline__ uint4 plane1_value(const float* v, const __half2* h, 
 }
 
 // output layout: the conv operand of common.cuh ("tile-major slabs"): y[plane][b][h][W/128][C/8][130][8]
-__global__ void __launch_bounds__(256) gn_act_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
+//
+// Work decomposition: block = (sample b, channel block of CB channels, a strided set of 128-pixel tiles); the grid is one
+// resident wave (~4 blocks / SM).  Warp item = 8 consecutive pixels x 32 consecutive channels (lane -> pixel lane/4,
+// 8-channel group lane%4): reads move whole 128-byte lines (32 channels of one pixel), writes move 128 contiguous
+// bytes of a slab (8 pixels of one channel group).  Four items (8 x 16-byte loads per lane) are requested before any
+// math; the first batch is requested before the coefficient prologue so that its latency overlaps it.
+struct GnItem {
+    const float* src;     // this lane's 8 input channels
+    size_t oi, oi2;       // fp16-element offsets of the 16-byte output unit and of its halo duplicate
+    int c;                // first channel (relative to the block's channel block: index into s_a / s_b)
+    bool ok, dup;
+};
+
+__global__ void __launch_bounds__(256, 4) gn_act_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
+                                                     int C1, const double* __restrict__ st0,
+                                                     const double* __restrict__ st1, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ ada,
+                                                     int ada_stride, int groups, float eps, int silu,
+                                                     __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
+                                                     int parts, int H, int W, int CB, int tile_blocks) {
+    extern __shared__ __align__(16) unsigned char gn_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int C = C0 + C1, c8n = C / 8;
+    const int HW = H * W, WT = W / OTW, tiles = H * WT;
+    const int b = blockIdx.y;
+    const int cbi = blockIdx.x / tile_blocks, tb = blockIdx.x - cbi * tile_blocks;
+    const int c0 = cbi * CB;
+    const int cb_n = min(CB, C - c0);                       // channels of this block
+    float* s_a = reinterpret_cast<float*>(gn_smem);         // [CB]
+    float* s_b = s_a + CB;                                  // [CB]
+    double* s_st = reinterpret_cast<double*>(gn_smem + 8 * CB);   // [2 * span] channel statistics of the covering groups
+    __shared__ float s_mean[64], s_rstd[64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int px = lane >> 2, g = lane & 3;
+    const int qn = (cb_n + 31) / 32;                        // 32-channel quads per tile row group
+    const int n_it = 16 * qn;                               // warp items per tile
+
+    // item `it` (warp-uniform) of tile t: quad q = it / 16 (32 channels), pixel group pg = it % 16 (8 pixels)
+    auto decode = [&](int t, int it) {
+        GnItem r;
+        r.dup = false;
+        r.src = nullptr; r.oi = r.oi2 = 0;
+        const int q = it >> 4, pg = it & 15;
+        r.c = q * 32 + g * 8;
+        r.ok = it < n_it && t < tiles && r.c < cb_n;
+        if (!r.ok) return r;
+        const int hh = t / WT, wt = t - hh * WT;
+        const int c = c0 + r.c, c8 = c >> 3;
+        const int tp = pg * 8 + px;                          // pixel inside the tile
+        const size_t pix = (size_t)b * HW + (size_t)hh * W + wt * OTW + tp;
+        r.src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
+        const size_t bh = (size_t)b * H + hh;
+        r.oi = operand_unit(bh, WT, c8n, wt, c8, tp + 1) * 8;
+        if (tp == 0) { r.dup = true; r.oi2 = operand_unit(bh, WT, c8n, wt == 0 ? WT - 1 : wt - 1, c8, OPX - 1) * 8; }
+        else if (tp == OTW - 1) { r.dup = true; r.oi2 = operand_unit(bh, WT, c8n, wt == WT - 1 ? 0 : wt + 1, c8, 0) * 8; }
+        return r;
+    };
+    constexpr int NU = 4;      // items in flight per warp: 8 x 16-byte loads per lane before any math
+    float4 ld[NU][2];
+    auto load_batch = [&](int t, int it0) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const GnItem r = decode(t, it0 + u * nwarps);
+            if (r.ok) {
+                ld[u][0] = *reinterpret_cast<const float4*>(r.src);
+                ld[u][1] = *reinterpret_cast<const float4*>(r.src + 4);
+            }
+        }
+    };
+
+    // ---- first loads in flight before the coefficient prologue ----
+    load_batch(tb, warp);
+
+    // ---- per-channel affine coefficients of GroupNorm(+AdaGN) for sample b: y = x * s_a[c] + s_b[c] ----
+    if (st0 != nullptr) {
+        const int cpg = C / groups;
+        const int g_lo = c0 / cpg, g_hi = (c0 + cb_n - 1) / cpg;          // groups overlapping this channel block
+        const int span0 = g_lo * cpg, span = (g_hi + 1) * cpg - span0;   // their channels
+        for (int i = threadIdx.x; i < span; i += blockDim.x) {
+            const int c = span0 + i;
+            const double* p = c < C0 ? st0 + ((size_t)b * C0 + c) * 2 : st1 + ((size_t)b * C1 + (c - C0)) * 2;
+            s_st[2 * i] = p[0];
+            s_st[2 * i + 1] = p[1];
+        }
+        // own coefficients' inputs in the same memory round trip
+        float ga = 1.f, be = 0.f, sc = 1.f, sh = 0.f;
+        const int cown = c0 + (int)threadIdx.x;
+        const bool own = (int)threadIdx.x < cb_n;
+        if (own) {
+            if (gamma) { ga = gamma[cown]; be = beta[cown]; }
+            if (ada) { sc = 1.f + ada[(size_t)b * ada_stride + cown]; sh = ada[(size_t)b * ada_stride + C + cown]; }
+        }
+        __syncthreads();
+        for (int gi = g_lo + warp; gi <= g_hi; gi += nwarps) {           // one warp per group, lanes over its channels
+            double s = 0.0, ss = 0.0;
+            for (int i = lane; i < cpg; i += 32) {
+                s += s_st[2 * ((gi - g_lo) * cpg + i)];
+                ss += s_st[2 * ((gi - g_lo) * cpg + i) + 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            }
+            if (lane == 0) {
+                const double n = (double)HW * cpg;
+                const double mean = s / n;
+                double var = ss / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mean[gi - g_lo] = (float)mean;
+                s_rstd[gi - g_lo] = (float)(1.0 / sqrt(var + (double)eps));
+            }
+        }
+        __syncthreads();
+        if (own) {
+            const int gi = cown / cpg - g_lo;
+            float a = s_rstd[gi], bb = -s_mean[gi] * s_rstd[gi];
+            a *= ga; bb = bb * ga + be;
+            a *= sc; bb = bb * sc + sh;
+            s_a[threadIdx.x] = a;
+            s_b[threadIdx.x] = bb;
+        }
+    } else {
+        for (int c = threadIdx.x; c < cb_n; c += blockDim.x) { s_a[c] = 1.f; s_b[c] = 0.f; }
+    }
+    __syncthreads();
+
+    bool first = true;
+    for (int t = tb; t < tiles; t += tile_blocks) {
+        for (int it0 = warp; it0 < n_it; it0 += NU * nwarps) {
+            if (!first) load_batch(t, it0);
+            first = false;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const GnItem it = decode(t, it0 + u * nwarps);
+                if (!it.ok) continue;     // warp-uniform for C % 32 == 0 (required by parts == 3: shuffles below)
+                float v[8] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w};
+                __half2 h[4];
+                if (y_raw) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                    const uint4 hv = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(y_raw + it.oi) = hv;
+                    if (it.dup) *reinterpret_cast<uint4*>(y_raw + it.oi2) = hv;
+                    if (parts >= 2) {
+                        const uint4 pv = plane1_value(v, h, parts, lane);
+                        *reinterpret_cast<uint4*>(y_raw + lo_off + it.oi) = pv;
+                        if (it.dup) *reinterpret_cast<uint4*>(y_raw + lo_off + it.oi2) = pv;
+                    }
+                }
+                const float4 a0 = *reinterpret_cast<const float4*>(s_a + it.c), a1 = *reinterpret_cast<const float4*>(s_a + it.c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(s_b + it.c), b1 = *reinterpret_cast<const float4*>(s_b + it.c + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float tt = fmaf(v[e], av[e], bv[e]);
+                    if (silu) tt = silu_f(tt);
+                    v[e] = tt;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                const uint4 hv = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(y + it.oi) = hv;
+                if (it.dup) *reinterpret_cast<uint4*>(y + it.oi2) = hv;
+                if (parts >= 2) {   // parts 2: lo = fp16(x - fp32(hi)); parts 3: e4m3 pair plane
+                    const uint4 pv = plane1_value(v, h, parts, lane);
+                    *reinterpret_cast<uint4*>(y + lo_off + it.oi) = pv;
+                    if (it.dup) *reinterpret_cast<uint4*>(y + lo_off + it.oi2) = pv;
+                }
+            }
+        }
+    }
+}
+
+// decomposition for large tensors: one block = up to 256 consecutive pixels x all channels
+__global__ void __launch_bounds__(256) gn_act_kernel_v1(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
                                                      int C1, const double* __restrict__ st0,
                                                      const double* __restrict__ st1, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, const float* __restrict__ ada,
@@ -473,7 +651,7 @@ __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restri
                                                            float* __restrict__ out, double* __restrict__ stats, int H,
                                                            int W, int Cx, int Cout, int ring) {
     __shared__ float red[256 * 8];
-    __shared__ float sw[4 * 9 * 256];                 // [ci][tap][co]
+    __shared__ float sw[4 * 9 * 128];                 // [ci][tap][co], Cout <= 128
     __shared__ float sx[4 * 3 * (IC_PIX + 2)];        // [ci][dy][pixel + 1]
     pdl_launch_dependents();
     pdl_wait();
@@ -721,13 +899,23 @@ extern "C" int b200_device_check(int dev) {
 
 static bool c4_ok(int C) { return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
 
+static int num_sms_cached() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                                const double* stats1, const float* gamma, const float* beta, const float* ada,
                                int ada_stride, int groups, float eps, int silu, void* y, void* y_raw, int parts, int B,
                                int H, int W, void* stream) {
     B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(W % OTW == 0);   // the conv operand is organised in 128-pixel tiles
-    const int HW = H * W;
     B200_CHECK_ARG(x0 && y && C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && (C1 == 0 || x1));
     const int C = C0 + C1;
     B200_CHECK_ARG(parts != 3 || C % 32 == 0);   // fp8 plane: whole warps per 32-channel item
@@ -739,13 +927,43 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     } else {
         B200_CHECK_ARG(!gamma && !ada);
     }
-    // pixels per block: large enough to amortise the per-block coefficient prologue, small enough to fill the GPU
-    int ppb = 256;
-    while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
-    dim3 grid(cdiv(HW, ppb), B);
-    launch_pdl(gn_act_kernel, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1, gamma,
-               beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
-               (size_t)B * H * (W / OTW) * ((C0 + C1) / 8) * OPX * 8, parts, HW, W, ppb);
+    // two decompositions (measured on B200, profiles/r01_gn_act_variants.txt): few large blocks of 256 pixels x all
+    // channels win on big tensors; channel-split blocks in one resident wave win when there are only a few tiles per
+    // sample (4x128 levels: 12 us instead of 18 us).  B200_GN_V1=0/1 forces one of them.
+    static int forced = -2, bps = 8;
+    if (forced == -2) {
+        const char* e = getenv("B200_GN_V1");
+        forced = e ? (e[0] == '1' ? 1 : 0) : -1;
+        if (const char* t = getenv("B200_GN_BPS")) bps = atoi(t) > 0 ? atoi(t) : 8;
+    }
+    const int variant = forced >= 0 ? forced : ((long long)H * W * B > 8192 ? 1 : 0);
+    if (variant == 1) {
+        const int HW = H * W;
+        int ppb = 256;
+        while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
+        dim3 grid(cdiv(HW, ppb), B);
+        launch_pdl(gn_act_kernel_v1, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1,
+                   gamma, beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
+                   (size_t)B * H * (W / OTW) * ((C0 + C1) / 8) * OPX * 8, parts, HW, W, ppb);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
+    // grid = one resident wave: channel blocks of CB (a multiple of 32) channels x strided tile sets, ~4 blocks per SM
+    const int tiles = H * (W / OTW);
+    const int target = bps * num_sms_cached();
+    int CB = C >= 128 ? 128 : ((C + 31) / 32) * 32;
+    while (CB > 32 && (long long)cdiv(C, CB) * tiles * B < target) CB >>= 1;
+    const int n_cb = cdiv(C, CB);
+    int tile_blocks = target / (n_cb * B);
+    if (tile_blocks < 1) tile_blocks = 1;
+    if (tile_blocks > tiles) tile_blocks = tiles;
+    const int cpg = stats0 ? C / groups : 1;
+    const size_t smem = (size_t)8 * CB + (size_t)16 * (CB + 2 * cpg);
+    B200_CHECK_ARG(smem <= 48 * 1024);
+    dim3 grid(n_cb * tile_blocks, B);
+    launch_pdl(gn_act_kernel, grid, dim3(256), smem, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1, gamma, beta, ada,
+               ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
+               (size_t)B * H * (W / OTW) * ((C0 + C1) / 8) * OPX * 8, parts, H, W, CB, tile_blocks);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -809,7 +1027,7 @@ extern "C" int b200_in_conv(const float* x, const float* w, const float* cst, in
                             double* stats, int B, int H, int W, int Cx, int Cout, int ring, void* stream) {
     B200_CHECK_ARG(x && w && cst && out);
     B200_CHECK_ARG(Cx >= 1 && Cx <= 4 && Cout <= 256 && c4_ok(Cout));
-    if (W % IC_PIX == 0) {
+    if (W % IC_PIX == 0 && Cout <= 128) {
         dim3 grid(W / IC_PIX, H, B);
         launch_pdl(in_conv_rows_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, w, cst, cst_batched, out, stats, H, W,
                    Cx, Cout, ring);

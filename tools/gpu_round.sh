@@ -19,6 +19,10 @@ timeout 600 python bench.py --steps 20 --warmup 3 --precision fp16f8 --profile-o
 echo "bench fp16f8 rc=$?"
 cat gpurun_out/bench_fp16f8.json | head -c 400
 timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
+if [ "${SPLIT:-0}" = "1" ]; then
+  timeout 600 python tools/exp_split.py fp16f8 8 > gpurun_out/exp_split.txt 2>&1
+  cat gpurun_out/exp_split.txt | tail -4
+fi
 if [ "${NCU:-0}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profiler-range > gpurun_out/ncu_bench.log 2>&1
