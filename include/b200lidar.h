@@ -60,6 +60,18 @@ const char* b200_last_error(void);
 int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
                  float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
                  int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
+/* b200_conv_tc + fused GroupNorm(+AdaGN)(+SiLU) tail: replaces  conv -> nn.GroupNorm / AdaGN -> SiLU  of
+ * ResidualBlock.forward (models/unets/efficient_unet.py:104-111; layout_unet_v1.py:229-243) in ONE launch.  After all tiles
+ * are written (out, stats as b200_conv_tc; stats must be non-NULL and zero on entry) the CTAs meet at a grid-wide barrier
+ * (the grid is <= one CTA per SM and co-resident by construction), then every CTA re-reads the tiles it produced (L2
+ * hits), normalises them with the now complete statistics and writes y = the conv operand (layout above, y_parts planes)
+ * that b200_gn_act_f16(out, stats, gamma, beta, ada, ...) would have written -- same arguments, same result.
+ * Needs bn % (Cout / groups) == 0 (every group inside one n-tile).                                      */
+int b200_conv_tc_gn(const void* a, const void* wpacked, const float* bias, const float* res,
+                    float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
+                    int Cout, int taps, int ring, int bn, int rows, int parts, const float* gamma,
+                    const float* beta, const float* ada, int ada_stride, int groups, float eps, int silu,
+                    void* y, int y_parts, void* stream);
 /* profiling aid: device buffer of [#CTAs][8] uint64 cycle counters filled by b200_conv_tc (NULL disables; see
  * conv_tc.cu g_conv_dbg for the slot meaning).  Not used on the product path.                          */
 int b200_conv_set_debug(void* dbg_u64);
@@ -113,6 +125,10 @@ int b200_channel_stats(const float* x, double* stats, int B, int HW, int C, void
  *   up=0: [B,H,W,C] -> [B,H/2,W/2,C];  up=1: [B,H,W,C] -> [B,2H,2W,C];  stats (optional) as above     */
 int b200_fir_resample(const float* x, float* y, double* stats, int B, int H, int W, int C, int up,
                       int ring, void* stream);
+/* FIR x2 upsample (as b200_fir_resample with up = 1) written directly as the conv operand (layout of b200_conv_tc,
+ * `parts` planes) of the ring conv that follows it in Block.forward (efficient_unet.py:176-190): x fp32 [B,H,W,C] ->
+ * y operand of the image [B,2H,2W,C].  2W % 128 == 0, C % 8 == 0 (parts 3: C % 32 == 0).                     */
+int b200_fir_up_operand(const float* x, void* y, int parts, int B, int H, int W, int C, int ring, void* stream);
 
 /* ---- K4: time embedding + all per-block (scale,shift) projections --------------------------------
  * replaces: SinusoidalPositionalEmbedding + 2 Linear (efficient_unet.py:237-242, ops.py:14-26) and the

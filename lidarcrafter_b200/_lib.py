@@ -23,6 +23,7 @@ PROTOTYPES = {
     "b200_device_check": (I, [I]),
     "b200_last_error": (C.c_char_p, []),
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+    "b200_conv_tc_gn": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, F, I, P, I, P]),
     "b200_conv_set_debug": (I, [P]),
     "b200_packed_weight_elems": (SZ, [I, I, I, I]),
     "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, F, P]),
@@ -36,6 +37,7 @@ PROTOTYPES = {
     "b200_flash_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
     "b200_channel_stats": (I, [P, P, I, I, I, P]),
     "b200_fir_resample": (I, [P, P, P, I, I, I, I, I, I, P]),
+    "b200_fir_up_operand": (I, [P, P, I, I, I, I, I, I, P]),
     "b200_time_embed": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
     "b200_in_conv": (I, [P, P, P, I, P, P, I, I, I, I, I, I, P]),
     "b200_conv_direct_f32": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),

@@ -300,6 +300,61 @@ __device__ __forceinline__ void store_operand_elem(__half* out, size_t plane_ele
     }
 }
 
+// second operand plane of one lane's 8 channels (v = fp32 values, h = their fp16 roundings), as one 16-byte unit:
+//   parts == 2: lo = fp16(x - hi)  (error-compensation term of the fp16x3 split)
+//   parts == 3: per 16-channel chunk the even 8-channel slab position holds L8 = e4m3((x - hi) * 2^11) of all 16
+//               channels and the odd one A8 = e4m3(x) (see common.cuh); the two lanes of a chunk swap halves.
+__device__ __forceinline__ uint4 plane1_value(const float* v, const __half2* h, int parts, int lane) {
+    float lo[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(h[e]);
+        lo[2 * e] = v[2 * e] - hf.x;
+        lo[2 * e + 1] = v[2 * e + 1] - hf.y;
+    }
+    if (parts == 2) {
+        __half2 l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l[e] = __floats2half2_rn(lo[2 * e], lo[2 * e + 1]);
+        return *reinterpret_cast<const uint4*>(l);
+    }
+    uint2 l8, a8;
+    l8.x = f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE, lo[3] * F8_LO_SCALE);
+    l8.y = f8x4(lo[4] * F8_LO_SCALE, lo[5] * F8_LO_SCALE, lo[6] * F8_LO_SCALE, lo[7] * F8_LO_SCALE);
+    a8.x = f8x4(v[0], v[1], v[2], v[3]);
+    a8.y = f8x4(v[4], v[5], v[6], v[7]);
+    const bool odd = lane & 1;
+    const uint2 send = odd ? l8 : a8;
+    uint2 recv;
+    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+    return odd ? make_uint4(recv.x, recv.y, a8.x, a8.y) : make_uint4(l8.x, l8.y, recv.x, recv.y);
+}
+
+// GroupNorm-apply (+SiLU) of one lane's 8 channels and store as conv operand unit(s): v <- act(v * a + b); writes the
+// fp16 hi unit, the plane-1 unit (parts >= 2) and the halo duplicates.  All 32 lanes of a warp must call it together
+// when parts == 3 (plane1_value shuffles between the two lanes of a 16-channel chunk).
+__device__ __forceinline__ void gn_apply_store(float* v, const float* av, const float* bv, int silu, int parts, __half* y,
+                                               size_t lo_off, size_t oi, size_t oi2, bool dup, int lane) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v[e], av[e], bv[e]);
+        if (silu) t = silu_f(t);
+        v[e] = t;
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const uint4 hv = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(y + oi) = hv;
+    if (dup) *reinterpret_cast<uint4*>(y + oi2) = hv;
+    if (parts >= 2) {   // parts 2: lo = fp16(x - fp32(hi)); parts 3: e4m3 pair plane
+        const uint4 pv = plane1_value(v, h, parts, lane);
+        *reinterpret_cast<uint4*>(y + lo_off + oi) = pv;
+        if (dup) *reinterpret_cast<uint4*>(y + lo_off + oi2) = pv;
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

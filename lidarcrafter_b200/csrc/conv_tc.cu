@@ -48,7 +48,40 @@ struct ConvParams {
     float w_inv;  // 1 / (power-of-two scale applied to the packed weights)
     int B, H, W, Cin, Cout, ring;
     int n_tiles;
+    // optional fused tail (b200_conv_tc_gn): after a grid-wide barrier every CTA re-reads the tiles it produced (L2 hits),
+    // applies GroupNorm(+AdaGN)(+SiLU) with the now complete statistics and writes the next conv's operand
+    __half* gn_y;             // nullptr: no tail
+    const float* gn_gamma;
+    const float* gn_beta;
+    const float* gn_ada;
+    int gn_ada_stride, gn_groups, gn_silu, gn_parts;
+    float gn_eps;
+    unsigned* gn_bar;         // {arrival count, generation} of this launch's barrier slot
 };
+
+__device__ unsigned g_gn_bar[64 * 2];   // barrier slots handed out round-robin by the host (one per launch in flight)
+
+// Grid-wide barrier for a grid that is co-resident by construction (<= one CTA per SM, checked on the host).  Bounded
+// spin: a scheduling assumption that does not hold becomes a trap (launch error), not a hung GPU.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n) {
+    volatile unsigned* vgen = bar + 1;
+    const unsigned gen = *vgen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == n - 1) {
+        bar[0] = 0;
+        __threadfence();
+        atomicAdd(bar + 1, 1u);
+    } else {
+        unsigned spins = 0;
+        while (*vgen == gen) {
+            if (++spins > (1u << 27)) {
+                printf("b200lidar: grid barrier timeout (block %d)\n", blockIdx.x);
+                __trap();
+            }
+        }
+    }
+    __threadfence();
+}
 
 __device__ __align__(128) unsigned char g_zero_page[16384];  // source of zero-padding rows / pixels
 
@@ -481,6 +514,97 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         __syncwarp();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+    if (p.gn_y != nullptr) {
+        // ------------------------------ fused GroupNorm(+AdaGN)+SiLU tail ------------------------------
+        __threadfence();           // this CTA's output stores and statistics atomics are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) grid_barrier(p.gn_bar, gridDim.x);   // ... before anyone reads the complete statistics
+        __syncthreads();
+        float* s_a = reinterpret_cast<float*>(smem + C::OFF_EPI);   // [BN] (the epilogue staging area is free now)
+        float* s_b = s_a + BN;                                      // [BN]
+        float* s_mr = s_b + BN;                                     // [2 * BN / cpg] mean, rstd
+        const int cpg = p.Cout / p.gn_groups;                       // BN % cpg == 0 (host check)
+        const int WTo = p.W / OTW, c8n = p.Cout / 8;
+        const size_t lo_off = (size_t)p.B * p.H * WTo * c8n * OPX * 8;
+        const int px = lane >> 2, g = lane & 3;
+        constexpr int QN = BN / 32, NIT = R * 16 * QN, NW = CONV_THREADS / 32;
+        int cur_b = -1, cur_nt = -1;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+            int t = tile;
+            const int wt = t % WT; t /= WT;
+            const int hg = t % HG; t /= HG;
+            const int nt = t % NT;
+            const int b = t / NT;
+            const int h0 = hg * R, n0 = nt * BN;
+            if (b != cur_b || nt != cur_nt) {      // per-channel affine coefficients of (sample b, channels n0 .. n0 + BN)
+                cur_b = b; cur_nt = nt;
+                __syncthreads();
+                if ((int)threadIdx.x < BN / cpg) {
+                    const double* st = p.stats + ((size_t)b * p.Cout + n0 + threadIdx.x * cpg) * 2;
+                    double su = 0.0, ss = 0.0;
+                    for (int c = 0; c < cpg; ++c) { su += __ldcg(st + 2 * c); ss += __ldcg(st + 2 * c + 1); }
+                    const double n = (double)p.H * p.W * cpg;
+                    const double mean = su / n;
+                    double var = ss / n - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    s_mr[2 * threadIdx.x] = (float)mean;
+                    s_mr[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+                }
+                __syncthreads();
+                if ((int)threadIdx.x < BN) {
+                    const int c = n0 + threadIdx.x, gi = threadIdx.x / cpg;
+                    float a = s_mr[2 * gi + 1], bb = -s_mr[2 * gi] * s_mr[2 * gi + 1];
+                    if (p.gn_gamma) { a *= p.gn_gamma[c]; bb = bb * p.gn_gamma[c] + p.gn_beta[c]; }
+                    if (p.gn_ada) {
+                        const float sc = 1.f + p.gn_ada[(size_t)b * p.gn_ada_stride + c];
+                        const float sh = p.gn_ada[(size_t)b * p.gn_ada_stride + p.Cout + c];
+                        a *= sc; bb = bb * sc + sh;
+                    }
+                    s_a[threadIdx.x] = a;
+                    s_b[threadIdx.x] = bb;
+                }
+                __syncthreads();
+            }
+            // warp item = 8 pixels x 32 channels of one tile row (lane -> pixel lane/4, 8-channel group lane%4); TNU
+            // items (2 x 16-byte loads per lane each) in flight: only 12 warps per SM hide the L2 latency here
+            constexpr int TNU = 6;
+            for (int it0 = warp; it0 < NIT; it0 += TNU * NW) {
+                float4 ld[TNU][2];
+#pragma unroll
+                for (int u = 0; u < TNU; ++u) {
+                    const int it = it0 + u * NW;
+                    if (it < NIT) {
+                        const int o = it / (16 * QN), r = it - o * 16 * QN;
+                        const int q = r >> 4, pg = r & 15;
+                        const float* src = p.out + ((size_t)(b * p.H + h0 + o) * p.W + wt * OTW + pg * 8 + px) * p.Cout +
+                                           n0 + q * 32 + g * 8;
+                        ld[u][0] = __ldcg(reinterpret_cast<const float4*>(src));
+                        ld[u][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TNU; ++u) {
+                    const int it = it0 + u * NW;
+                    if (it >= NIT) continue;
+                    const int o = it / (16 * QN), r = it - o * 16 * QN;
+                    const int q = r >> 4, pg = r & 15;
+                    const int cl = q * 32 + g * 8, c8 = (n0 + cl) >> 3, tp = pg * 8 + px;
+                    const size_t bh = (size_t)b * p.H + h0 + o;
+                    const size_t oi = operand_unit(bh, WTo, c8n, wt, c8, tp + 1) * 8;
+                    size_t oi2 = 0;
+                    bool dup = false;
+                    if (tp == 0) { dup = true; oi2 = operand_unit(bh, WTo, c8n, wt == 0 ? WTo - 1 : wt - 1, c8, OPX - 1) * 8; }
+                    else if (tp == OTW - 1) { dup = true; oi2 = operand_unit(bh, WTo, c8n, wt == WTo - 1 ? 0 : wt + 1, c8, 0) * 8; }
+                    float v[8] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w};
+                    const float4 a0 = *reinterpret_cast<const float4*>(s_a + cl), a1 = *reinterpret_cast<const float4*>(s_a + cl + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_b + cl), b1 = *reinterpret_cast<const float4*>(s_b + cl + 4);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    gn_apply_store(v, av, bv, p.gn_silu, p.gn_parts, p.gn_y, lo_off, oi, oi2, dup, lane);
+                }
+            }
+        }
+    }
 #undef FULL_A
 #undef EMPTY_A
 #undef FULL_B
@@ -754,9 +878,18 @@ extern "C" int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, 
     return B200_OK;
 }
 
-extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
-                            float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
-                            int ring, int bn, int rows, int parts, void* stream) {
+struct GnTail {
+    void* y = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    const float* ada = nullptr;
+    int ada_stride = 0, groups = 0, silu = 0, parts = 0;
+    float eps = 0.f;
+};
+
+static int conv_tc_impl(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
+                        float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps, int ring,
+                        int bn, int rows, int parts, const GnTail& gn, void* stream) {
     B200_CHECK_ARG(a && wpacked && out);
     B200_CHECK_ARG(B > 0 && H > 0 && W > 0);
     B200_CHECK_ARG(taps == 9 || taps == 1);
@@ -767,6 +900,23 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(rows * bn <= 256);   // two TMEM accumulator sets <= 512 columns (merged mode is chosen when 2x fits)
     ConvParams p{(const __half*)a, (const __half*)wpacked, bias, res, out, stats, out_scale, w_inv,
                  B, H, W, Cin, Cout, ring, 0};
+    p.gn_y = nullptr;
+    if (gn.y) {
+        B200_CHECK_ARG(stats != nullptr);                                   // the tail normalises with THIS launch's statistics
+        B200_CHECK_ARG(gn.groups > 0 && Cout % gn.groups == 0 && bn % (Cout / gn.groups) == 0);   // groups inside an n-tile
+        B200_CHECK_ARG(gn.parts >= 1 && gn.parts <= 3 && (gn.gamma == nullptr) == (gn.beta == nullptr));
+        static unsigned slot = 0;
+        unsigned* bars = nullptr;
+        if (cudaGetSymbolAddress((void**)&bars, g_gn_bar) != cudaSuccess) {
+            set_error("conv_tc_gn: cudaGetSymbolAddress failed");
+            return B200_E_CUDA;
+        }
+        p.gn_y = (__half*)gn.y;
+        p.gn_gamma = gn.gamma; p.gn_beta = gn.beta; p.gn_ada = gn.ada;
+        p.gn_ada_stride = gn.ada_stride; p.gn_groups = gn.groups; p.gn_silu = gn.silu; p.gn_parts = gn.parts;
+        p.gn_eps = gn.eps;
+        p.gn_bar = bars + 2 * (slot++ % 64);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -799,6 +949,26 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
 #undef B200_CONV_CASE
     set_error("conv_tc: unsupported tile bn=%d rows=%d (need rows*bn <= 256)", bn, rows);
     return B200_E_ARG;
+}
+
+extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
+                            float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
+                            int ring, int bn, int rows, int parts, void* stream) {
+    return conv_tc_impl(a, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
+                        parts, GnTail{}, stream);
+}
+
+extern "C" int b200_conv_tc_gn(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
+                               float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
+                               int ring, int bn, int rows, int parts, const float* gamma, const float* beta,
+                               const float* ada, int ada_stride, int groups, float eps, int silu, void* y, int y_parts,
+                               void* stream) {
+    B200_CHECK_ARG(y != nullptr);
+    GnTail gn;
+    gn.y = y; gn.gamma = gamma; gn.beta = beta; gn.ada = ada; gn.ada_stride = ada_stride; gn.groups = groups;
+    gn.eps = eps; gn.silu = silu; gn.parts = y_parts;
+    return conv_tc_impl(a, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
+                        parts, gn, stream);
 }
 
 extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias, const float* res, float out_scale,

@@ -75,37 +75,6 @@ __device__ __forceinline__ void gn_coefficients(const double* __restrict__ st0, 
     }
 }
 
-// second operand plane of one lane's 8 channels (v = fp32 values, h = their fp16 roundings), as one 16-byte unit:
-//   parts == 2: lo = fp16(x - hi)  (error-compensation term of the fp16x3 split)
-//   parts == 3: per 16-channel chunk the even 8-channel slab position holds L8 = e4m3((x - hi) * 2^11) of all 16
-//               channels and the odd one A8 = e4m3(x) (see common.cuh); the two lanes of a chunk swap halves.
-__device__ __forceinline__ uint4 plane1_value(const float* v, const __half2* h, int parts, int lane) {
-    float lo[8];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 hf = __half22float2(h[e]);
-        lo[2 * e] = v[2 * e] - hf.x;
-        lo[2 * e + 1] = v[2 * e + 1] - hf.y;
-    }
-    if (parts == 2) {
-        __half2 l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) l[e] = __floats2half2_rn(lo[2 * e], lo[2 * e + 1]);
-        return *reinterpret_cast<const uint4*>(l);
-    }
-    uint2 l8, a8;
-    l8.x = f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE, lo[3] * F8_LO_SCALE);
-    l8.y = f8x4(lo[4] * F8_LO_SCALE, lo[5] * F8_LO_SCALE, lo[6] * F8_LO_SCALE, lo[7] * F8_LO_SCALE);
-    a8.x = f8x4(v[0], v[1], v[2], v[3]);
-    a8.y = f8x4(v[4], v[5], v[6], v[7]);
-    const bool odd = lane & 1;
-    const uint2 send = odd ? l8 : a8;
-    uint2 recv;
-    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
-    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-    return odd ? make_uint4(recv.x, recv.y, a8.x, a8.y) : make_uint4(l8.x, l8.y, recv.x, recv.y);
-}
-
 // output layout: the conv operand of common.cuh ("tile-major slabs"): y[plane][b][h][W/128][C/8][130][8]
 //
 // Work decomposition: block = (sample b, channel block of CB channels, a strided set of 128-pixel tiles); the grid is one
@@ -521,6 +490,58 @@ __global__ void __launch_bounds__(256) fir_kernel(const float* __restrict__ x, f
     if (stats) block_channel_reduce(s1, s2, C, b, stats, red);
 }
 
+// FIR x2 upsample written DIRECTLY as the next conv's operand (Block.forward: Resample(up) -> ring conv,
+// efficient_unet.py:176-190): same taps / summation order as fir_kernel<true>, no fp32 round trip through HBM and no
+// separate cast launch.  Block = one 128-pixel tile of one output row; warp item = 8 pixels x 32 channels.
+__global__ void __launch_bounds__(256) fir_up_operand_kernel(const float* __restrict__ x, __half* __restrict__ y,
+                                                             size_t lo_off, int parts, int H, int W, int C, int ring) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Ho = 2 * H, Wo = 2 * W, WT = Wo / OTW, c8n = C / 8;
+    const int b = blockIdx.y;
+    const int oh = blockIdx.x / WT, wt = blockIdx.x - oh * WT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int px = lane >> 2, g = lane & 3;
+    const int ih = oh >> 1;
+    const int hn = (oh & 1) ? ih + 1 : ih - 1;
+    const bool hn_ok = hn >= 0 && hn < H;
+    const int qn = (C + 31) / 32;
+    const float* xb = x + (size_t)b * H * W * C;
+    const size_t bh = (size_t)b * Ho + oh;
+    for (int it = warp; it < 16 * qn; it += nwarps) {
+        const int q = it >> 4, pg = it & 15;
+        const int c = q * 32 + g * 8;
+        if (c >= C) continue;                 // warp-uniform when C % 32 == 0 (required for parts == 3)
+        const int tp = pg * 8 + px, ow = wt * OTW + tp;
+        const int iw = ow >> 1;
+        int wn = (ow & 1) ? iw + 1 : iw - 1;
+        bool wn_ok = true;
+        if (wn < 0) { if (ring) wn += W; else wn_ok = false; }
+        else if (wn >= W) { if (ring) wn -= W; else wn_ok = false; }
+        float v[8];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const float* xc = xb + c + 4 * hf;
+            float4 acc = make_float4(0, 0, 0, 0);
+            fma4(acc, 9.f / 16.f, ld4(xc + ((size_t)ih * W + iw) * C));
+            if (wn_ok) fma4(acc, 3.f / 16.f, ld4(xc + ((size_t)ih * W + wn) * C));
+            if (hn_ok) {
+                fma4(acc, 3.f / 16.f, ld4(xc + ((size_t)hn * W + iw) * C));
+                if (wn_ok) fma4(acc, 1.f / 16.f, ld4(xc + ((size_t)hn * W + wn) * C));
+            }
+            v[4 * hf] = acc.x; v[4 * hf + 1] = acc.y; v[4 * hf + 2] = acc.z; v[4 * hf + 3] = acc.w;
+        }
+        const int c8 = c >> 3;
+        const size_t oi = operand_unit(bh, WT, c8n, wt, c8, tp + 1) * 8;
+        size_t oi2 = 0;
+        bool dup = false;
+        if (tp == 0) { dup = true; oi2 = operand_unit(bh, WT, c8n, wt == 0 ? WT - 1 : wt - 1, c8, OPX - 1) * 8; }
+        else if (tp == OTW - 1) { dup = true; oi2 = operand_unit(bh, WT, c8n, wt == WT - 1 ? 0 : wt + 1, c8, 0) * 8; }
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        gn_apply_store(v, one, zero, 0, parts, y, lo_off, oi, oi2, dup, lane);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // time embedding MLP + stacked (scale, shift) projections
 // ---------------------------------------------------------------------------------------------------------
@@ -778,49 +799,60 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const TIn* __restrict__ a
     for (int co = 0; co < Cout; ++co) pred[((size_t)b * Cout + co) * HW + pp] = acc[co] + bias[co];
 }
 
-// out_conv, row-tiled: one block = 128 consecutive pixels of one image row.  Stage 1 reads every input pixel of the
-// three halo rows ONCE (coalesced 256 B per pixel) and reduces its Cin channels to the 3 x Cout partial sums of the
-// filter row it feeds; stage 2 adds the 9 partial sums of each output pixel.  (The thread-per-pixel kernel above
-// re-reads every input pixel 9 times from L1/L2.)
-constexpr int OC_PIX = 128, OC_THREADS = 256;
+// out_conv, row-tiled: one block = 128 consecutive pixels of one image row.  The three halo rows are staged through
+// shared memory in 16-channel chunks with COALESCED loads (4 lanes x 16 B per pixel; a thread-per-pixel walk over the
+// 256-byte pixel rows costs 32 L1 line look-ups per load instruction and ran at 0.1 ms on B200).  Stage 1: thread =
+// one staged pixel, reduces its channels to the 3 x Cout partial sums of the filter row it feeds; stage 2 adds the 9
+// partial sums of each output pixel.
+constexpr int OC_PIX = 128, OC_THREADS = 416, OC_CH = 16, OC_PITCH = 20;   // 3 * 130 = 390 staged pixels <= 416 threads
 
 __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ pred,
                                                                    int H, int W, int Cin, int Cout, int ring) {
-    extern __shared__ float osm[];
+    extern __shared__ __align__(16) float osm[];
     pdl_launch_dependents();
     pdl_wait();
     float* sw = osm;                                   // [3 dy][Cin][12]  (dx*4 + co, zero padded)
-    float* st = osm + 3 * Cin * 12;                    // [3 rows][130 px][12]
+    float* sx = osm + 3 * Cin * 12;                    // [3 rows][130 px][OC_PITCH] channel chunk; later [3][130][12] sums
     for (int i = threadIdx.x; i < 3 * Cin * 12; i += OC_THREADS) {
         const int q = i % 12, ci = (i / 12) % Cin, dy = i / (12 * Cin);
         const int dx = q >> 2, co = q & 3;
         sw[i] = co < Cout ? w[((size_t)co * Cin + ci) * 9 + dy * 3 + dx] : 0.f;
     }
-    __syncthreads();
     const int wt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int w0 = wt * OC_PIX;
-    for (int item = threadIdx.x; item < 3 * (OC_PIX + 2); item += OC_THREADS) {
-        const int r = item / (OC_PIX + 2), j = item - r * (OC_PIX + 2);
-        const int gh = h + r - 1;
-        int gw = w0 + j - 1;
-        bool ok = gh >= 0 && gh < H;
-        if (gw < 0) { if (ring) gw += W; else ok = false; }
-        else if (gw >= W) { if (ring) gw -= W; else ok = false; }
-        float acc[12];
+    constexpr int NPX = OC_PIX + 2;
+    const int item = threadIdx.x;                      // staged pixel (r, j) of this thread
+    const int ir = item / NPX, ij = item - ir * NPX;
+    float acc[12];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) acc[q] = 0.f;
-        if (ok) {
-            const float* ap = a + ((size_t)(b * H + gh) * W + gw) * Cin;
-            const float* wr = sw + r * Cin * 12;
-            for (int ci = 0; ci < Cin; ci += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(ap + ci);
+    for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+    for (int c0 = 0; c0 < Cin; c0 += OC_CH) {
+        __syncthreads();                               // previous chunk consumed (and, first time, sw complete)
+        for (int i = threadIdx.x; i < 3 * NPX * (OC_CH / 4); i += OC_THREADS) {
+            const int f = i % (OC_CH / 4), pj = i / (OC_CH / 4);
+            const int r = pj / NPX, j = pj - r * NPX;
+            const int gh = h + r - 1;
+            int gw = w0 + j - 1;
+            bool ok = gh >= 0 && gh < H;
+            if (gw < 0) { if (ring) gw += W; else ok = false; }
+            else if (gw >= W) { if (ring) gw -= W; else ok = false; }
+            const float4 v = ok ? ld4(a + ((size_t)(b * H + gh) * W + gw) * Cin + c0 + 4 * f) : make_float4(0, 0, 0, 0);
+            *reinterpret_cast<float4*>(sx + (size_t)pj * OC_PITCH + 4 * f) = v;
+        }
+        __syncthreads();
+        if (item < 3 * NPX) {
+            const float* xp = sx + (size_t)item * OC_PITCH;
+            const float* wr = sw + ((size_t)ir * Cin + c0) * 12;
+#pragma unroll
+            for (int f = 0; f < OC_CH / 4; ++f) {
+                const float4 v = *reinterpret_cast<const float4*>(xp + 4 * f);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float4 w0v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12);
-                    const float4 w1v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12 + 4);
-                    const float4 w2v = *reinterpret_cast<const float4*>(wr + (ci + e) * 12 + 8);
+                    const float4 w0v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12);
+                    const float4 w1v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 4);
+                    const float4 w2v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 8);
                     acc[0] = fmaf(vv[e], w0v.x, acc[0]); acc[1] = fmaf(vv[e], w0v.y, acc[1]);
                     acc[2] = fmaf(vv[e], w0v.z, acc[2]); acc[3] = fmaf(vv[e], w0v.w, acc[3]);
                     acc[4] = fmaf(vv[e], w1v.x, acc[4]); acc[5] = fmaf(vv[e], w1v.y, acc[5]);
@@ -830,19 +862,22 @@ __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* 
                 }
             }
         }
-        float* o = st + (size_t)(r * (OC_PIX + 2) + j) * 12;
+    }
+    __syncthreads();                                   // all chunk reads done: reuse sx for the partial sums
+    float* st = sx;                                    // [3 rows][130 px][12]
+    if (item < 3 * NPX) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) o[q] = acc[q];
+        for (int q = 0; q < 12; ++q) st[(size_t)item * 12 + q] = acc[q];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < OC_PIX * Cout; i += OC_THREADS) {
         const int co = i / OC_PIX, px = i - co * OC_PIX;     // consecutive threads -> consecutive pixels (NCHW store)
-        float acc = bias[co];
+        float o = bias[co];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) acc += st[(size_t)(r * (OC_PIX + 2) + px + dx) * 12 + dx * 4 + co];
-        pred[((size_t)(b * Cout + co) * H + h) * W + w0 + px] = acc;
+            for (int dx = 0; dx < 3; ++dx) o += st[(size_t)(r * NPX + px + dx) * 12 + dx * 4 + co];
+        pred[((size_t)(b * Cout + co) * H + h) * W + w0 + px] = o;
     }
 }
 
@@ -1005,6 +1040,16 @@ extern "C" int b200_fir_resample(const float* x, float* y, double* stats, int B,
     return B200_OK;
 }
 
+extern "C" int b200_fir_up_operand(const float* x, void* y, int parts, int B, int H, int W, int C, int ring, void* stream) {
+    B200_CHECK_ARG(x && y && parts >= 1 && parts <= 3);
+    B200_CHECK_ARG(C % 8 == 0 && (parts != 3 || C % 32 == 0) && (2 * W) % OTW == 0);
+    dim3 grid(2 * H * (2 * W / OTW), B);
+    launch_pdl(fir_up_operand_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, (__half*)y,
+               (size_t)B * 2 * H * (2 * W / OTW) * (C / 8) * OPX * 8, parts, H, W, C, ring);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
 extern "C" int b200_time_embed(const float* t, const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* temb_add, const float* wp, const float* bp, float* temb, float* ada, int B,
                                int Cs, int E, int P, void* stream) {
@@ -1055,8 +1100,8 @@ extern "C" int b200_out_conv(const void* a, int a_is_f16, const float* w, const 
                              int W, int Cin, int Cout, int ring, void* stream) {
     B200_CHECK_ARG(a && w && bias && pred && Cout >= 1 && Cout <= 4);
     B200_CHECK_ARG(Cin % 8 == 0);
-    if (!a_is_f16 && W % OC_PIX == 0) {
-        const size_t sm = ((size_t)3 * Cin * 12 + 3 * (OC_PIX + 2) * 12) * sizeof(float);
+    if (!a_is_f16 && W % OC_PIX == 0 && Cin % OC_CH == 0) {
+        const size_t sm = ((size_t)3 * Cin * 12 + 3 * (OC_PIX + 2) * OC_PITCH) * sizeof(float);
         if (sm <= 48 * 1024) {
             dim3 grid(W / OC_PIX, H, B);
             launch_pdl(out_conv_rows_kernel, grid, dim3(OC_THREADS), sm, (cudaStream_t)stream, (const float*)a, w, bias, pred,

@@ -327,9 +327,10 @@ class EfficientUNetPlan:
         a1 = pb.gn_act(srcs, rb.norm1.weight, rb.norm1.bias, G, eps, True, also_raw=has_skip)
         if has_skip:
             a1, x16 = a1
-        hmid, st_h = pb.conv(a1, H, W, rb.conv1.weight, rb.conv1.bias, None, 1.0, True)
-        a2 = pb.gn_act([Act(hmid, H, W, rb.cout, st_h)], None, None, G, eps, True, ada=self.ada, ada_stride=self.P,
-                       ada_off=self.ada_off[id(rb)])
+        # conv1 -> AdaGN(norm2) -> SiLU in one launch (fused tail); a2 = the operand of conv2
+        hmid, st_h, a2 = pb.conv(a1, H, W, rb.conv1.weight, rb.conv1.bias, None, 1.0, True,
+                                 gn=dict(gamma=None, beta=None, groups=G, eps=eps, silu=True, ada=self.ada,
+                                         ada_stride=self.P, ada_off=self.ada_off[id(rb)]))
         if not has_skip:
             assert len(srcs) == 1
             res = srcs[0].t
@@ -372,11 +373,10 @@ class EfficientUNetPlan:
         if blk.has_attn:
             h = self._attention(blk.self_attn_block, h)
         if blk.has_up:
-            hu = pb.fir(h, up=True, want_stats=False)
             conv = blk.upsample[1]
-            x16 = pb.cast16([hu])
-            y, st = pb.conv(x16, hu.H, hu.W, conv.weight, conv.bias, None, 1.0, True)
-            h = Act(y, hu.H, hu.W, conv.weight.shape[0], st)
+            x16, Hu, Wu = pb.fir_up_operand(h)      # Resample(up) -> conv operand in one pass (no fp32 round trip)
+            y, st = pb.conv(x16, Hu, Wu, conv.weight, conv.bias, None, 1.0, True)
+            h = Act(y, Hu, Wu, conv.weight.shape[0], st)
         return h
 
     # ------------------------------------------------------------------------------------------

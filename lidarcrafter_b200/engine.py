@@ -8,6 +8,7 @@ per forward; weights repacked once into the tensor-core tile image (fp16).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -215,26 +216,46 @@ class PlanBuilder:
         self.ring = 1 if ring else 0
         self.stream = stream
         self.B = plan.B
+        # conv -> GroupNorm -> conv chains in one launch (b200_conv_tc_gn): opt-in with B200_FUSE_GN=1.  Measured on B200
+        # (profiles/r01_fused_gn_tail.txt): the tail runs with 12 warps/SM from L2 and costs what the separate gn_act
+        # launch costs (step 4.07 ms fused vs 3.92 ms unfused), so the default keeps the separate launch.
+        self.fuse_gn = os.environ.get("B200_FUSE_GN", "0") == "1"
 
     # ---- conv on tensor cores (or the FFMA cross-check path) ----
     def conv(self, a16: torch.Tensor, H: int, W: int, weight, bias, res: torch.Tensor | None, scale: float,
-             want_stats: bool) -> tuple[torch.Tensor, dict | None]:
+             want_stats: bool, gn: dict | None = None):
+        """-> (out, stats slot); with ``gn`` (dict(gamma, beta, groups, eps, silu, ada, ada_stride, ada_off)) the
+        GroupNorm(+AdaGN)(+SiLU) of the output is applied by the same launch (b200_conv_tc_gn: grid barrier + tail) and
+        the normalised conv operand is returned as a third value -- the separate gn_act launch and its HBM read of
+        ``out`` disappear."""
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
         out = self.p.f32(self.B, H * W, Cout)
-        st = self.p.new_stats(Cout) if want_stats else None
+        st = self.p.new_stats(Cout) if (want_stats or gn is not None) else None
         fl = 2.0 * self.B * H * W * taps * Cin * Cout
         self.p.flops += fl
         npix = self.B * H * W
         by = npix * (2.0 * planes(self.p.parts) * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
             + 2.0 * planes(self.p.parts) * taps * Cin * Cout
+        y = None
         if self.p.conv_impl == "tc":
             bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
             pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             self.p.bufs.append(pc)
-            self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
-                       1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
-                       self.p.parts, name="conv_tc", flops=fl, nbytes=by)
+            base = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale), 1.0 / pc.wscale, _ptr(out),
+                    _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows, self.p.parts)
+            if gn is not None and self.fuse_gn and bn % (Cout // gn["groups"]) == 0:
+                y = self.p.operand(H, W, Cout)
+                g = None if gn.get("gamma") is None else gn["gamma"].detach().float().contiguous()
+                b = None if gn.get("beta") is None else gn["beta"].detach().float().contiguous()
+                self.p.bufs += [g, b]
+                ada = gn.get("ada")
+                ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * gn.get("ada_off", 0)
+                self.p.add(self.lib.conv_tc_gn, *base, _ptr(g), _ptr(b), ada_ptr, gn.get("ada_stride", 0), gn["groups"],
+                           float(gn["eps"]), 1 if gn["silu"] else 0, _ptr(y), self.p.parts, name="conv_tc", flops=fl,
+                           nbytes=by + npix * 2.0 * planes(self.p.parts) * Cout)
+            else:
+                self.p.add(self.lib.conv_tc, *base, name="conv_tc", flops=fl, nbytes=by)
         else:
             w = weight.detach().float().contiguous()
             ws = weight_scale(w, self.p.parts)
@@ -245,7 +266,12 @@ class PlanBuilder:
             self.p.add(self.lib.conv_ffma, _ptr(a16), _ptr(w16), _ptr(b32), _ptr(res), float(scale), 1.0 / ws,
                        _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts,
                        name="conv_ffma", flops=fl, nbytes=by)
-        return out, st
+        if gn is None:
+            return out, st
+        if y is None:     # unfused: separate GroupNorm-apply launch (cross-check path / groups crossing n-tiles)
+            y = self.gn_act([Act(out, H, W, Cout, st)], gn.get("gamma"), gn.get("beta"), gn["groups"], gn["eps"],
+                            gn["silu"], ada=gn.get("ada"), ada_stride=gn.get("ada_stride", 0), ada_off=gn.get("ada_off", 0))
+        return out, st, y
 
     def tune_tile(self, a16, H, W, weight, bias, res, out):
         """(bn, rows) of b200_conv_tc for this shape: measured once per shape on the device (CUDA events, best of the
@@ -306,6 +332,14 @@ class PlanBuilder:
 
     def cast16(self, srcs: list[Act]) -> torch.Tensor:
         return self.gn_act(srcs, None, None, 1, 0.0, False, normalize=False)
+
+    def fir_up_operand(self, x: Act) -> tuple[torch.Tensor, int, int]:
+        """FIR x2 upsample written straight into the operand of the conv that follows -> (operand, 2H, 2W)"""
+        Ho, Wo = 2 * x.H, 2 * x.W
+        y = self.p.operand(Ho, Wo, x.C)
+        self.p.add(self.lib.fir_up_operand, _ptr(x.t), _ptr(y), self.p.parts, self.B, x.H, x.W, x.C, self.ring,
+                   name="fir_resample", nbytes=self.B * x.C * x.H * x.W * (4.0 + 4 * 2.0 * planes(self.p.parts)))
+        return y, Ho, Wo
 
     def fir(self, x: Act, up: bool, want_stats: bool) -> Act:
         Ho, Wo = (2 * x.H, 2 * x.W) if up else (x.H // 2, x.W // 2)

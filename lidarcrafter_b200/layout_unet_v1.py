@@ -269,10 +269,13 @@ class LayoutUnetPlan:
             plan.bufs += [g, b]
             plan.add(self.lib.gn_act_f32, _ptr(x0.t), _sp(x0.stats), _ptr(g), _ptr(b), GN_GROUPS, GN_EPS, 1, _ptr(t),
                      self.B, H * W, x0.C, name="gn_act_f32", nbytes=8.0 * self.B * H * W * x0.C)
-            tr = pb.fir(Act(t, H, W, x0.C), up=rb.up, want_stats=False)
             xr = pb.fir(x0, up=rb.up, want_stats=False)
-            a1 = pb.cast16([tr])
-            H, W = tr.H, tr.W
+            if rb.up:       # Resample(up) written straight into conv1's operand
+                a1, H, W = pb.fir_up_operand(Act(t, H, W, x0.C))
+            else:
+                tr = pb.fir(Act(t, H, W, x0.C), up=False, want_stats=False)
+                a1 = pb.cast16([tr])
+                H, W = tr.H, tr.W
             res = xr.t
         else:
             has_skip = not isinstance(rb.skip_connection, nn.Identity)
@@ -280,9 +283,10 @@ class LayoutUnetPlan:
             if has_skip:
                 a1, x16 = a1
             res = None
-        hmid, st_h = pb.conv(a1, H, W, conv1.weight, conv1.bias, None, 1.0, True)
-        a2 = pb.gn_act([Act(hmid, H, W, rb.cout, st_h)], n2.weight, n2.bias, GN_GROUPS, GN_EPS, True, ada=self.ada,
-                       ada_stride=self.P, ada_off=self.ada_off[id(rb)])
+        # conv1 -> GroupNorm32 * (1 + scale) + shift -> SiLU in one launch (fused tail); a2 = the operand of conv2
+        hmid, st_h, a2 = pb.conv(a1, H, W, conv1.weight, conv1.bias, None, 1.0, True,
+                                 gn=dict(gamma=n2.weight, beta=n2.bias, groups=GN_GROUPS, eps=GN_EPS, silu=True,
+                                         ada=self.ada, ada_stride=self.P, ada_off=self.ada_off[id(rb)]))
         if res is None:
             if isinstance(rb.skip_connection, nn.Identity):
                 assert len(srcs) == 1

@@ -231,6 +231,20 @@ class EmulatedLib:
         self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
         return 0
 
+    def conv_tc_gn(self, a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts,
+                   gamma, beta, ada, ada_stride, groups, eps, silu, y, y_parts, stream):
+        """conv_tc, then the GroupNorm(+AdaGN)(+SiLU) of its output written as the next conv's operand"""
+        assert stats and bn % (Cout // groups) == 0
+        self.conv_tc(a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts,
+                     stream)
+        self.calls[-1] = "conv_tc_gn"
+        n0 = self.n_launches
+        self.gn_act_f16(out, Cout, 0, 0, stats, 0, gamma, beta, ada, ada_stride, groups, eps, silu, y, 0, y_parts, B, H, W,
+                        stream)
+        self.calls.pop()
+        self.n_launches = n0
+        return 0
+
     def conv_ffma(self, a, w16, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts, stream):
         self._rec("conv_ffma")
         k = 3 if taps == 9 else 1
@@ -334,6 +348,14 @@ class EmulatedLib:
             st = f64(stats, B, C, 2)
             st[:, :, 0] += r.double().sum(dim=(1, 2))
             st[:, :, 1] += (r.double() ** 2).sum(dim=(1, 2))
+        return 0
+
+    def fir_up_operand(self, x, y, parts, B, H, W, C, ring, stream):
+        self._rec("fir_up_operand")
+        from oracle import unet_torch as O
+        t = f32(x, B, H, W, C).permute(0, 3, 1, 2)
+        r = O.fir_up2(t, bool(ring)).permute(0, 2, 3, 1).contiguous()
+        store_operand(y, r, parts, B, 2 * H, 2 * W, C)
         return 0
 
     def time_embed(self, t, w1, b1, w2, b2, add, wp, bp, temb, ada, B, Cs, E, P, stream):

@@ -124,6 +124,43 @@ def test_conv_tc_matches_contract(parts, taps, bn, rows, Cin, Cout, H, W, B):
     assert rel(gs, cs) < 2e-5
 
 
+@pytest.mark.parametrize("parts", [2, 3])
+@pytest.mark.parametrize("bn,rows,Cin,Cout,H,W,B,groups,affine", [
+    (64, 2, 64, 64, 8, 256, 2, 8, False),
+    (64, 2, 64, 64, 32, 1024, 3, 8, False),       # several tiles per CTA, sample changes inside a CTA's tile range
+    (128, 2, 128, 256, 16, 512, 2, 32, True),
+    (128, 1, 256, 128, 4, 128, 3, 8, False),
+])
+def test_conv_tc_gn_fused_tail(parts, bn, rows, Cin, Cout, H, W, B, groups, affine):
+    """conv + (grid barrier) + GroupNorm(+AdaGN)+SiLU tail in one launch == conv_tc followed by gn_act_f16"""
+    h = Both()
+    taps = 9
+    w = h.t(randn(Cout, Cin, 3, 3, seed=1, scale=1 / math.sqrt(Cin * taps)))
+    a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
+    bias = h.t(randn(Cout, seed=3, scale=0.1))
+    wp = h.t(wp_zeros(Cout, Cin, taps, parts))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    gam, bet = h.t(1 + 0.1 * randn(Cout, seed=5)), h.t(0.1 * randn(Cout, seed=6))
+    P = 2 * Cout + 16
+    ada = h.t(0.3 * randn(B, P, seed=7))
+    y = h.t(operand_zeros(parts, B, H, W, Cout))
+    wscale = 64.0 if parts < 3 else 2.0 ** 16
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, rows, parts, wscale])
+    h.call("conv_tc_gn", [("t", a), ("t", wp), ("t", bias), None, 1.0, 1.0 / wscale, ("t", out), ("t", st), B, H, W, Cin,
+                          Cout, taps, 1, bn, rows, parts, ("t", gam) if affine else None, ("t", bet) if affine else None,
+                          ("t", ada), P, groups, 1e-6, 1, ("t", y), parts])
+    assert rel(*h.out(out)) < 1e-5
+    assert rel(*h.out(st)) < 2e-5
+    g, c = h.out(y)
+    pg, pc = load_operand(g.data_ptr(), parts, B, H, W, Cout), load_operand(c.data_ptr(), parts, B, H, W, Cout)
+    val = (lambda p_: p_[0] + p_[1]) if parts == 2 else (lambda p_: p_[0] + p_[1] / 2048.0)
+    assert rel(val(pg), val(pc)) < 1e-4          # the normalised values inherit the conv's fp32 accumulation-order noise
+    raw = g.view(torch.int16).view(n_planes(parts), B, H, W // OTW, Cout // 8, OPX, 8)
+    assert torch.equal(raw[..., 0, :], torch.roll(raw, 1, dims=3)[..., OTW, :])          # halo duplicates
+    assert torch.equal(raw[..., OPX - 1, :], torch.roll(raw, -1, dims=3)[..., 1, :])
+
+
 def test_conv_tc_zero_pad_no_bias_no_res():
     h = Both()
     B, H, W, Cin, Cout = 1, 4, 128, 64, 64
@@ -238,6 +275,21 @@ def test_channel_stats_and_fir():
     st = h.t(torch.zeros(2, 128, 2, dtype=torch.float64))
     h.call("channel_stats", [("t", x), ("t", st), 2, 700, 128])
     assert rel(*h.out(st)) < 1e-6
+
+
+@pytest.mark.parametrize("parts", [2, 1, 3])
+@pytest.mark.parametrize("ring", [1, 0])
+def test_fir_up_operand(parts, ring):
+    h = Both()
+    B, H, W, C = 2, 3, 128, 64
+    x = h.t(randn(B, H, W, C, seed=1))
+    y = h.t(operand_zeros(parts, B, 2 * H, 2 * W, C))
+    h.call("fir_up_operand", [("t", x), ("t", y), parts, B, H, W, C, ring])
+    g, c = h.out(y)
+    if parts == 2:
+        pg, pc = load_operand(g.data_ptr(), 2, B, 2 * H, 2 * W, C), load_operand(c.data_ptr(), 2, B, 2 * H, 2 * W, C)
+        assert rel(pg[0] + pg[1], pc[0] + pc[1]) < 1e-6
+    operand_close(g, c, parts, B, 2 * H, 2 * W, C)
 
 
 def test_time_embed():

@@ -151,3 +151,15 @@ def test_per_sample_generators_and_sampling_shape():
     b = ddpm.sample(batch_size=3, num_steps=2, progress=False, rng=rng, mode="ddim")
     assert a.shape == (3, 2, *res)
     assert rel_l2(a[0].cpu(), b[2].cpu()) < 1e-5      # per-sample trajectories are independent of batch position
+
+
+def test_unet_fused_gn_tail_equals_separate_launch(monkeypatch):
+    """B200_FUSE_GN=1 (conv + grid barrier + GroupNorm tail in one launch) gives the same forward as the default"""
+    res, nres, B = CASES["eunet_mini"]
+    x, t, y_ref = golden_inputs("eunet_mini")
+    m, _ = make_unet(res, nres)
+    y0 = m.cuda()(x.cuda(), t.cuda()).cpu()
+    monkeypatch.setenv("B200_FUSE_GN", "1")
+    m2, _ = make_unet(res, nres)
+    y1 = m2.cuda()(x.cuda(), t.cuda()).cpu()
+    assert rel_l2(y1, y0) < 1e-5 and rel_l2(y1, y_ref) < TOL

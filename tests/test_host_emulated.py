@@ -30,6 +30,16 @@ def test_plan_mini_matches_reference(emu, precision, tol):
     assert emu.calls.count("conv_tc") == 30
 
 
+def test_plan_mini_fused_gn_tail(emu, monkeypatch):
+    """B200_FUSE_GN=1: conv1 of the 8 ResidualBlocks carries the AdaGN + SiLU tail (b200_conv_tc_gn), same result"""
+    monkeypatch.setenv("B200_FUSE_GN", "1")
+    res, nres, B = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres)
+    x, t, y_ref = golden_inputs("eunet_mini")
+    assert rel_l2(m(x, t), y_ref) < 2e-5
+    assert emu.calls.count("conv_tc_gn") == 8 and emu.calls.count("conv_tc") == 22
+
+
 def test_plan_full_matches_reference(emu):
     res, nres, B = CASES["eunet_full"]
     m, _ = make_unet(res, nres)
