@@ -2,6 +2,8 @@
 // shared memory (never materialised in HBM, unlike the reference's [B*h, T, S] fp32 tensor).
 // replaces nn.MultiheadAttention's core (efficient_unet.py:39-53) and QKVAttentionLegacy
 // (layout_unet_v1.py:488-505).  fp32 CUDA-core math; output fp16 (operand of the out-projection GEMM).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -462,8 +464,260 @@ __global__ void __launch_bounds__(FA_THREADS) flash_attn_kernel(const FAParams p
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core version of the same contract (the one the plans launch).  64 queries x 64 keys per step, 4 warps, one
+// warp = 16 query rows.  S = Q K^T and O += P V run on mma.sync.m16n8k16 (fp16 operands, fp32 accumulators in
+// registers) with the error-compensated split used by the convs: x = x_hi + x_lo (both fp16), three MMAs per product
+// (hi*hi + lo*hi + hi*lo), so logits and outputs keep ~2^-22 relative accuracy -- a single fp16 pass would put 1e-2
+// absolute error on logits of magnitude ~10.  P never leaves registers: the accumulator fragment of two adjacent
+// 8-key tiles IS the A fragment of the next k-step of P V.  K is staged [key][d] and V transposed [dv][key] (both
+// hi | lo planes, rows padded by 8 halves -> conflict-free 32-bit fragment loads).  Softmax runs in the exp2 domain
+// (scale * log2 e folded into Q before the split).  (A tcgen05/TMEM version would need the FA4 correction pipeline;
+// at T <= 2048 and d <= 64 the step is 6-15% attention, so the register-level path was chosen.)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FM_BQ = 64, FM_BK = 64, FM_THREADS = 128;
+
+__device__ __forceinline__ void mma_f16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) -> fp16 pair hi and the fp16 pair of the residuals
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int DQ, int DV>
+__global__ void __launch_bounds__(FM_THREADS) flash_attn_mma_kernel(const FAParams p) {
+    constexpr int KP = DQ + 8, VP = FM_BK + 8;
+    extern __shared__ __align__(16) unsigned char fm_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
+    __half* sKh = reinterpret_cast<__half*>(fm_smem);   // [FM_BK][KP]
+    __half* sKl = sKh + FM_BK * KP;
+    __half* sVh = sKl + FM_BK * KP;                      // [DV][VP]  (transposed: value dim major, key minor)
+    __half* sVl = sVh + DV * VP;
+    const int q0 = blockIdx.x * FM_BQ, head = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const float qscale = p.scale * 1.4426950408889634f;
+
+    // ---- this warp's 16 query rows as A fragments (hi | lo), scaled ----
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    auto qpair = [&](int row, int c, uint32_t& hi, uint32_t& lo) {   // elements (row, c) and (row, c + 1)
+        float2 v = make_float2(0.f, 0.f);
+        if (row < p.T) {
+            const size_t tok = (size_t)b * p.T + row;
+            v = c < p.d1 ? *reinterpret_cast<const float2*>(p.q1 + tok * p.ldq1 + head * p.d1 + c)
+                         : *reinterpret_cast<const float2*>(p.q2 + tok * p.ldq2 + head * p.d2 + (c - p.d1));
+        }
+        split_h2(v.x * qscale, v.y * qscale, hi, lo);
+    };
+    uint32_t qh[DQ / 16][4], ql[DQ / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < DQ / 16; ++ks) {
+        const int c = ks * 16 + 2 * t;
+        qpair(r0, c, qh[ks][0], ql[ks][0]);
+        qpair(r1, c, qh[ks][1], ql[ks][1]);
+        qpair(r0, c + 8, qh[ks][2], ql[ks][2]);
+        qpair(r1, c + 8, qh[ks][3], ql[ks][3]);
+    }
+    float o[DV / 8][4];
+#pragma unroll
+    for (int n = 0; n < DV / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;    // rows g and g + 8 (l: this thread's partial sums)
+
+    const int S = p.T + p.Tx;
+    const int ntiles = (S + FM_BK - 1) / FM_BK;
+    // K / V tiles travel global -> registers (requested one tile ahead, in flight during the MMAs of the current tile)
+    // -> fp16 hi | lo split -> shared memory
+    constexpr int KN = FM_BK * (DQ / 4) / FM_THREADS, VN = FM_BK * (DV / 4) / FM_THREADS;
+    float4 kreg[KN], vreg[VN];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < KN; ++u) {
+            const int i = tid + u * FM_THREADS;
+            const int kj = i / (DQ / 4), c4 = (i - kj * (DQ / 4)) * 4;
+            const int tk = k0 + kj;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (tk < p.T) {
+                const size_t tok = (size_t)b * p.T + tk;
+                v = c4 < p.d1 ? *reinterpret_cast<const float4*>(p.k1 + tok * p.ldk1 + head * p.d1 + c4)
+                              : *reinterpret_cast<const float4*>(p.k2 + tok * p.ldk2 + head * p.d2 + (c4 - p.d1));
+            } else if (tk < S) {
+                const size_t tok = (size_t)b * p.Tx + (tk - p.T);
+                v = c4 < p.d1 ? *reinterpret_cast<const float4*>(p.xk1 + tok * p.ldx + head * p.d1 + c4)
+                              : *reinterpret_cast<const float4*>(p.xk2 + tok * p.ldx + head * p.d2 + (c4 - p.d1));
+            }
+            kreg[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < VN; ++u) {
+            const int i = tid + u * FM_THREADS;
+            const int kj = i % FM_BK, c4 = (i / FM_BK) * 4;            // consecutive threads -> consecutive keys
+            const int tk = k0 + kj;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (tk < p.T) v = *reinterpret_cast<const float4*>(p.v + ((size_t)b * p.T + tk) * p.ldv + head * DV + c4);
+            else if (tk < S) v = *reinterpret_cast<const float4*>(p.xv + ((size_t)b * p.Tx + (tk - p.T)) * p.ldx + head * DV + c4);
+            vreg[u] = v;
+        }
+    };
+    load_tile(0);
+    for (int kt = 0; kt < ntiles; ++kt) {
+        const int k0 = kt * FM_BK;
+        __syncthreads();       // previous tile fully consumed
+        // ---- registers -> K [key][d] and V^T [dv][key], split into fp16 hi | lo ----
+#pragma unroll
+        for (int u = 0; u < KN; ++u) {
+            const int i = tid + u * FM_THREADS;
+            const int kj = i / (DQ / 4), c4 = (i - kj * (DQ / 4)) * 4;
+            uint2 hi, lo;
+            split_h2(kreg[u].x, kreg[u].y, hi.x, lo.x);
+            split_h2(kreg[u].z, kreg[u].w, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(sKh + kj * KP + c4) = hi;
+            *reinterpret_cast<uint2*>(sKl + kj * KP + c4) = lo;
+        }
+#pragma unroll
+        for (int u = 0; u < VN; ++u) {
+            const int i = tid + u * FM_THREADS;
+            const int kj = i % FM_BK, c4 = (i / FM_BK) * 4;
+            const float vv[4] = {vreg[u].x, vreg[u].y, vreg[u].z, vreg[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half hi = __float2half_rn(vv[e]);
+                sVh[(c4 + e) * VP + kj] = hi;
+                sVl[(c4 + e) * VP + kj] = __float2half_rn(vv[e] - __half2float(hi));
+            }
+        }
+        __syncthreads();
+        if (kt + 1 < ntiles) load_tile(k0 + FM_BK);
+        // ---- S = Q K^T: 8 key tiles of 8, fp32 accumulators ----
+        // (loop order: consecutive MMAs always target DIFFERENT accumulators -- the three split terms of one accumulator
+        //  are 4 instructions apart -- because back-to-back dependent HMMAs stall for the full pipeline latency)
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < DQ / 16; ++ks) {
+#pragma unroll
+            for (int j0 = 0; j0 < 8; j0 += 4) {
+                uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const __half* kh = sKh + ((j0 + jj) * 8 + g) * KP + 2 * t + ks * 16;
+                    const __half* kl = sKl + ((j0 + jj) * 8 + g) * KP + 2 * t + ks * 16;
+                    bh[jj][0] = *reinterpret_cast<const uint32_t*>(kh);
+                    bh[jj][1] = *reinterpret_cast<const uint32_t*>(kh + 8);
+                    bl[jj][0] = *reinterpret_cast<const uint32_t*>(kl);
+                    bl[jj][1] = *reinterpret_cast<const uint32_t*>(kl + 8);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_f16_16816(s[j0 + jj], qh[ks], bh[jj][0], bh[jj][1]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_f16_16816(s[j0 + jj], ql[ks], bh[jj][0], bh[jj][1]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_f16_16816(s[j0 + jj], qh[ks], bl[jj][0], bl[jj][1]);
+            }
+        }
+        if (k0 + FM_BK > S) {      // mask keys past the end (last tile only)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kc = k0 + j * 8 + 2 * t;
+                if (kc >= S) s[j][0] = s[j][2] = -INFINITY;
+                if (kc + 1 >= S) s[j][1] = s[j][3] = -INFINITY;
+            }
+        }
+        // ---- online softmax (exp2 domain); a row lives in the 4 lanes of a quad ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);     // exp2(-inf) = 0 on the first tile
+        m0 = mn0; m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
+            s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
+            rs0 += s[j][0] + s[j][1];
+            rs1 += s[j][2] + s[j][3];
+        }
+        l0 = l0 * al0 + rs0;
+        l1 = l1 * al1 + rs1;
+#pragma unroll
+        for (int n = 0; n < DV / 8; ++n) { o[n][0] *= al0; o[n][1] *= al0; o[n][2] *= al1; o[n][3] *= al1; }
+        // ---- O += P V: the S fragments of key tiles (2kk, 2kk+1) are the A fragment of k-step kk ----
+#pragma unroll
+        for (int kk = 0; kk < FM_BK / 16; ++kk) {
+            uint32_t ph[4], pl[4];
+            split_h2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+            split_h2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+            split_h2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+            split_h2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int n0 = 0; n0 < DV / 8; n0 += 4) {
+                uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) {
+                    const __half* vh = sVh + ((n0 + nn) * 8 + g) * VP + kk * 16 + 2 * t;
+                    const __half* vl = sVl + ((n0 + nn) * 8 + g) * VP + kk * 16 + 2 * t;
+                    bh[nn][0] = *reinterpret_cast<const uint32_t*>(vh);
+                    bh[nn][1] = *reinterpret_cast<const uint32_t*>(vh + 8);
+                    bl[nn][0] = *reinterpret_cast<const uint32_t*>(vl);
+                    bl[nn][1] = *reinterpret_cast<const uint32_t*>(vl + 8);
+                }
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) mma_f16_16816(o[n0 + nn], ph, bh[nn][0], bh[nn][1]);
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) mma_f16_16816(o[n0 + nn], pl, bh[nn][0], bh[nn][1]);
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) mma_f16_16816(o[n0 + nn], ph, bl[nn][0], bl[nn][1]);
+            }
+        }
+    }
+    // ---- normalise and store (conv operand layout, common.cuh) ----
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+        const int tq = hrow ? r1 : r0;
+        if (tq >= p.T) continue;
+        const float inv = hrow ? inv1 : inv0;
+        const int hh = tq / p.Wimg, ww = tq - hh * p.Wimg;
+#pragma unroll
+        for (int n = 0; n < DV / 8; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                store_operand_elem(p.out, p.lo_off, p.parts, (size_t)b * (p.T / p.Wimg) + hh, p.C, p.Wimg, ww,
+                                   head * DV + n * 8 + 2 * t + e, o[n][2 * hrow + e] * inv);
+    }
+}
+
 template <int DQ, int DV>
 static int launch_fa(const FAParams& p, int B, int heads, cudaStream_t st) {
+    static int ffma = -1;       // B200_FA_FFMA=1: the CUDA-core kernel above (A/B timing, cross-check)
+    if (ffma < 0) {
+        const char* e = getenv("B200_FA_FFMA");
+        ffma = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!ffma) {
+        const size_t smem = ((size_t)2 * FM_BK * (DQ + 8) + (size_t)2 * DV * (FM_BK + 8)) * sizeof(__half);
+        dim3 grid(cdiv(p.T, FM_BQ), heads, B);
+        launch_pdl(flash_attn_mma_kernel<DQ, DV>, grid, dim3(FM_THREADS), smem, st, p);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     const size_t smem = ((size_t)2 * DQ * FA_PAD + FA_BK * DV + FA_BK * FA_PAD) * sizeof(float);
     static bool attr = false;
     if (!attr && smem > 48 * 1024) {

@@ -19,6 +19,10 @@ timeout 600 python bench.py --steps 20 --warmup 3 --precision fp16f8 --profile-o
 echo "bench fp16f8 rc=$?"
 cat gpurun_out/bench_fp16f8.json | head -c 400
 timeout 300 python tools/bench_layout.py 4 > gpurun_out/bench_layout.json 2> gpurun_out/bench_layout.err
+if [ "${ATTN:-0}" = "1" ]; then
+  (B200_FA_FFMA=1 python tools/gpu_bench_attn.py; python tools/gpu_bench_attn.py) > gpurun_out/attn_bench.txt 2>&1
+  cat gpurun_out/attn_bench.txt
+fi
 if [ "${SPLIT:-0}" = "1" ]; then
   timeout 600 python tools/exp_split.py fp16f8 8 > gpurun_out/exp_split.txt 2>&1
   cat gpurun_out/exp_split.txt | tail -4
