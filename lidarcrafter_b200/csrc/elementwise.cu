@@ -253,14 +253,19 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const float* __restrict_
     }
 }
 
-// decomposition for large tensors: one block = up to 256 consecutive pixels x all channels
+// decomposition for large tensors: one block = 2^k (<= 256, <= W) consecutive pixels of ONE image row x all channels.
+// ncu on B200 showed the first version of this kernel ISSUE-bound (smsp issue active 68 %, ~500 instructions per
+// 8-element item, most of them 64-bit address arithmetic and an integer division per item), not memory-bound: here
+// everything that can be per-block is (row, base pointers), per-item offsets are 32-bit shifts / multiplies, and
+// `parts` / the raw second output are template parameters.
+template <int PARTS, bool RAW>
 __global__ void __launch_bounds__(256) gn_act_kernel_v1(const float* __restrict__ x0, int C0, const float* __restrict__ x1,
-                                                     int C1, const double* __restrict__ st0,
-                                                     const double* __restrict__ st1, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, const float* __restrict__ ada,
-                                                     int ada_stride, int groups, float eps, int silu,
-                                                     __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
-                                                     int parts, int HW, int W, int pix_per_block) {
+                                                        int C1, const double* __restrict__ st0,
+                                                        const double* __restrict__ st1, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ ada,
+                                                        int ada_stride, int groups, float eps, int silu,
+                                                        __half* __restrict__ y, __half* __restrict__ y_raw, size_t lo_off,
+                                                        int HW, int W, int ppb_log2) {
     // dynamic shared memory sized by the channel count (24 B / channel): keeps 8 blocks resident per SM
     extern __shared__ __align__(16) unsigned char gn_smem[];
     pdl_launch_dependents();
@@ -277,18 +282,24 @@ __global__ void __launch_bounds__(256) gn_act_kernel_v1(const float* __restrict_
         for (int c = threadIdx.x; c < C; c += blockDim.x) { s_a[c] = 1.f; s_b[c] = 0.f; }
     }
     __syncthreads();
-    const int c8n = C / 8;
-    const int p0 = blockIdx.x * pix_per_block;
-    const int np = min(pix_per_block, HW - p0);
-    // One warp item = 8 consecutive pixels x 32 consecutive channels: lane -> (pixel lane/4, 8-channel group lane%4).
-    // Reads: each pixel's 32 channels are one 128-byte line; writes: for each of the 4 channel groups the 8 pixels
-    // are 128 contiguous bytes of the tile-major operand -> both directions move whole lines.
+    const int c8n = C / 8, WT = W >> 7, Himg = HW / W;
+    const int p0 = blockIdx.x << ppb_log2;                  // the block lies inside one image row (W % ppb == 0)
+    const int hh = p0 / W, w_start = p0 - hh * W;
+    const int pbn_log2 = ppb_log2 - 3, pb_mask = (1 << pbn_log2) - 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int px = lane >> 2, g = lane & 3;
-    const int cb_n = (C + 31) / 32, pb_n = np / 8;      // np is a multiple of 8 (W % 8 == 0)
-    const int Himg = HW / W, WT = W / OTW;
-    const int n_items = pb_n * cb_n;
-    // two items per iteration: all four 16-byte loads are issued before any math (memory-level parallelism)
+    const int cb_n = (C + 31) / 32;
+    const int n_items = cb_n << pbn_log2;
+    // per-block 64-bit bases; everything per item below is 32-bit
+    const float* x0b = x0 + ((size_t)b * HW + p0) * C0;
+    const float* x1b = C1 ? x1 + ((size_t)b * HW + p0) * C1 : nullptr;
+    const size_t row_off = ((size_t)b * Himg + hh) * WT * c8n * (OPX * 8);
+    __half* yb = y + row_off;
+    __half* yrb = RAW ? y_raw + row_off : nullptr;
+    // One warp item = 8 consecutive pixels x 32 consecutive channels: lane -> (pixel lane/4, 8-channel group lane%4).
+    // Reads: each pixel's 32 channels are one 128-byte line; writes: for each of the 4 channel groups the 8 pixels
+    // are 128 contiguous bytes of the tile-major operand.  Two items per iteration: all four 16-byte loads are
+    // issued before any math (memory-level parallelism).
     for (int it0 = warp; it0 < n_items; it0 += 2 * nwarps) {
         float4 ld[2][2];
         int c8s[2], pls[2];
@@ -296,56 +307,58 @@ __global__ void __launch_bounds__(256) gn_act_kernel_v1(const float* __restrict_
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int it = it0 + u * nwarps;
-            const int cb = it / pb_n, pb = it - cb * pb_n;
-            c8s[u] = cb * 4 + g;
-            pls[u] = p0 + pb * 8 + px;
+            c8s[u] = (it >> pbn_log2) * 4 + g;
+            pls[u] = ((it & pb_mask) << 3) + px;
             ok[u] = it < n_items && c8s[u] < c8n;
             if (ok[u]) {
                 const int c = c8s[u] * 8;
-                const size_t pix = (size_t)b * HW + pls[u];
-                const float* src = c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
+                const float* src = c < C0 ? x0b + pls[u] * C0 + c : x1b + pls[u] * C1 + (c - C0);
                 ld[u][0] = *reinterpret_cast<const float4*>(src);
                 ld[u][1] = *reinterpret_cast<const float4*>(src + 4);
             }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (!ok[u]) continue;
-            const int c8 = c8s[u], c = c8 * 8, pl = pls[u];
+            if (!ok[u]) continue;     // warp-uniform for C % 32 == 0 (required by parts == 3: shuffles below)
+            const int c8 = c8s[u], c = c8 * 8;
+            const int ww = w_start + pls[u], wt = ww >> 7, tp = ww & (OTW - 1);
+            const int oi = ((wt * c8n + c8) * OPX + tp + 1) * 8;
+            int oi2 = -1;                                         // halo duplicate in the neighbouring tile
+            if (tp == 0) oi2 = (((wt == 0 ? WT - 1 : wt - 1) * c8n + c8) * OPX + OPX - 1) * 8;
+            else if (tp == OTW - 1) oi2 = (((wt == WT - 1 ? 0 : wt + 1) * c8n + c8) * OPX) * 8;
             float v[8] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w};
             __half2 h[4];
-            const int hh = pl / W, ww = pl - hh * W;
-            const OperandPos op = operand_pos(ww, WT);
-            const size_t bh = (size_t)b * Himg + hh;
-            const size_t oi = operand_unit(bh, WT, c8n, op.wt, c8, op.pos) * 8;
-            const size_t oi2 = op.wt2 >= 0 ? operand_unit(bh, WT, c8n, op.wt2, c8, op.pos2) * 8 : 0;   // halo duplicate
-            if (y_raw) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
+            if (RAW) {   // second output: the un-normalised input as a conv operand (1x1 skip conv of the same block)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                 const uint4 hv = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(y_raw + oi) = hv;
-                if (op.wt2 >= 0) *reinterpret_cast<uint4*>(y_raw + oi2) = hv;
-                if (parts >= 2) {
-                    const uint4 pv = plane1_value(v, h, parts, lane);
-                    *reinterpret_cast<uint4*>(y_raw + lo_off + oi) = pv;
-                    if (op.wt2 >= 0) *reinterpret_cast<uint4*>(y_raw + lo_off + oi2) = pv;
+                *reinterpret_cast<uint4*>(yrb + oi) = hv;
+                if (oi2 >= 0) *reinterpret_cast<uint4*>(yrb + oi2) = hv;
+                if (PARTS >= 2) {
+                    const uint4 pv = plane1_value(v, h, PARTS, lane);
+                    *reinterpret_cast<uint4*>(yrb + lo_off + oi) = pv;
+                    if (oi2 >= 0) *reinterpret_cast<uint4*>(yrb + lo_off + oi2) = pv;
                 }
             }
+            const float4 a0 = *reinterpret_cast<const float4*>(s_a + c), a1 = *reinterpret_cast<const float4*>(s_a + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_b + c), b1 = *reinterpret_cast<const float4*>(s_b + c + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float t = fmaf(v[e], s_a[c + e], s_b[c + e]);
+                float t = fmaf(v[e], av[e], bv[e]);
                 if (silu) t = silu_f(t);
                 v[e] = t;
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
             const uint4 hv = *reinterpret_cast<const uint4*>(h);
-            *reinterpret_cast<uint4*>(y + oi) = hv;
-            if (op.wt2 >= 0) *reinterpret_cast<uint4*>(y + oi2) = hv;
-            if (parts >= 2) {   // parts 2: lo = fp16(x - fp32(hi)); parts 3: e4m3 pair plane
-                const uint4 pv = plane1_value(v, h, parts, lane);
-                *reinterpret_cast<uint4*>(y + lo_off + oi) = pv;
-                if (op.wt2 >= 0) *reinterpret_cast<uint4*>(y + lo_off + oi2) = pv;
+            *reinterpret_cast<uint4*>(yb + oi) = hv;
+            if (oi2 >= 0) *reinterpret_cast<uint4*>(yb + oi2) = hv;
+            if (PARTS >= 2) {   // parts 2: lo = fp16(x - fp32(hi)); parts 3: e4m3 pair plane
+                const uint4 pv = plane1_value(v, h, PARTS, lane);
+                *reinterpret_cast<uint4*>(yb + lo_off + oi) = pv;
+                if (oi2 >= 0) *reinterpret_cast<uint4*>(yb + lo_off + oi2) = pv;
             }
         }
     }
@@ -545,6 +558,11 @@ __global__ void __launch_bounds__(256) fir_up_operand_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------------------
 // time embedding MLP + stacked (scale, shift) projections
 // ---------------------------------------------------------------------------------------------------------
+// grid (B, E / TEMB_EO): every block recomputes the small first layer (all loads of a thread are independent and
+// issued together) and produces TEMB_EO outputs of the second layer, one warp per 4 outputs with all row loads in
+// flight before the reductions.  (The first version -- one block per sample, outputs looped serially -- took 38 us
+// of pure dependent L2 latency on B200.)
+constexpr int TEMB_EO = 32;
 __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, const float* __restrict__ w1,
                                                    const float* __restrict__ b1, const float* __restrict__ w2,
                                                    const float* __restrict__ b2, const float* __restrict__ add,
@@ -554,7 +572,7 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
     pdl_wait();
     float* e0 = sm;        // [Cs]
     float* h1 = sm + Cs;   // [E]
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, o0 = blockIdx.y * TEMB_EO;
     const float tv = t[b];
     const int half = Cs / 2;
     for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -567,21 +585,44 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
     for (int o = threadIdx.x; o < E; o += blockDim.x) {
         float acc = b1[o];
         const float* wr = w1 + (size_t)o * Cs;
-        for (int k = 0; k < Cs; ++k) acc = fmaf(wr[k], e0[k], acc);
+        if (Cs % 16 == 0) {
+            for (int k0 = 0; k0 < Cs; k0 += 16) {
+                float4 wv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) wv[u] = ld4(wr + k0 + 4 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc = fmaf(wv[u].x, e0[k0 + 4 * u], acc); acc = fmaf(wv[u].y, e0[k0 + 4 * u + 1], acc);
+                    acc = fmaf(wv[u].z, e0[k0 + 4 * u + 2], acc); acc = fmaf(wv[u].w, e0[k0 + 4 * u + 3], acc);
+                }
+            }
+        } else {
+            for (int k = 0; k < Cs; ++k) acc = fmaf(wr[k], e0[k], acc);
+        }
         h1[o] = silu_f(acc);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int o = warp; o < E; o += nw) {
-        const float* wr = w2 + (size_t)o * E;
-        float acc = 0.f;
-        for (int k = lane; k < E; k += 32) acc = fmaf(wr[k], h1[k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) temb[(size_t)b * E + o] = acc + b2[o] + (add ? add[(size_t)b * E + o] : 0.f);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int OPW = TEMB_EO / 8;                    // outputs per warp
+    float acc[OPW];
+#pragma unroll
+    for (int u = 0; u < OPW; ++u) {
+        const int o = o0 + warp * OPW + u;
+        acc[u] = 0.f;
+        if (o < E) {
+            const float* wr = w2 + (size_t)o * E;
+            for (int k = lane; k < E; k += 32) acc[u] = fmaf(wr[k], h1[k], acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < OPW; ++u) {
+        const int o = o0 + warp * OPW + u;
+        const float v = warp_sum(acc[u]);
+        if (lane == 0 && o < E) temb[(size_t)b * E + o] = v + b2[o] + (add ? add[(size_t)b * E + o] : 0.f);
     }
 }
 
-constexpr int ADA_ROWS_PER_BLOCK = 32;
+constexpr int ADA_ROWS_PER_BLOCK = 8;    // one projection row per warp: 960 blocks for P = 7680, one memory round trip
 constexpr int ADA_MAX_B = 16;
 
 __global__ void __launch_bounds__(256) ada_proj_kernel(const float* __restrict__ temb, const float* __restrict__ wp,
@@ -590,28 +631,42 @@ __global__ void __launch_bounds__(256) ada_proj_kernel(const float* __restrict__
     extern __shared__ float sm[];  // silu(temb) [B][E]
     pdl_launch_dependents();
     pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * ADA_ROWS_PER_BLOCK + warp;
+    // this warp's weight row is requested before the activations are staged (independent of them)
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = (row < P && lane + 32 * u < E) ? wp[(size_t)row * E + lane + 32 * u] : 0.f;
     for (int i = threadIdx.x; i < B * E; i += blockDim.x) sm[i] = silu_f(temb[i]);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int rr = warp; rr < ADA_ROWS_PER_BLOCK; rr += 8) {
-        const int row = blockIdx.x * ADA_ROWS_PER_BLOCK + rr;
-        if (row >= P) break;
-        const float* wr = wp + (size_t)row * E;
-        float acc[ADA_MAX_B];
+    if (row >= P) return;
+    float acc[ADA_MAX_B];
 #pragma unroll
-        for (int b = 0; b < ADA_MAX_B; ++b) acc[b] = 0.f;
+    for (int b = 0; b < ADA_MAX_B; ++b) acc[b] = 0.f;
+    if (E <= 256) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = lane + 32 * u;
+            if (k < E) {
+#pragma unroll
+                for (int b = 0; b < ADA_MAX_B; ++b)
+                    if (b < B) acc[b] = fmaf(wv[u], sm[b * E + k], acc[b]);
+            }
+        }
+    } else {
+        const float* wr = wp + (size_t)row * E;
         for (int k = lane; k < E; k += 32) {
-            const float wv = wr[k];
+            const float w = wr[k];
 #pragma unroll
             for (int b = 0; b < ADA_MAX_B; ++b)
-                if (b < B) acc[b] = fmaf(wv, sm[b * E + k], acc[b]);
+                if (b < B) acc[b] = fmaf(w, sm[b * E + k], acc[b]);
         }
+    }
 #pragma unroll
-        for (int b = 0; b < ADA_MAX_B; ++b) {
-            if (b < B) {
-                const float v = warp_sum(acc[b]);
-                if (lane == 0) ada[(size_t)b * P + row] = v + bp[row];
-            }
+    for (int b = 0; b < ADA_MAX_B; ++b) {
+        if (b < B) {
+            const float v = warp_sum(acc[b]);
+            if (lane == 0) ada[(size_t)b * P + row] = v + bp[row];
         }
     }
 }
@@ -694,22 +749,40 @@ __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restri
         sx[i] = ok ? x[((size_t)b * Cx + ci) * HW + (size_t)gh * W + gw] : 0.f;
     }
     __syncthreads();
+    // thread = 4 output channels x (128 / pstep) pixels px = poff + i * pstep: every weight float4 read from shared
+    // memory feeds all of the thread's pixels (one-pixel-at-a-time was LDS-bound: ncu l1tex 69 %, 75 us on B200)
     const int c4n = Cout / 4;
     const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-    for (int px = poff; px < IC_PIX; px += pstep) {
-        const size_t pp = (size_t)h * W + w0 + px;
-        float4 acc = ld4(cst + ((size_t)(cst_batched ? b : 0) * HW + pp) * Cout + c4 * 4);
+    constexpr int PB = 8;                              // pixels per register batch
+    for (int pb = poff; pb < IC_PIX; pb += PB * pstep) {
+        float4 acc[PB];
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            const int px = pb + i * pstep;
+            acc[i] = px < IC_PIX ? ld4(cst + ((size_t)(cst_batched ? b : 0) * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4)
+                                 : make_float4(0, 0, 0, 0);
+        }
         for (int ci = 0; ci < Cx; ++ci) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const float xv = sx[(ci * 3 + tap / 3) * (IC_PIX + 2) + px + tap % 3];
-                fma4(acc, xv, *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4));
+                const float4 wv = *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4);
+                const float* xr = sx + (ci * 3 + tap / 3) * (IC_PIX + 2) + tap % 3;
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    const int px = pb + i * pstep;
+                    if (px < IC_PIX) fma4(acc[i], xr[px], wv);
+                }
             }
         }
-        *reinterpret_cast<float4*>(out + ((size_t)b * HW + pp) * Cout + c4 * 4) = acc;
-        s1.x += acc.x; s1.y += acc.y; s1.z += acc.z; s1.w += acc.w;
-        s2.x += acc.x * acc.x; s2.y += acc.y * acc.y; s2.z += acc.z * acc.z; s2.w += acc.w * acc.w;
+#pragma unroll
+        for (int i = 0; i < PB; ++i) {
+            const int px = pb + i * pstep;
+            if (px >= IC_PIX) continue;
+            *reinterpret_cast<float4*>(out + ((size_t)b * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4) = acc[i];
+            s1.x += acc[i].x; s1.y += acc[i].y; s1.z += acc[i].z; s1.w += acc[i].w;
+            s2.x += acc[i].x * acc[i].x; s2.y += acc[i].y * acc[i].y; s2.z += acc[i].z * acc[i].z; s2.w += acc[i].w * acc[i].w;
+        }
     }
     if (stats) block_channel_reduce(s1, s2, Cout, b, stats, red);
 }
@@ -804,7 +877,7 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const TIn* __restrict__ a
 // 256-byte pixel rows costs 32 L1 line look-ups per load instruction and ran at 0.1 ms on B200).  Stage 1: thread =
 // one staged pixel, reduces its channels to the 3 x Cout partial sums of the filter row it feeds; stage 2 adds the 9
 // partial sums of each output pixel.
-constexpr int OC_PIX = 128, OC_THREADS = 416, OC_CH = 16, OC_PITCH = 20;   // 3 * 130 = 390 staged pixels <= 416 threads
+constexpr int OC_PIX = 128, OC_THREADS = 96, OC_CH = 16, OC_PITCH = 20, OC_PPL = 5;   // warp = staged row, lane = 5 pixels
 
 __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ pred,
@@ -822,11 +895,15 @@ __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* 
     const int wt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int w0 = wt * OC_PIX;
     constexpr int NPX = OC_PIX + 2;
-    const int item = threadIdx.x;                      // staged pixel (r, j) of this thread
-    const int ir = item / NPX, ij = item - ir * NPX;
-    float acc[12];
+    // Stage 1: warp r owns staged row r, lane l owns pixels l, l + 32, ... (consecutive lanes -> consecutive pixels:
+    // conflict-free 16-byte reads at the 20-word pitch).  Every weight float4 read from shared memory feeds 5 pixels:
+    // the one-pixel-per-thread version was bound by those LDS.128 (ncu: l1tex 71 %, 101 us on B200).
+    const int ir = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[OC_PPL][12];
 #pragma unroll
-    for (int q = 0; q < 12; ++q) acc[q] = 0.f;
+    for (int i = 0; i < OC_PPL; ++i)
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc[i][q] = 0.f;
     for (int c0 = 0; c0 < Cin; c0 += OC_CH) {
         __syncthreads();                               // previous chunk consumed (and, first time, sw complete)
         for (int i = threadIdx.x; i < 3 * NPX * (OC_CH / 4); i += OC_THREADS) {
@@ -841,33 +918,43 @@ __global__ void __launch_bounds__(OC_THREADS) out_conv_rows_kernel(const float* 
             *reinterpret_cast<float4*>(sx + (size_t)pj * OC_PITCH + 4 * f) = v;
         }
         __syncthreads();
-        if (item < 3 * NPX) {
-            const float* xp = sx + (size_t)item * OC_PITCH;
-            const float* wr = sw + ((size_t)ir * Cin + c0) * 12;
+        const float* wr = sw + ((size_t)ir * Cin + c0) * 12;
 #pragma unroll
-            for (int f = 0; f < OC_CH / 4; ++f) {
-                const float4 v = *reinterpret_cast<const float4*>(xp + 4 * f);
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int f = 0; f < OC_CH / 4; ++f) {
+            float4 xv[OC_PPL];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 w0v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12);
-                    const float4 w1v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 4);
-                    const float4 w2v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 8);
-                    acc[0] = fmaf(vv[e], w0v.x, acc[0]); acc[1] = fmaf(vv[e], w0v.y, acc[1]);
-                    acc[2] = fmaf(vv[e], w0v.z, acc[2]); acc[3] = fmaf(vv[e], w0v.w, acc[3]);
-                    acc[4] = fmaf(vv[e], w1v.x, acc[4]); acc[5] = fmaf(vv[e], w1v.y, acc[5]);
-                    acc[6] = fmaf(vv[e], w1v.z, acc[6]); acc[7] = fmaf(vv[e], w1v.w, acc[7]);
-                    acc[8] = fmaf(vv[e], w2v.x, acc[8]); acc[9] = fmaf(vv[e], w2v.y, acc[9]);
-                    acc[10] = fmaf(vv[e], w2v.z, acc[10]); acc[11] = fmaf(vv[e], w2v.w, acc[11]);
+            for (int i = 0; i < OC_PPL; ++i) {
+                const int j = lane + 32 * i;
+                xv[i] = j < NPX ? *reinterpret_cast<const float4*>(sx + (size_t)(ir * NPX + j) * OC_PITCH + 4 * f)
+                                : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 w0v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12);
+                const float4 w1v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 4);
+                const float4 w2v = *reinterpret_cast<const float4*>(wr + (4 * f + e) * 12 + 8);
+#pragma unroll
+                for (int i = 0; i < OC_PPL; ++i) {
+                    const float x = e == 0 ? xv[i].x : e == 1 ? xv[i].y : e == 2 ? xv[i].z : xv[i].w;
+                    acc[i][0] = fmaf(x, w0v.x, acc[i][0]); acc[i][1] = fmaf(x, w0v.y, acc[i][1]);
+                    acc[i][2] = fmaf(x, w0v.z, acc[i][2]); acc[i][3] = fmaf(x, w0v.w, acc[i][3]);
+                    acc[i][4] = fmaf(x, w1v.x, acc[i][4]); acc[i][5] = fmaf(x, w1v.y, acc[i][5]);
+                    acc[i][6] = fmaf(x, w1v.z, acc[i][6]); acc[i][7] = fmaf(x, w1v.w, acc[i][7]);
+                    acc[i][8] = fmaf(x, w2v.x, acc[i][8]); acc[i][9] = fmaf(x, w2v.y, acc[i][9]);
+                    acc[i][10] = fmaf(x, w2v.z, acc[i][10]); acc[i][11] = fmaf(x, w2v.w, acc[i][11]);
                 }
             }
         }
     }
     __syncthreads();                                   // all chunk reads done: reuse sx for the partial sums
     float* st = sx;                                    // [3 rows][130 px][12]
-    if (item < 3 * NPX) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) st[(size_t)item * 12 + q] = acc[q];
+    for (int i = 0; i < OC_PPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NPX) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) st[(size_t)(ir * NPX + j) * 12 + q] = acc[i][q];
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < OC_PIX * Cout; i += OC_THREADS) {
@@ -974,12 +1061,20 @@ extern "C" int b200_gn_act_f16(const float* x0, int C0, const float* x1, int C1,
     const int variant = forced >= 0 ? forced : ((long long)H * W * B > 8192 ? 1 : 0);
     if (variant == 1) {
         const int HW = H * W;
-        int ppb = 256;
-        while (ppb > 32 && (long long)cdiv(HW, ppb) * B < 2 * 148) ppb >>= 1;
-        dim3 grid(cdiv(HW, ppb), B);
-        launch_pdl(gn_act_kernel_v1, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0, stats1,
-                   gamma, beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw,
-                   (size_t)B * H * (W / OTW) * ((C0 + C1) / 8) * OPX * 8, parts, HW, W, ppb);
+        int ppb_log2 = 8;                                    // 256 pixels per block, never more than one image row
+        while ((1 << ppb_log2) > W) --ppb_log2;
+        while (ppb_log2 > 5 && (long long)(HW >> ppb_log2) * B < 2 * 148) --ppb_log2;
+        dim3 grid(HW >> ppb_log2, B);
+        const size_t plane = (size_t)B * H * (W / OTW) * ((C0 + C1) / 8) * OPX * 8;
+#define B200_GN_V1(P_, R_)                                                                                              \
+    launch_pdl(gn_act_kernel_v1<P_, R_>, grid, dim3(256), (size_t)24 * C, (cudaStream_t)stream, x0, C0, x1, C1, stats0,    \
+               stats1, gamma, beta, ada, ada_stride, groups, eps, silu, (__half*)y, (__half*)y_raw, plane, HW, W, ppb_log2)
+        if (y_raw) {
+            if (parts == 1) B200_GN_V1(1, true); else if (parts == 2) B200_GN_V1(2, true); else B200_GN_V1(3, true);
+        } else {
+            if (parts == 1) B200_GN_V1(1, false); else if (parts == 2) B200_GN_V1(2, false); else B200_GN_V1(3, false);
+        }
+#undef B200_GN_V1
         B200_CHECK_LAUNCH();
         return B200_OK;
     }
@@ -1055,8 +1150,8 @@ extern "C" int b200_time_embed(const float* t, const float* w1, const float* b1,
                                int Cs, int E, int P, void* stream) {
     B200_CHECK_ARG(t && w1 && b1 && w2 && b2 && temb);
     B200_CHECK_ARG(B > 0 && B <= ADA_MAX_B && Cs % 2 == 0 && Cs >= 4);
-    launch_pdl(temb_kernel, dim3(B), dim3(256), (Cs + E) * sizeof(float), (cudaStream_t)stream, t, w1, b1, w2, b2, temb_add,
-               temb, Cs, E);
+    launch_pdl(temb_kernel, dim3(B, cdiv(E, TEMB_EO)), dim3(256), (Cs + E) * sizeof(float), (cudaStream_t)stream, t, w1, b1,
+               w2, b2, temb_add, temb, Cs, E);
     B200_CHECK_LAUNCH();
     if (P > 0) {
         B200_CHECK_ARG(wp && bp && ada);
