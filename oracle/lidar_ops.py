@@ -71,3 +71,42 @@ def depth_to_xyz(x_norm, ray_angles, min_depth=1.45, max_depth=80.0):
     m2 = ((metric > min_depth) & (metric < max_depth)).astype(np.float32)
     xyz = np.concatenate([metric * np.cos(phi) * np.cos(th), metric * np.cos(phi) * np.sin(th), metric * np.sin(phi)], 1)
     return metric, (xyz * m2).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's OWN roiaware_pool3d code (oracle/_ref, built by oracle/Makefile from /root/reference in the
+# build container; the prebuilt .so files travel to the GPU box).  TEST INFRASTRUCTURE ONLY.
+# ---------------------------------------------------------------------------------------------------------
+_REF_CPU = os.path.join(_HERE, "_ref", "libref_roiaware_cpu.so")
+_REF_CUDA = os.path.join(_HERE, "_ref", "libref_roiaware_cuda.so")
+_ref_cpu = None
+_ref_cuda = None
+
+
+def ref_cpu_available() -> bool:
+    return os.path.exists(_REF_CPU)
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(_REF_CUDA)
+
+
+def ref_points_in_boxes_cpu(points, boxes):
+    """roiaware_pool3d.cpp:144-168 itself (no 0.2 m enlargement: that is the Python wrapper's job)."""
+    global _ref_cpu
+    if _ref_cpu is None:
+        _ref_cpu = C.CDLL(_REF_CPU)
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    bx = np.ascontiguousarray(boxes, dtype=np.float32)
+    out = np.zeros((bx.shape[0], pts.shape[0]), np.int32)
+    rc = _ref_cpu.ref_points_in_boxes_cpu(_p(bx), _p(pts), bx.shape[0], pts.shape[0], _p(out))
+    assert rc == 1
+    return out
+
+
+def ref_cuda_lib():
+    """ctypes handle of the reference's CUDA kernels (device pointers in, device pointers out)."""
+    global _ref_cuda
+    if _ref_cuda is None:
+        _ref_cuda = C.CDLL(_REF_CUDA)
+    return _ref_cuda

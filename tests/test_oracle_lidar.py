@@ -7,7 +7,9 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import pytest  # noqa: E402
 from make_golden_lidar import synth_sweep  # noqa: E402
+from make_golden_roiaware import synth_box_points, synth_boxes  # noqa: E402
 from oracle import lidar_ops as LO  # noqa: E402
 
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "projection.npz"))
@@ -32,6 +34,39 @@ def test_projection_edge_cases():
     assert win[8, 256] == 4                       # equal depth: highest index wins
     assert grid[2, 1] in (0, 1023) and grid[3, 1] in (0, 1023)
     assert img[8, 512, 5] == 0.0                  # depth 0 < min_depth -> mask 0 (but it still owns the pixel)
+
+
+ROI_GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "roiaware.npz"))
+
+
+def test_points_in_boxes_oracle_matches_reference_cpp_golden():
+    """tests/golden/roiaware.npz = outputs of the reference's own roiaware_pool3d.cpp (oracle/_ref); a third of the
+    points lie within 2e-6 m of a face, so this pins the rounding of the restatement, not just its logic."""
+    for seed in (0, 1):
+        boxes = synth_boxes(seed)
+        pts = synth_box_points(seed, boxes)
+        got = LO.points_in_boxes(pts, boxes)
+        want = np.unpackbits(ROI_GOLD[f"bits_{seed}"], axis=1)[:, :pts.shape[0]].astype(np.int32)
+        assert int(want.sum()) == int(ROI_GOLD[f"count_{seed}"][0]) > 5000
+        assert np.array_equal(got, want)
+        big = boxes.copy(); big[:, 3:6] += 0.2
+        want_big = np.unpackbits(ROI_GOLD[f"bits_big_{seed}"], axis=1)[:, :pts.shape[0]].astype(np.int32)
+        assert np.array_equal(LO.points_in_boxes(pts, big), want_big)
+
+
+@pytest.mark.skipif(not LO.ref_cpu_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_points_in_boxes_oracle_matches_reference_cpp_live():
+    """the compiled reference itself on fresh seeds (build container, or a box that received the prebuilt oracle/_ref)"""
+    for seed in (7, 8, 9):
+        boxes = synth_boxes(seed)
+        pts = synth_box_points(seed, boxes, per_box=4000)
+        assert np.array_equal(LO.points_in_boxes(pts, boxes), LO.ref_points_in_boxes_cpu(pts, boxes))
+    # empty / degenerate inputs the reference accepts
+    boxes = synth_boxes(3, 1)
+    assert LO.ref_points_in_boxes_cpu(np.zeros((0, 3), np.float32), boxes).shape == (1, 0)
+    flat = boxes.copy(); flat[:, 5] = 0.0                      # zero-height box: only z == cz passes the first test
+    p = np.array([[flat[0, 0], flat[0, 1], flat[0, 2]], [flat[0, 0], flat[0, 1], flat[0, 2] + 1e-3]], np.float32)
+    assert np.array_equal(LO.points_in_boxes(p, flat), LO.ref_points_in_boxes_cpu(p, flat))
 
 
 def _boxes(rs, n):
