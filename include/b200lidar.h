@@ -215,6 +215,48 @@ int b200_voxel_index(const float* pts, const float* rois, int* out, int N, int M
 int b200_depth_to_xyz(const float* x_norm, const float* ray_angles, float* depth, float* xyz, int B,
                       int H, int W, float min_depth, float max_depth, void* stream);
 
+/* ---- K8: evaluation-side projection + integer voxel quantiser (metrics/metric_utils.py) --------------
+ * pcd2range (metric_utils.py:65-121): F clouds, pcd fp32 [F,M,3], npts int32 [F] (NULL: all M valid), optional per-point
+ *   feature fp32 [F,M] (remission: feature_fill = -1; labels: 0).  Points with depth_min < ||xyz|| < depth_max (strict)
+ *   are binned (fp32 arithmetic of NumPy >= 2 on float32 input; no +1e-6, no modulo, clamp to the image); the nearest
+ *   point per pixel wins (equal depth: lowest index).  proj_range fp32 [F,H,W] (-1 where empty), proj_feature fp32
+ *   [F,H,W] or NULL;  zbuf: uint64 scratch [F,H,W].                                                          */
+int b200_pcd2range(const float* pcd, const int* npts, const float* feature, float* proj_range,
+                   float* proj_feature, void* zbuf, int F, int M, int H, int W, float fov_up_deg,
+                   float fov_down_deg, float depth_min, float depth_max, float feature_fill, void* stream);
+/* range2xyz (metric_utils.py:124-154): range_img fp32 [F,H,W] -> xyz fp64 [F,3,H,W] (-1 outside the depth range);
+ *   log_scale: depth = exp2(range * depth_scale) - 1 (fp32), else depth = range.                              */
+int b200_range2xyz(const float* range_img, double* xyz, int F, int H, int W, float fov_up_deg,
+                   float fov_down_deg, float depth_min, float depth_max, float depth_scale, int log_scale,
+                   void* stream);
+/* np.floor(coords / voxel_size).astype(np.int32) (sparse_quantize :51; pcd2bev_* / pcd2voxel_full :189,249):
+ *   coords [M,stride] fp32 (coords_f64 = 0) or fp64 (1), first D (2|3) columns used;  div_f32 = 1: fp32 division by
+ *   fp32(v) (python-float voxel size), 0: fp64 division (np.array voxel size).  voxel int32 [M,D];
+ *   minmax int32 [6] (device): per-axis min in [0:3], max in [3:6] -- the caller reads it back to size the workspace.  */
+int b200_quantize_coords(const void* coords, int coords_f64, int M, int D, int stride, double v0, double v1,
+                         double v2, int div_f32, int32_t* voxel, int32_t* minmax, void* stream);
+/* bytes of workspace b200_sparse_quantize needs for this bounding grid (minmax on the HOST); 0 = grid too large */
+size_t b200_sparse_quantize_workspace(const int32_t* minmax_host, int D, int M);
+/* ravel_hash (metric_utils.py:28-41): uint64 key of every voxel [M]                                          */
+int b200_ravel_hash(const int32_t* voxel, int M, int D, const int32_t* minmax_host, uint64_t* out, void* stream);
+/* np.unique(ravel_hash(voxel), return_index=True, return_inverse=True) (metric_utils.py:53-62), sort-free: bitmap of
+ *   the bounding grid -> popcount scan -> rank.  uniq_coords int32 [M,D] (first n_unique rows valid, hash order),
+ *   indices int64 [M] (first occurrence), inverse int64 [M], n_unique int32 [1] (device); any of the first three may
+ *   be NULL.                                                                                                  */
+int b200_sparse_quantize(const int32_t* voxel, int M, int D, const int32_t* minmax_host, void* workspace,
+                         size_t workspace_bytes, int32_t* uniq_coords, int64_t* indices, int64_t* inverse,
+                         int32_t* n_unique, void* stream);
+/* pcd2bev_sum (metric_utils.py:231-256): clouds concatenated in pcd fp32 [total,stride] with offsets int32
+ *   [n_clouds+1] (device); volume_sum fp32 [X,Y] += 1 per (cloud, occupied cell); bitmap_ws: n_clouds *
+ *   ceil(X*Y/32) uint32 scratch.  Strict range test, cell = floor(v / fp32(voxel)) - min_bound.               */
+int b200_bev_occupancy_sum(const float* pcd, const int* offsets, int n_clouds, int max_cloud_pts, int stride,
+                           float x_lo, float x_hi, float y_lo, float y_hi, float voxel, int min_bx, int min_by,
+                           int X, int Y, void* bitmap_ws, float* volume_sum, void* stream);
+/* pcd2voxel_full (metric_utils.py:170-199): one cloud -> vol fp32 [X,Y,Z] of 0/1.  range_lo_hi_host = {x0,x1,y0,y1,
+ *   z0,z1}, min_bound_host / dims_host int32 [3] (HOST pointers).                                            */
+int b200_voxel_occupancy(const float* pcd, int M, int stride, const float* range_lo_hi_host, float voxel,
+                         const int32_t* min_bound_host, const int32_t* dims_host, float* vol, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ P = C.c_void_p
 I = C.c_int
 F = C.c_float
 SZ = C.c_size_t
+D = C.c_double
 
 # name -> (restype, argtypes); must mirror include/b200lidar.h exactly (tests/test_abi.py checks it)
 PROTOTYPES = {
@@ -49,9 +50,18 @@ PROTOTYPES = {
     "b200_points_in_boxes_first": (I, [P, P, P, I, I, I, P]),
     "b200_voxel_index": (I, [P, P, P, I, I, I, I, I, P]),
     "b200_depth_to_xyz": (I, [P, P, P, P, I, I, I, F, F, P]),
+    "b200_pcd2range": (I, [P, P, P, P, P, P, I, I, I, I, F, F, F, F, F, P]),
+    "b200_range2xyz": (I, [P, P, I, I, I, F, F, F, F, F, I, P]),
+    "b200_quantize_coords": (I, [P, I, I, I, I, D, D, D, I, P, P, P]),
+    "b200_sparse_quantize_workspace": (SZ, [P, I, I]),
+    "b200_ravel_hash": (I, [P, I, I, P, P, P]),
+    "b200_sparse_quantize": (I, [P, I, I, P, P, SZ, P, P, P, P, P]),
+    "b200_bev_occupancy_sum": (I, [P, P, I, I, I, F, F, F, F, F, I, I, I, I, P, P, P]),
+    "b200_voxel_occupancy": (I, [P, I, I, P, F, P, P, P, P]),
 }
 
-_NO_STATUS = {"b200_conv_merged", "b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems"}
+_NO_STATUS = {"b200_conv_merged", "b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems",
+              "b200_sparse_quantize_workspace"}
 
 
 class B200LidarError(RuntimeError):

@@ -87,3 +87,14 @@ def transforms_common():
     setup()
     from lidargen.dataset.transforms_3d import common as m
     return m
+
+
+def metric_utils():
+    """lidargen/metrics/metric_utils.py (the package __init__ imports cleanly: torchsparse / chamfer / emd are optional
+    there and only print a hint when missing)."""
+    setup()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        from lidargen.metrics import metric_utils as m
+    return m
