@@ -94,14 +94,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def random_weights(sd: dict, seed: int = 0) -> dict:
+    """Random-init weights of the named architecture (there are no checkpoints offline).  The reference zero-inits the
+    last conv of every branch, which would make the timed network degenerate, so every floating parameter is redrawn:
+    GroupNorm gamma ~ N(1, 0.1), beta ~ N(0, 0.1), biases ~ N(0, 0.02), weights ~ N(0, 1/fan_in); one generator per key
+    (same recipe as the test oracle uses, restated here so that the measured arm never imports oracle/)."""
+    import math
+    import zlib
+    out = {}
+    for k, v in sd.items():
+        leaf = k.split(".")[-1]
+        if leaf in ("coords", "scale", "kernel", "freqs", "phase", "_dummy") or not v.is_floating_point():
+            out[k] = v.clone()
+            continue
+        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) % (2 ** 31))
+        if leaf == "weight" and v.dim() == 1:
+            out[k] = 1 + 0.1 * torch.randn(v.shape, generator=g)
+        elif "norm" in k and leaf == "bias" and "proj" not in k:
+            out[k] = 0.1 * torch.randn(v.shape, generator=g)
+        elif leaf in ("bias", "in_proj_bias") or v.dim() == 1:
+            out[k] = 0.02 * torch.randn(v.shape, generator=g)
+        else:
+            out[k] = torch.randn(v.shape, generator=g) / math.sqrt(v[0].numel())
+    return out
+
+
 def build_model(device, precision):
     import lidarcrafter_b200 as L
-    from oracle import unet_torch as O  # only for the deterministic random weights (no oracle compute here)
     m = L.EfficientUNet(in_channels=2, resolution=RES, base_channels=64, channel_multiplier=(1, 2, 4, 8),
                         num_residual_blocks=NRES, gn_num_groups=8, gn_eps=1e-6, attn_num_heads=8,
                         coords_encoding="fourier_features", ring=True)
     m.coords = L.get_linear_ray_angles(RES[0], RES[1], 10, -30)
-    m.load_state_dict(O.randomize_state_dict(m.state_dict(), seed=0))
+    m.load_state_dict(random_weights(m.state_dict(), seed=0))
     m.precision = precision
     m = m.to(device).eval()
     ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type="eps", noise_schedule="cosine").to(device)
@@ -242,17 +266,21 @@ def main():
         ms = float(tms)
     value = B * world * K / (ms / 1e3)
 
-    # ---- e2e: the public API with HOST buffers: every step H2D x_t (pinned) -> p_step -> D2H x_s ----
+    # ---- e2e: the public API (GaussianDiffusion.p_step) with HOST buffers: every step H2D x_t (pinned) -> p_step -> D2H x_s ----
     xh = torch.empty(B, 2, *RES, pin_memory=True).copy_(x0.cpu())
     yh = torch.empty(B, 2, *RES, pin_memory=True)
     Ke = min(K, 20)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    xd = torch.empty(B, 2, *RES, device=dev)
+    ddpm.p_step(xd.copy_(xh), steps[0].repeat(B), steps[1].repeat(B), mode="ddim")   # untimed warm-up of the public call
+    barrier()
     t0.record()
     for i in range(Ke):
-        plan.x_in.copy_(xh, non_blocking=True)
-        one_step(W + i)
-        yh.copy_(plan.x_in, non_blocking=True)
+        j = (W + i) % 50
+        xd.copy_(xh, non_blocking=True)                                             # H2D of this step's input
+        y = ddpm.p_step(xd, steps[j].repeat(B), steps[j + 1].repeat(B), mode="ddim")  # the public call (continuous_time.py:195)
+        yh.copy_(y, non_blocking=True)                                              # D2H of this step's result
         torch.cuda.current_stream(dev).synchronize()   # the caller reads the result every step
         xh, yh = yh, xh
     t1.record()

@@ -185,6 +185,19 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         if mode not in ("ddpm", "ddim"):
             raise ValueError(f"invalid mode {mode}")
         lt, coef = self._coefficients(step_t, step_s, ddim_eta)
+        if self.use_cuda_graph and x_t.is_cuda and hasattr(self.model, "get_plan"):
+            # the same captured step (model plan + fused update) that sample() replays: one graph launch per call
+            plan = self.model.get_plan(x_t.shape[0])
+            entry = self._step_graph(plan, x_t.shape[0], mode)
+            if entry["graph"] is not None:
+                plan.x_in.copy_(x_t)
+                plan.t_in.copy_(lt)
+                entry["coef"].copy_(coef)
+                noise = self.randn_like(x_t, rng=rng)      # drawn every step like the reference (RNG stream parity)
+                if mode == "ddpm" or ddim_eta != 0.0:
+                    entry["noise"].copy_(noise)
+                entry["graph"].replay()
+                return plan.x_in.clone()
         pred = self._predict(x_t, lt).contiguous()
         noise = self.randn_like(x_t, rng=rng).contiguous()
         x_t = x_t.contiguous()
