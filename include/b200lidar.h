@@ -75,6 +75,8 @@ int b200_conv_tc_gn(const void* a, const void* wpacked, const float* bias, const
 /* profiling aid: device buffer of [#CTAs][8] uint64 cycle counters filled by b200_conv_tc (NULL disables; see
  * conv_tc.cu g_conv_dbg for the slot meaning).  Not used on the product path.                          */
 int b200_conv_set_debug(void* dbg_u64);
+/* diagnostic builds only (-DB200_CONV_ABLATE): timing ablations of the conv pipeline (see conv_tc.cu); mask 0 = off */
+int b200_conv_set_ablate(int mask);
 /* number of fp16-sized elements of the packed weight image (== planes*taps*Cout*Cin, planes = 1 for parts 1 else 2) */
 size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
 /* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
@@ -188,6 +190,14 @@ int b200_flash_attention_oa(const float* qkv, const float* pos_p, const float* k
 int b200_sampler_update(const float* x_t, const float* pred, const float* noise, const float* coef,
                         float* x_s, int B, int n_per_sample, int mode, int objective, float clip,
                         void* stream);
+
+/* log-SNR schedule + step coefficients of a batch in one launch (continuous_time.py:14-63,200-231):
+ *   step_t, step_s fp32 [B] in [0,1];  schedule 0 = linear, 1 = cosine, 2 = cosine_shifted, 3 = cosine_interpolated;
+ *   t_min = atan(exp(-logsnr_max/2)), t_span = atan(exp(-logsnr_min/2)) - t_min, shift_* = 2 log(noise_d/image_d);
+ *   log_snr_t fp32 [B] (the network's time condition), coef fp32 [B,8] as b200_sampler_update expects.      */
+int b200_sampler_coefficients(const float* step_t, const float* step_s, int schedule, float t_min, float t_span,
+                              float shift_lo, float shift_hi, float ddim_eta, float* log_snr_t, float* coef,
+                              int B, void* stream);
 
 /* ---- K6: point cloud -> range image ----------------------------------------------------------------
  * replaces load_points_as_images (dataset/transforms_3d/common.py:26-91, scan_unfolding=False).

@@ -26,6 +26,7 @@ PROTOTYPES = {
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b200_conv_tc_gn": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, F, I, P, I, P]),
     "b200_conv_set_debug": (I, [P]),
+    "b200_conv_set_ablate": (I, [I]),
     "b200_packed_weight_elems": (SZ, [I, I, I, I]),
     "b200_pack_conv_weight": (I, [P, P, I, I, I, I, I, I, F, P]),
     "b200_conv_merged": (I, [I, I, I]),
@@ -45,6 +46,7 @@ PROTOTYPES = {
     "b200_out_conv": (I, [P, I, P, P, P, I, I, I, I, I, I, P]),
     "b200_attention": (I, [P, I, I, P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, F, P]),
     "b200_sampler_update": (I, [P, P, P, P, P, I, I, I, I, F, P]),
+    "b200_sampler_coefficients": (I, [P, P, I, F, F, F, F, F, P, P, I, P]),
     "b200_range_project": (I, [P, P, P, P, P, I, I, I, I, F, F, F, F, P]),
     "b200_points_in_boxes": (I, [P, P, P, I, I, P]),
     "b200_points_in_boxes_first": (I, [P, P, P, I, I, I, P]),

@@ -89,6 +89,16 @@ __device__ __align__(128) unsigned char g_zero_page[16384];  // source of zero-p
 //   [0] MMA thread total, [1] wait FULL_A, [2] wait FULL_B, [3] wait ACC_EMPTY,
 //   [4] epilogue warp 0 total, [5] epilogue wait ACC_FULL, [6] producer wait EMPTY_A, [7] producer wait EMPTY_B
 __device__ unsigned long long* g_conv_dbg = nullptr;
+// Timing ablations (b200_conv_set_ablate; results are WRONG with any bit set -- bottleneck analysis only):
+//   1 MMA thread does not wait for FULL_A, 2 ... for FULL_B, 4 epilogue skips the residual loads / global stores,
+//   8 no tcgen05.mma is issued (commits only), 16 producers arrive without copying (no TMA traffic),
+//   32 the issuing warp idles ~300 cycles after every chunk (is its own time hidden behind queued MMAs?)
+__device__ int g_conv_ablate = 0;
+#ifdef B200_CONV_ABLATE          // diagnostic builds only (make EXTRA=-DB200_CONV_ABLATE); the product build compiles them out
+#define ABL(bit) (ablate & (bit))
+#else
+#define ABL(bit) false
+#endif
 #define DBG_T0() const long long t0__ = dbg ? clock64() : 0
 #define DBG_ACC(slot) do { if (dbg) dbg_acc[slot] += clock64() - t0__; } while (0)
 
@@ -120,7 +130,10 @@ struct ConvCfg {
     static constexpr int EPI_STG = EPI_WARPS * 32 * 36 * 4;            // per-warp transpose staging
     static constexpr int EPI = EPI_STG + EPI_WARPS * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BUDGET = 227 * 1024 - EPI - 320;
-    static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= 3 ? 3 : 2;
+#ifndef B200_CONV_SA_MAX
+#define B200_CONV_SA_MAX 3
+#endif
+    static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2;
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
     static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;   // weight ring: as deep as shared memory allows
     static_assert(SB >= 3, "weight ring too shallow");
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             mbar_init(EMPTY_B(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(ACC_FULL(s), 1);
+            mbar_init(ACC_FULL(s), 2);     // one commit from each of the two MMA issuer warps
             mbar_init(ACC_EMPTY(s), EPI_WARPS * 32);
         }
         fence_barrier_init();
@@ -190,6 +203,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                // everything above (barriers, TMEM) overlapped the previous kernel's tail
 
+    const int ablate = g_conv_ablate;
+    (void)ablate;
     if (warp == 4) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
         uint32_t ia = 0;
@@ -210,9 +225,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         DBG_T0();
                         mbar_wait(EMPTY_A(s), ph ^ 1);
                         DBG_ACC(6);
-                        mbar_expect_tx(FULL_A(s), C::A_STAGE);
+                        if (ABL(16)) mbar_arrive(FULL_A(s));
+                        else mbar_expect_tx(FULL_A(s), C::A_STAGE);
                     }
                     __syncwarp();
+                    if (ABL(16)) { ++ia; continue; }
                     const uint32_t dst0 = sbase + C::OFF_A + s * C::A_STAGE;
                     // one bulk copy per (plane, staged row): the KG slabs of this K chunk are contiguous in the
                     // tile-major operand and already carry the two halo pixels
@@ -265,6 +282,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         mbar_wait(EMPTY_B(s), ph ^ 1);
                         DBG_ACC(7);
                     }
+                    if (ABL(16)) { mbar_arrive(FULL_B(s)); continue; }
                     mbar_expect_tx(FULL_B(s), C::B_STAGE);
                     bulk_copy_g2s(sbase + C::OFF_B + s * C::B_STAGE, wsrc + (size_t)q * (C::B_STAGE / 2), C::B_STAGE,
                                   FULL_B(s));
@@ -272,17 +290,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             }
             if (dbg) dbg[blockIdx.x * 8 + 7] = dbg_acc[7];
         }
-    } else if (warp == 5) {
-        // ------------------------------ MMA issuer ------------------------------
-        // The whole warp runs the loop (uniform control flow, waits included); one elected lane issues the MMAs and
-        // commits.  Keeping the branch warp-uniform lets the descriptor arithmetic live in uniform registers: between
-        // two tcgen05.mma there is one 32-bit add per operand (see desc_lo / tc_mma_f16_lh).
+    } else if (warp == 5 || warp == 7) {
+        // ------------------------------ MMA issuers (two warps, ping-pong over the K chunks) ------------------------------
+        // Measured with the ablation build (tools/exp_conv_ablate.py): the tensor pipe queues only a couple of MMAs, so every
+        // cycle the issuing warp spends NOT issuing (barrier polls ~140 cycles each, fence, election, descriptor moves into
+        // uniform registers, commits: 800-1300 cycles per chunk against ~2000 cycles of MMAs) is a cycle the pipe idles --
+        // an artificial 300-cycle pause per chunk lengthened the kernel by exactly 300 cycles x chunks.  Hence two issuers:
+        // while one warp's MMAs of chunk g run, the other has already waited for the operands of chunk g + 1 and built
+        // its descriptors, and starts issuing the moment it is handed the turn (named barriers 2 / 3, ~tens of cycles).
+        // Each warp runs its loop with uniform control flow (waits included) and one elected lane issues: the descriptor
+        // arithmetic stays in uniform registers (one 32-bit add per operand between two tcgen05.mma).  Every warp commits
+        // the stages it read and, per tile, its own share of the accumulator (ACC_FULL counts two arrivals).
         {
+            const uint32_t par = warp == 7 ? 1u : 0u;
             constexpr uint32_t idesc = make_idesc_f16(128, BN);
             constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * BN);
             constexpr uint32_t KGS = C::MERGE ? 2 * BN * 16 : BN * 16;   // byte stride between 8-channel groups of B
             uint32_t ia = 0, ib = 0, it = 0;
-            unsigned long long* dbg = lane == 0 ? g_conv_dbg : nullptr;
+            unsigned long long* dbg = (lane == 0 && par == 0) ? g_conv_dbg : nullptr;
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const long long t_start = dbg ? clock64() : 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
@@ -294,25 +319,41 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 }
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * C::ACC_COLS;
-                for (int c = 0; c < NCH; ++c, ++ia) {
+                for (int c = 0; c < NCH; ++c, ++ia, ib += C::TG) {
+                    if ((ia & 1u) != par) continue;          // the other issuer's chunk
                     const int sa = ia % C::SA;
-                    {
+                    // (all 32 lanes poll: a lane-0-only poll + __syncwarp() was measured 25 % SLOWER -- the divergent region
+                    // takes the descriptor arithmetic out of the uniform datapath)
+                    if (!ABL(1)) {
                         DBG_T0();
                         mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
                         DBG_ACC(1);
                     }
+                    if (!ABL(2)) {
+                        DBG_T0();
+#pragma unroll
+                        for (int dy = 0; dy < C::TG; ++dy) mbar_wait(FULL_B((ib + dy) % C::SB), ((ib + dy) / C::SB) & 1);
+                        DBG_ACC(2);
+                    }
                     const uint32_t a_lo0 = desc_lo(sbase + C::OFF_A + sa * C::A_STAGE, C::SLAB);
-                    for (int dy = 0; dy < C::TG; ++dy, ++ib) {
-                        const int sb = ib % C::SB;
-                        {
-                            DBG_T0();
-                            mbar_wait(FULL_B(sb), (ib / C::SB) & 1);
-                            DBG_ACC(2);
-                        }
-                        tc_fence_after();
-                        const uint32_t b_lo0 = desc_lo(sbase + C::OFF_B + sb * C::B_STAGE, KGS);
-                        const uint32_t first_cd = (uint32_t)((c | dy) != 0);
-                        if (elect_one()) {
+                    uint32_t b_lo[C::TG];
+#pragma unroll
+                    for (int dy = 0; dy < C::TG; ++dy) b_lo[dy] = desc_lo(sbase + C::OFF_B + ((ib + dy) % C::SB) * C::B_STAGE, KGS);
+                    if (ABL(32)) {   // is this warp's own time hidden now?  (+300 cycles of preparation per chunk)
+                        const long long t_spin = clock64();
+                        while (clock64() - t_spin < 300) {}
+                    }
+                    if (ia != 0) {   // my turn: the other issuer has issued chunk ia - 1
+                        DBG_T0();
+                        named_bar_sync(2 + par, 64);
+                        DBG_ACC(4);
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int dy = 0; dy < C::TG; ++dy) {
+                            const uint32_t first_cd = (uint32_t)((c | dy) != 0);
+                            if (!ABL(8))
 #pragma unroll
                             for (int dx = 0; dx < C::TW; ++dx) {
 #pragma unroll
@@ -322,7 +363,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                                         // staged input row o + dy feeds output row o through filter row dy
                                         const uint32_t a_hi = a_lo0 + ((uint32_t)(dy * C::KG * C::SLAB) >> 4) +
                                                               (((o * C::KG + ks * 2) * C::SLAB + (dx + C::DX0) * 16) >> 4);
-                                        const uint32_t b_hi = b_lo0 + ((dx * C::B_TAP + ks * 2 * KGS) >> 4);
+                                        const uint32_t b_hi = b_lo[dy] + ((dx * C::B_TAP + ks * 2 * KGS) >> 4);
                                         const uint32_t first = (dx | ks) != 0 ? 1u : first_cd;
                                         const uint32_t d = acc + o * C::ACC_ROW;
                                         if (C::F8) {
@@ -343,15 +384,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                                     }
                                 }
                             }
-                            tc_commit(EMPTY_B(sb));  // weights slot free once these MMAs retire
-                            if (dy == C::TG - 1) {
-                                tc_commit(EMPTY_A(sa));
-                                if (c == NCH - 1) tc_commit(ACC_FULL(buf));
-                            }
+                            tc_commit(EMPTY_B((ib + dy) % C::SB));  // weights slot free once these MMAs retire
                         }
-                        __syncwarp();
+                        tc_commit(EMPTY_A(sa));
                     }
+                    __syncwarp();
+                    tc_fence_before();
+                    named_bar_arrive(2 + (par ^ 1u), 64);    // hand the tensor pipe to the other issuer
                 }
+                // this warp's share of the tile's accumulator is complete when ITS MMAs have retired
+                if (elect_one()) tc_commit(ACC_FULL(buf));
+                __syncwarp();
             }
             if (dbg) {
                 dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
@@ -360,7 +403,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
             }
         }
-    } else if (warp != 7) {
+    } else {
         // ------------------------------ epilogue: warps 0-3 and 8-11; warp w reads TMEM lanes 32*(w%4) .. +31 ------------------------------
         // the two warps of a lane quarter split the (row, 32-column slice) work items of a tile between them
         const int ew = warp < 4 ? warp : warp - 4;       // 0..7: epilogue warp index
@@ -419,7 +462,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 return p.res + ((size_t)(b * p.H + h0 + o) * p.W + w0 + quarter * 32 + rb) * p.Cout + n0 + sl * 32 + col4 * 4;
             };
             float4 rv[8];
-            if (p.res && egroup < NITEM) {
+            const bool do_res = p.res && !ABL(4);
+            if (do_res && egroup < NITEM) {
                 const float* rp = res_ptr(egroup);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
@@ -445,7 +489,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         for (int j = 0; j < 32; ++j) v[j] += v2[j];
                     }
                     float4 rn[8];      // next item's residual: in flight during this item's transpose / stores
-                    if (p.res && item + 2 < NITEM) {
+                    if (do_res && item + 2 < NITEM) {
                         const float* rp = res_ptr(item + 2);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
@@ -470,9 +514,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         const size_t gi = row_base + (size_t)row * p.Cout + nb;
                         tv.x = fmaf(tv.x, winv, bi.x); tv.y = fmaf(tv.y, winv, bi.y);
                         tv.z = fmaf(tv.z, winv, bi.z); tv.w = fmaf(tv.w, winv, bi.w);
-                        if (p.res) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
+                        if (do_res) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
                         tv.x *= scale; tv.y *= scale; tv.z *= scale; tv.w *= scale;
-                        *reinterpret_cast<float4*>(p.out + gi) = tv;
+                        if (!ABL(4)) *reinterpret_cast<float4*>(p.out + gi) = tv;
                         s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
                         s2[0] += tv.x * tv.x; s2[1] += tv.y * tv.y; s2[2] += tv.z * tv.z; s2[3] += tv.w * tv.w;
                     }
@@ -494,7 +538,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         }
                     }
                     __syncwarp();
-                    if (p.res && item + 2 < NITEM) {
+                    if (do_res && item + 2 < NITEM) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rv[i] = rn[i];
                     }
@@ -832,6 +876,21 @@ extern "C" int b200_conv_set_debug(void* dbg_u64) {
     cudaError_t e = cudaMemcpyToSymbol(g_conv_dbg, &p, sizeof(p));
     if (e != cudaSuccess) {
         set_error("conv_set_debug: %s", cudaGetErrorString(e));
+        return B200_E_CUDA;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_conv_set_ablate(int mask) {
+#ifndef B200_CONV_ABLATE
+    if (mask != 0) {
+        set_error("conv_set_ablate: this build has no ablation switches (make EXTRA=-DB200_CONV_ABLATE)");
+        return B200_E_ARG;
+    }
+#endif
+    cudaError_t e = cudaMemcpyToSymbol(g_conv_ablate, &mask, sizeof(mask));
+    if (e != cudaSuccess) {
+        set_error("conv_set_ablate: %s", cudaGetErrorString(e));
         return B200_E_CUDA;
     }
     return B200_OK;

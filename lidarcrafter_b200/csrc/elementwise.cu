@@ -1000,9 +1000,54 @@ __global__ void sampler_update_kernel(const float* __restrict__ x_t, const float
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// sampler coefficients: log-SNR schedules + DDIM/DDPM step coefficients of a whole batch in ONE launch
+// (continuous_time.py:14-63 and :200-231 evaluate them with ~25 tiny elementwise kernels per p_step)
+// ---------------------------------------------------------------------------------------------------------
+struct ScheduleParams {
+    int kind;             // 0 linear, 1 cosine, 2 cosine_shifted, 3 cosine_interpolated
+    float t_min, t_span;  // cosine family: atan(exp(-logsnr_max/2)), t_max - t_min
+    float shift_lo, shift_hi;   // 2 log(noise_d / image_d) for noise_d_low / noise_d_high
+};
+
+__device__ __forceinline__ float log_snr_f(const ScheduleParams& sp, float t) {
+    if (sp.kind == 0) return -logf(fmaxf(expm1f(__fadd_rn(1e-4f, __fmul_rn(10.f, __fmul_rn(t, t)))), 1e-20f));
+    const float base = -2.f * logf(fmaxf(tanf(__fadd_rn(sp.t_min, __fmul_rn(t, sp.t_span))), 1e-20f));
+    if (sp.kind == 1) return base;
+    if (sp.kind == 2) return base + sp.shift_lo;
+    return t * (base + sp.shift_lo) + (1.f - t) * (base + sp.shift_hi);
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void sampler_coef_kernel(const float* __restrict__ step_t, const float* __restrict__ step_s, ScheduleParams sp,
+                                    float eta, float* __restrict__ log_snr_t, float* __restrict__ coef, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float lt = log_snr_f(sp, step_t[b]), ls = log_snr_f(sp, step_s[b]);
+    const float a_t = sqrtf(sigmoid_f(lt)), s_t = sqrtf(sigmoid_f(-lt));
+    const float a_s = sqrtf(sigmoid_f(ls)), s_s = sqrtf(sigmoid_f(-ls));
+    const float c1 = eta * s_s / s_t * sqrtf(1.f - (a_t * a_t) / (a_s * a_s));
+    const float c2 = sqrtf(1.f - a_s * a_s - c1 * c1);
+    const float cc = -expm1f(lt - ls);
+    log_snr_t[b] = lt;
+    float* o = coef + (size_t)b * 8;
+    o[0] = a_t; o[1] = s_t; o[2] = a_s; o[3] = s_s; o[4] = c1; o[5] = c2; o[6] = cc; o[7] = 0.f;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_sampler_coefficients(const float* step_t, const float* step_s, int schedule, float t_min, float t_span,
+                                         float shift_lo, float shift_hi, float ddim_eta, float* log_snr_t, float* coef,
+                                         int B, void* stream) {
+    B200_CHECK_ARG(step_t && step_s && log_snr_t && coef && B > 0 && schedule >= 0 && schedule <= 3);
+    ScheduleParams sp{schedule, t_min, t_span, shift_lo, shift_hi};
+    sampler_coef_kernel<<<cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(step_t, step_s, sp, ddim_eta, log_snr_t, coef, B);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
 
 extern "C" int b200_version(void) { return 100; }
 extern "C" const char* b200_last_error(void) { return g_err; }

@@ -130,17 +130,24 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         self.use_cuda_graph = True
 
     def setup_parameters(self) -> None:
+        t_min, t_max = math.atan(math.exp(-0.5 * 15)), math.atan(math.exp(0.5 * 15))
+        # (kind, t_min, t_span, shift_lo, shift_hi) of b200_sampler_coefficients -- the device mirror of self.log_snr
         if self.noise_schedule == "linear":
             self.log_snr = _log_snr_schedule_linear
+            self._sched = (0, 0.0, 0.0, 0.0, 0.0)
         elif self.noise_schedule == "cosine":
             self.log_snr = _log_snr_schedule_cosine
+            self._sched = (1, t_min, t_max - t_min, 0.0, 0.0)
         elif self.noise_schedule == "cosine_shifted":
             assert self.image_d is not None and self.noise_d_low is not None
             self.log_snr = partial(_log_snr_schedule_cosine_shifted, image_d=self.image_d, noise_d=self.noise_d_low)
+            self._sched = (2, t_min, t_max - t_min, 2 * math.log(self.noise_d_low / self.image_d), 0.0)
         elif self.noise_schedule == "cosine_interpolated":
             assert self.image_d is not None and self.noise_d_low is not None and self.noise_d_high is not None
             self.log_snr = partial(_log_snr_schedule_cosine_interpolated, image_d=self.image_d,
                                    noise_d_low=self.noise_d_low, noise_d_high=self.noise_d_high)
+            self._sched = (3, t_min, t_max - t_min, 2 * math.log(self.noise_d_low / self.image_d),
+                           2 * math.log(self.noise_d_high / self.image_d))
         else:
             raise ValueError(f"invalid beta schedule: {self.noise_schedule}")
 
@@ -164,7 +171,22 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         return x_s * alpha_ts + var.sqrt() * var_noise
 
     # ---- sampler coefficients: [.., 8] = alpha_t, sigma_t, alpha_s, sigma_s, c1, c2, ddpm_c, 0 ----
-    def _coefficients(self, step_t: torch.Tensor, step_s: torch.Tensor, ddim_eta: float):
+    def _coefficients(self, step_t: torch.Tensor, step_s: torch.Tensor, ddim_eta: float, out=None):
+        """-> (log-SNR(t) [B], coefficient rows [B,8]); ``out`` = (lt, coef) device buffers to write into."""
+        if step_t.is_cuda:
+            # one launch instead of the ~25 elementwise kernels of the expressions below (same fp32 formulas)
+            B = step_t.shape[0]
+            st, ss = step_t.float().contiguous(), step_s.float().contiguous()
+            if out is not None:
+                lt, coef = out
+            else:
+                lt = torch.empty(B, device=st.device, dtype=torch.float32)
+                coef = torch.empty(B, 8, device=st.device, dtype=torch.float32)
+            k, t_min, t_span, sh_lo, sh_hi = self._sched
+            _lib.get_lib().sampler_coefficients(st.data_ptr(), ss.data_ptr(), k, t_min, t_span, sh_lo, sh_hi,
+                                                float(ddim_eta), lt.data_ptr(), coef.data_ptr(), B,
+                                                _lib.current_stream(st.device))
+            return lt, coef
         lt = self.log_snr(step_t)[:, 0, 0, 0]
         ls = self.log_snr(step_s)[:, 0, 0, 0]
         a_t, s_t = _log_snr_to_alpha_sigma(lt)
@@ -184,20 +206,19 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         """continuous_time.py:194-234: one reverse step (model forward + fused update kernel)."""
         if mode not in ("ddpm", "ddim"):
             raise ValueError(f"invalid mode {mode}")
-        lt, coef = self._coefficients(step_t, step_s, ddim_eta)
         if self.use_cuda_graph and x_t.is_cuda and hasattr(self.model, "get_plan"):
             # the same captured step (model plan + fused update) that sample() replays: one graph launch per call
             plan = self.model.get_plan(x_t.shape[0])
             entry = self._step_graph(plan, x_t.shape[0], mode)
             if entry["graph"] is not None:
                 plan.x_in.copy_(x_t)
-                plan.t_in.copy_(lt)
-                entry["coef"].copy_(coef)
+                self._coefficients(step_t, step_s, ddim_eta, out=(plan.t_in, entry["coef"]))   # straight into the graph's inputs
                 noise = self.randn_like(x_t, rng=rng)      # drawn every step like the reference (RNG stream parity)
                 if mode == "ddpm" or ddim_eta != 0.0:
                     entry["noise"].copy_(noise)
                 entry["graph"].replay()
                 return plan.x_in.clone()
+        lt, coef = self._coefficients(step_t, step_s, ddim_eta)
         pred = self._predict(x_t, lt).contiguous()
         noise = self.randn_like(x_t, rng=rng).contiguous()
         x_t = x_t.contiguous()
@@ -302,12 +323,8 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         entry = self._step_graph(plan, B, mode)
         steps = torch.linspace(1.0, 0.0, num_steps + 1, device=dev)
         # per-step tables (same fp32 torch math as the reference, evaluated once for the whole trajectory)
-        lts, coefs = [], []
-        for i in range(num_steps):
-            lt, coef = self._coefficients(steps[i].repeat(B), steps[i + 1].repeat(B), ddim_eta)
-            lts.append(lt)
-            coefs.append(coef)
-        lts, coefs = torch.stack(lts), torch.stack(coefs)
+        lts, coefs = self._coefficients(steps[:-1].repeat_interleave(B), steps[1:].repeat_interleave(B), ddim_eta)
+        lts, coefs = lts.view(num_steps, B), coefs.view(num_steps, B, 8)
         need_noise = mode == "ddpm" or ddim_eta != 0.0
         plan.x_in.copy_(x)
         out = [x] if return_all else None

@@ -163,3 +163,24 @@ def test_unet_fused_gn_tail_equals_separate_launch(monkeypatch):
     m2, _ = make_unet(res, nres)
     y1 = m2.cuda()(x.cuda(), t.cuda()).cpu()
     assert rel_l2(y1, y0) < 1e-5 and rel_l2(y1, y_ref) < TOL
+
+
+@pytest.mark.parametrize("schedule,kw", [("linear", {}), ("cosine", {}),
+                                         ("cosine_shifted", dict(image_d=64.0, noise_d_low=32.0)),
+                                         ("cosine_interpolated", dict(image_d=64.0, noise_d_low=32.0, noise_d_high=256.0))])
+def test_sampler_coefficient_kernel_vs_torch_expressions(schedule, kw):
+    """b200_sampler_coefficients (one launch) == the reference's chain of fp32 torch expressions
+    (continuous_time.py:14-63,200-231), evaluated here on the CPU by the same host code."""
+    res, nres, _ = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres)
+    ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type="eps", noise_schedule=schedule, **kw)
+    t = torch.linspace(1.0, 0.02, 50)
+    s = t - 0.02
+    for eta in (0.0, 0.5):
+        # CPU tensors -> torch expressions, one sample at a time: the reference's cosine_interpolated broadcasts
+        # t[B] against log_snr[B,1,1,1] (continuous_time.py:57), which is only well defined for B == 1 / equal steps
+        refs = [ddpm._coefficients(t[i:i + 1], s[i:i + 1], eta) for i in range(len(t))]
+        lt_ref, coef_ref = torch.cat([r[0] for r in refs]), torch.cat([r[1] for r in refs])
+        lt, coef = ddpm._coefficients(t.cuda(), s.cuda(), eta)        # CUDA tensors -> the kernel
+        assert torch.allclose(lt.cpu(), lt_ref, rtol=2e-5, atol=2e-5)
+        assert torch.allclose(coef.cpu(), coef_ref, rtol=1e-4, atol=2e-6), (coef.cpu() - coef_ref).abs().max()
