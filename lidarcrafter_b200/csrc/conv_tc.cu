@@ -104,7 +104,7 @@ __device__ int g_conv_ablate = 0;
 
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
 constexpr int CONV_THREADS = 384;   // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: A producer; 5: MMA; 6: B producer
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS_MAX = 8;   // warps 0-3 and 8-11; ConvCfg::EW of them work (BN = 128 tiles: 4, see ConvCfg)
 
 template <int BN, int R, int TAPS, int NP>
 struct ConvCfg {
@@ -127,13 +127,20 @@ struct ConvCfg {
     static constexpr int B_PART = BN * KC * 2;
     static constexpr int B_TAP = PL * B_PART;
     static constexpr int B_STAGE = TW * B_TAP;
-    static constexpr int EPI_STG = EPI_WARPS * 32 * 36 * 4;            // per-warp transpose staging
-    static constexpr int EPI = EPI_STG + EPI_WARPS * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
+    // Epilogue warps: 8 (two per TMEM lane quarter) for BN = 64, where the full-resolution layers keep the epilogue ~50 % busy;
+    // 4 for BN = 128, whose epilogue is 75-99 % idle: the 22 KB of staging it gives back buys two more weight stages, and
+    // the weight ring must hold TWO chunks (the waiting issuer polls one chunk ahead of the one being multiplied).
+    static constexpr int EW = BN == 128 ? 4 : 8;
+    static constexpr int EG = EW / 4;                           // warps per TMEM lane quarter = item stride
+    static constexpr int EPI_STG = EW * 32 * 36 * 4;            // per-warp transpose staging
+    static constexpr int EPI = EPI_STG + EW * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BUDGET = 227 * 1024 - EPI - 320;
 #ifndef B200_CONV_SA_MAX
 #define B200_CONV_SA_MAX 3
 #endif
-    static constexpr int SA = (BUDGET - 4 * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2;
+    static constexpr int TGC = TAPS == 9 ? 3 : 1;               // weight stages per chunk
+    // activations: 3 chunks in flight if two chunks of weights still fit next to them, else 2
+    static constexpr int SA = (BUDGET - (2 * TGC - 1) * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2;
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
     static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;   // weight ring: as deep as shared memory allows
     static_assert(SB >= 3, "weight ring too shallow");
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(ACC_FULL(s), 2);     // one commit from each of the two MMA issuer warps
-            mbar_init(ACC_EMPTY(s), EPI_WARPS * 32);
+            mbar_init(ACC_EMPTY(s), C::EW * 32);
         }
         fence_barrier_init();
     }
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
             }
         }
-    } else {
+    } else if (warp < 4 || C::EW == 8) {
         // ------------------------------ epilogue: warps 0-3 and 8-11; warp w reads TMEM lanes 32*(w%4) .. +31 ------------------------------
         // the two warps of a lane quarter split the (row, 32-column slice) work items of a tile between them
         const int ew = warp < 4 ? warp : warp - 4;       // 0..7: epilogue warp index
@@ -422,13 +429,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         // flush the CTA's per-channel partial sums: ONE fp64 atomic pair per channel per (batch, n-tile) change instead of
         // one per warp x row x tile (same-address atomics serialise at L2: 1024 of them per address cost ~100 us)
         auto flush_stats = [&]() {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            named_bar_sync(1, C::EW * 32);
             if (cur_b >= 0) {
                 float* all = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG);
-                for (int ch = ew * 32 + lane; ch < BN; ch += EPI_WARPS * 32) {
+                for (int ch = ew * 32 + lane; ch < BN; ch += C::EW * 32) {
                     float a = 0.f, q = 0.f;
 #pragma unroll
-                    for (int w = 0; w < EPI_WARPS; ++w) {
+                    for (int w = 0; w < C::EW; ++w) {
                         a += all[w * 2 * BN + ch];
                         q += all[w * 2 * BN + BN + ch];
                         all[w * 2 * BN + ch] = 0.f;
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     atomicAdd(st + 1, (double)q);
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            named_bar_sync(1, C::EW * 32);
         };
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             int t = tile;
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             }
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * C::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-            for (int item = egroup; item < NITEM; item += 2) {
+            for (int item = egroup; item < NITEM; item += C::EG) {
                 const int o = item / NSL, sl = item - o * NSL;
                 const int h = h0 + o;
                 const size_t row_base = ((size_t)(b * p.H + h) * p.W + w0 + quarter * 32) * p.Cout;
@@ -489,12 +496,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         for (int j = 0; j < 32; ++j) v[j] += v2[j];
                     }
                     float4 rn[8];      // next item's residual: in flight during this item's transpose / stores
-                    if (do_res && item + 2 < NITEM) {
-                        const float* rp = res_ptr(item + 2);
+                    if (do_res && item + C::EG < NITEM) {
+                        const float* rp = res_ptr(item + C::EG);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
                     }
-                    if (item + 2 >= NITEM) {
+                    if (item + C::EG >= NITEM) {
                         // this warp's TMEM reads of the accumulator set are done -> hand it back to the MMA warp
                         tc_fence_before();
                         mbar_arrive(ACC_EMPTY(buf));
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                         }
                     }
                     __syncwarp();
-                    if (do_res && item + 2 < NITEM) {
+                    if (do_res && item + C::EG < NITEM) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rv[i] = rn[i];
                     }

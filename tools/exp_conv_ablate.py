@@ -18,8 +18,17 @@ SHAPES = [  # B, H, W, Cin, Cout, bn, rows, res
     (8, 16, 512, 128, 128, 128, 1, 0),
     (8, 8, 256, 256, 256, 128, 1, 0),
     (8, 4, 128, 512, 512, 128, 1, 0),
+    (8, 32, 1024, 64, 64, 64, 4, 0),
+    (8, 32, 1024, 64, 64, 64, 1, 0),
+    (8, 16, 512, 128, 128, 128, 2, 0),
+    (8, 8, 256, 256, 256, 128, 2, 0),
+    (8, 4, 128, 512, 512, 128, 2, 0),
+    (8, 16, 512, 128, 128, 64, 2, 0),
+    (8, 8, 256, 256, 256, 64, 2, 0),
+    (8, 4, 128, 512, 512, 64, 2, 0),
+    (8, 4, 128, 512, 512, 64, 1, 0),
 ]
-MASKS = [0, 32, 16]
+MASKS = [0, 64, 16]
 
 
 def main():
