@@ -37,6 +37,23 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // its first global-memory access.  The next kernel's CTAs are then scheduled (and run their prologue: barrier init,
 // TMEM allocation, coefficient setup) while the tail of the previous kernel is still draining.  Opt-in with B200_PDL=1 (measured neutral-to-slightly-negative inside CUDA graphs).
 bool pdl_enabled();
+bool pdl_enabled_conv();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_if(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

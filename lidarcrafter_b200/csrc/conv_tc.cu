@@ -134,13 +134,20 @@ struct ConvCfg {
     static constexpr int EG = EW / 4;                           // warps per TMEM lane quarter = item stride
     static constexpr int EPI_STG = EW * 32 * 36 * 4;            // per-warp transpose staging
     static constexpr int EPI = EPI_STG + EW * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
-    static constexpr int BUDGET = 227 * 1024 - EPI - 320;
+    static constexpr int BAR_BYTES = 448;                       // 4 rings x 12 mbarriers + 4 accumulator barriers + TMEM slot
+    static constexpr int BUDGET = 227 * 1024 - EPI - BAR_BYTES;
 #ifndef B200_CONV_SA_MAX
 #define B200_CONV_SA_MAX 3
 #endif
     static constexpr int TGC = TAPS == 9 ? 3 : 1;               // weight stages per chunk
-    // activations: 3 chunks in flight if two chunks of weights still fit next to them, else 2
-    static constexpr int SA = (BUDGET - (2 * TGC - 1) * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2;
+    // Issue unit of an MMA issuer warp = GRP consecutive K chunks.  A 1x1 conv has only R (x2-3) MMAs per 16-channel chunk
+    // (~200-600 cycles of tensor pipe) against ~1000 cycles of per-visit work of the issuer, so its chunks are visited in
+    // groups; their stages are small, the rings just get deeper (2 groups in flight + 1 chunk of slack).
+    static constexpr int GRP = TAPS == 1 ? (R == 1 ? 4 : (R == 2 ? 2 : 1)) : 1;
+    // 3x3: 3 activation chunks in flight if five weight stages still fit next to them, else 2
+    static constexpr int SA = TAPS == 1 ? 2 * GRP + 1
+                                        : ((BUDGET - (2 * TGC - 1) * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2);
+    static_assert(SA <= 12, "barrier block holds 12 slots per ring");
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
     static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;   // weight ring: as deep as shared memory allows
     static_assert(SB >= 3, "weight ring too shallow");
@@ -148,7 +155,7 @@ struct ConvCfg {
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI;
-    static constexpr int SMEM = OFF_BAR + 320;
+    static constexpr int SMEM = OFF_BAR + BAR_BYTES;
     // MERGE (fp16x3 whenever 2 x R x BN accumulator columns fit twice in TMEM): the weight tile keeps hi and lo rows
     // adjacent ([KG][hi|lo][BN][8]) so that a_hi x [w_hi ; w_lo] is ONE N = 2 BN MMA (A is fetched from shared memory
     // once for 2 BN accumulator columns instead of twice) and only a_lo x w_hi remains an N = BN MMA.  The two partial
@@ -170,13 +177,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + C::OFF_BAR;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 288);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 416);
 #define FULL_A(s) (bar0 + 8u * (s))
-#define EMPTY_A(s) (bar0 + 32u + 8u * (s))
-#define FULL_B(s) (bar0 + 64u + 8u * (s))
-#define EMPTY_B(s) (bar0 + 160u + 8u * (s))
-#define ACC_FULL(s) (bar0 + 256u + 8u * (s))
-#define ACC_EMPTY(s) (bar0 + 272u + 8u * (s))
+#define EMPTY_A(s) (bar0 + 96u + 8u * (s))
+#define FULL_B(s) (bar0 + 192u + 8u * (s))
+#define EMPTY_B(s) (bar0 + 288u + 8u * (s))
+#define ACC_FULL(s) (bar0 + 384u + 8u * (s))
+#define ACC_EMPTY(s) (bar0 + 400u + 8u * (s))
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.Cout / BN, WT = p.W / PIX, HG = p.H / R;
@@ -208,7 +215,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                // everything above (barriers, TMEM) overlapped the previous kernel's tail
+    // everything above (barriers, TMEM) overlapped the previous kernel's tail; so does the weight producer's first ring
+    // fill: packed weights and the zero page are constants of the plan, every other role touches the previous kernels'
+    // outputs and waits for them here
+    if (warp != 6) pdl_wait();
 
     const int ablate = g_conv_ablate;
     (void)ablate;
@@ -303,7 +313,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         // cycle the issuing warp spends NOT issuing (barrier polls ~140 cycles each, fence, election, descriptor moves into
         // uniform registers, commits: 800-1300 cycles per chunk against ~2000 cycles of MMAs) is a cycle the pipe idles --
         // an artificial 300-cycle pause per chunk lengthened the kernel by exactly 300 cycles x chunks.  Hence two issuers:
-        // while one warp's MMAs of chunk g run, the other has already waited for the operands of chunk g + 1 and built
+        // while one warp's MMAs of issue unit g (a K chunk; a group of chunks for 1x1 convs) run, the other has already
+        // waited for the operands of unit g + 1 and built
         // its descriptors, and starts issuing the moment it is handed the turn (named barriers 2 / 3, ~tens of cycles).
         // Each warp runs its loop with uniform control flow (waits included) and one elected lane issues: the descriptor
         // arithmetic stays in uniform registers (one 32-bit add per operand between two tcgen05.mma).  Every warp commits
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             constexpr uint32_t idesc = make_idesc_f16(128, BN);
             constexpr uint32_t idesc2 = make_idesc_f16(128, 2 * BN);
             constexpr uint32_t KGS = C::MERGE ? 2 * BN * 16 : BN * 16;   // byte stride between 8-channel groups of B
-            uint32_t ia = 0, ib = 0, it = 0;
+            uint32_t ia = 0, ib = 0, it = 0, ig = 0;     // chunk / weight-stage / tile / issue-unit counters
             unsigned long long* dbg = (lane == 0 && par == 0) ? g_conv_dbg : nullptr;
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const long long t_start = dbg ? clock64() : 0;
@@ -326,31 +337,39 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 }
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * C::ACC_COLS;
-                for (int c = 0; c < NCH; ++c, ++ia, ib += C::TG) {
-                    if ((ia & 1u) != par) continue;          // the other issuer's chunk
-                    const int sa = ia % C::SA;
+                for (int c = 0; c < NCH; c += C::GRP, ++ig) {
+                    const int ng = min(C::GRP, NCH - c);     // chunks of this issue unit (warp-uniform)
+                    if ((ig & 1u) != par) {                  // the other issuer's unit
+                        ia += ng;
+                        ib += ng * C::TG;
+                        continue;
+                    }
                     // (all 32 lanes poll: a lane-0-only poll + __syncwarp() was measured 25 % SLOWER -- the divergent region
                     // takes the descriptor arithmetic out of the uniform datapath)
                     if (!ABL(1)) {
                         DBG_T0();
-                        mbar_wait(FULL_A(sa), (ia / C::SA) & 1);
+#pragma unroll
+                        for (int g = 0; g < C::GRP; ++g)
+                            if (g < ng) mbar_wait(FULL_A((ia + g) % C::SA), ((ia + g) / C::SA) & 1);
                         DBG_ACC(1);
                     }
                     if (!ABL(2)) {
                         DBG_T0();
 #pragma unroll
-                        for (int dy = 0; dy < C::TG; ++dy) mbar_wait(FULL_B((ib + dy) % C::SB), ((ib + dy) / C::SB) & 1);
+                        for (int q = 0; q < C::GRP * C::TG; ++q)
+                            if (q < ng * C::TG) mbar_wait(FULL_B((ib + q) % C::SB), ((ib + q) / C::SB) & 1);
                         DBG_ACC(2);
                     }
-                    const uint32_t a_lo0 = desc_lo(sbase + C::OFF_A + sa * C::A_STAGE, C::SLAB);
-                    uint32_t b_lo[C::TG];
+                    uint32_t a_lo[C::GRP], b_lo[C::GRP * C::TG];
 #pragma unroll
-                    for (int dy = 0; dy < C::TG; ++dy) b_lo[dy] = desc_lo(sbase + C::OFF_B + ((ib + dy) % C::SB) * C::B_STAGE, KGS);
-                    if (ABL(32)) {   // is this warp's own time hidden now?  (+300 cycles of preparation per chunk)
+                    for (int g = 0; g < C::GRP; ++g) a_lo[g] = desc_lo(sbase + C::OFF_A + ((ia + g) % C::SA) * C::A_STAGE, C::SLAB);
+#pragma unroll
+                    for (int q = 0; q < C::GRP * C::TG; ++q) b_lo[q] = desc_lo(sbase + C::OFF_B + ((ib + q) % C::SB) * C::B_STAGE, KGS);
+                    if (ABL(32)) {   // is this warp's own time hidden now?  (+300 cycles of preparation per unit)
                         const long long t_spin = clock64();
                         while (clock64() - t_spin < 300) {}
                     }
-                    if (ia != 0) {   // my turn: the other issuer has issued chunk ia - 1
+                    if (ig != 0) {   // my turn: the other issuer has issued unit ig - 1
                         DBG_T0();
                         named_bar_sync(2 + par, 64);
                         DBG_ACC(4);
@@ -358,46 +377,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
-                        for (int dy = 0; dy < C::TG; ++dy) {
-                            const uint32_t first_cd = (uint32_t)((c | dy) != 0);
-                            if (!ABL(8))
+                        for (int g = 0; g < C::GRP; ++g) {
+                            if (g < ng) {
 #pragma unroll
-                            for (int dx = 0; dx < C::TW; ++dx) {
+                                for (int dy = 0; dy < C::TG; ++dy) {
+                                    const uint32_t first_cd = (uint32_t)(((c + g) | dy) != 0);
+                                    if (!ABL(8))
 #pragma unroll
-                                for (int o = 0; o < R; ++o) {
+                                    for (int dx = 0; dx < C::TW; ++dx) {
 #pragma unroll
-                                    for (int ks = 0; ks < C::KS; ++ks) {
-                                        // staged input row o + dy feeds output row o through filter row dy
-                                        const uint32_t a_hi = a_lo0 + ((uint32_t)(dy * C::KG * C::SLAB) >> 4) +
-                                                              (((o * C::KG + ks * 2) * C::SLAB + (dx + C::DX0) * 16) >> 4);
-                                        const uint32_t b_hi = b_lo[dy] + ((dx * C::B_TAP + ks * 2 * KGS) >> 4);
-                                        const uint32_t first = (dx | ks) != 0 ? 1u : first_cd;
-                                        const uint32_t d = acc + o * C::ACC_ROW;
-                                        if (C::F8) {
-                                            // plane 1 of both operands: [L8 | A8] x [e4m3(w 2^-11) | e4m3(w_lo)], K = 32
-                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
-                                            tc_mma_f8_lh(d + (C::SEP ? BN : 0), a_hi + (C::A_PART >> 4), b_hi + (C::B_PART >> 4),
-                                                         idesc, C::SEP ? first : 1u);
-                                        } else if (C::MERGE) {
-                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc2, first);                       // [hi*hi | hi*lo]
-                                            tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);        // += lo*hi
-                                        } else {
-                                            tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
-                                            if (NP == 2) {
-                                                tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);
-                                                tc_mma_f16_lh(d, a_hi, b_hi + (C::B_PART >> 4), idesc, 1u);
+                                        for (int o = 0; o < R; ++o) {
+#pragma unroll
+                                            for (int ks = 0; ks < C::KS; ++ks) {
+                                                // staged input row o + dy feeds output row o through filter row dy
+                                                const uint32_t a_hi = a_lo[g] + ((uint32_t)(dy * C::KG * C::SLAB) >> 4) +
+                                                                      (((o * C::KG + ks * 2) * C::SLAB + (dx + C::DX0) * 16) >> 4);
+                                                const uint32_t b_hi = b_lo[g * C::TG + dy] + ((dx * C::B_TAP + ks * 2 * KGS) >> 4);
+                                                const uint32_t first = (dx | ks) != 0 ? 1u : first_cd;
+                                                const uint32_t d = acc + o * C::ACC_ROW;
+                                                if (C::F8) {
+                                                    // plane 1 of both operands: [L8 | A8] x [e4m3(w 2^-11) | e4m3(w_lo)], K = 32
+                                                    tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
+                                                    tc_mma_f8_lh(d + (C::SEP ? BN : 0), a_hi + (C::A_PART >> 4),
+                                                                 b_hi + (C::B_PART >> 4), idesc, C::SEP ? first : 1u);
+                                                } else if (C::MERGE) {
+                                                    tc_mma_f16_lh(d, a_hi, b_hi, idesc2, first);                  // [hi*hi | hi*lo]
+                                                    tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);   // += lo*hi
+                                                } else {
+                                                    tc_mma_f16_lh(d, a_hi, b_hi, idesc, first);
+                                                    if (NP == 2) {
+                                                        tc_mma_f16_lh(d, a_hi + (C::A_PART >> 4), b_hi, idesc, 1u);
+                                                        tc_mma_f16_lh(d, a_hi, b_hi + (C::B_PART >> 4), idesc, 1u);
+                                                    }
+                                                }
                                             }
                                         }
                                     }
+                                    tc_commit(EMPTY_B((ib + g * C::TG + dy) % C::SB));  // weights slot free once these MMAs retire
                                 }
+                                tc_commit(EMPTY_A((ia + g) % C::SA));
                             }
-                            tc_commit(EMPTY_B((ib + dy) % C::SB));  // weights slot free once these MMAs retire
                         }
-                        tc_commit(EMPTY_A(sa));
                     }
                     __syncwarp();
                     tc_fence_before();
                     named_bar_arrive(2 + (par ^ 1u), 64);    // hand the tensor pipe to the other issuer
+                    ia += ng;
+                    ib += ng * C::TG;
                 }
                 // this warp's share of the tile's accumulator is complete when ITS MMAs have retired
                 if (elect_one()) tc_commit(ACC_FULL(buf));
@@ -681,7 +707,7 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     const int tpc = (p.n_tiles + grid - 1) / grid;
     grid = (p.n_tiles + tpc - 1) / tpc;     // no empty CTAs with contiguous chunks
-    launch_pdl(conv_tc_kernel<BN, R, TAPS, NP>, dim3(grid), dim3(CONV_THREADS), (size_t)C::SMEM, st, p);
+    launch_pdl_if(pdl_enabled_conv(), conv_tc_kernel<BN, R, TAPS, NP>, dim3(grid), dim3(CONV_THREADS), (size_t)C::SMEM, st, p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

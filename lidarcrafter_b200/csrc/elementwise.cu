@@ -8,14 +8,20 @@
 namespace b200 {
 
 static thread_local char g_err[512] = "";
-bool pdl_enabled() {
+// B200_PDL=1: every step kernel is launched as a programmatic dependent; B200_PDL=2: only the conv kernels (their
+// prologue -- barrier init, TMEM allocation -- and the weight prefetch do not depend on the previous kernel)
+static int pdl_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("B200_PDL");
-        v = (e && e[0] == '1') ? 1 : 0;   // measured on B200 inside the step graphs: no gain (4.90 vs 4.78 ms), so opt-in
+        // measured on B200 inside the step graph (profiles/r01s2_pdl.txt): all kernels 4.01 ms, none 3.92 ms, conv only
+        // 3.84-3.89 ms -> default 2
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
     }
-    return v == 1;
+    return v;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }
+bool pdl_enabled_conv() { return pdl_mode() >= 1; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
