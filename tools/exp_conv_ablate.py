@@ -15,19 +15,16 @@ from lidarcrafter_b200 import _lib  # noqa: E402
 SHAPES = [  # B, H, W, Cin, Cout, bn, rows, res, taps
     (8, 32, 1024, 64, 64, 64, 2, 0, 9),
     (8, 32, 1024, 64, 64, 64, 2, 1, 9),
+    (8, 32, 1024, 64, 64, 64, 1, 0, 9),
+    (8, 16, 512, 64, 64, 64, 2, 0, 9),
     (8, 16, 512, 128, 128, 128, 1, 0, 9),
     (8, 8, 256, 256, 256, 128, 1, 0, 9),
     (8, 4, 128, 512, 512, 128, 1, 0, 9),
-    (8, 32, 1024, 128, 64, 64, 4, 0, 1),
-    (8, 32, 1024, 128, 64, 64, 2, 0, 1),
-    (8, 16, 512, 256, 64, 64, 4, 0, 1),
-    (8, 16, 512, 256, 64, 64, 2, 0, 1),
-    (8, 4, 128, 512, 1536, 128, 2, 0, 1),
-    (8, 4, 128, 512, 1536, 128, 1, 0, 1),
-    (8, 4, 128, 512, 512, 128, 1, 0, 1),
-    (8, 8, 256, 512, 128, 128, 1, 0, 1),
-    (8, 4, 128, 256, 256, 64, 1, 0, 1),
-    (8, 4, 128, 256, 256, 64, 2, 0, 1),
+    (8, 4, 128, 256, 256, 64, 1, 0, 9),
+    (8, 4, 128, 256, 256, 128, 1, 0, 9),
+    (8, 8, 256, 128, 128, 128, 1, 0, 9),
+    (8, 8, 256, 128, 128, 64, 1, 0, 9),
+    (8, 8, 256, 128, 128, 64, 2, 0, 9),
 ]
 MASKS = [0, 16]
 
