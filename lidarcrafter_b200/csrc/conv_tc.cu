@@ -133,20 +133,20 @@ struct ConvCfg {
     static constexpr int EW = BN == 128 ? 4 : 8;
     static constexpr int EG = EW / 4;                           // warps per TMEM lane quarter = item stride
     static constexpr int EPI_STG = EW * 32 * 36 * 4;            // per-warp transpose staging
-    static constexpr int EPI = EPI_STG + 2 * BN * 4;            // + the CTA's channel sum / sum-of-squares partials
+    static constexpr int EPI = EPI_STG + EW * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BAR_BYTES = 448;                       // 4 rings x 12 mbarriers + 4 accumulator barriers + TMEM slot
     static constexpr int BUDGET = 227 * 1024 - EPI - BAR_BYTES;
 #ifndef B200_CONV_SA_MAX
-#define B200_CONV_SA_MAX 4
+#define B200_CONV_SA_MAX 3
 #endif
     static constexpr int TGC = TAPS == 9 ? 3 : 1;               // weight stages per chunk
     // Issue unit of an MMA issuer warp = GRP consecutive K chunks.  A 1x1 conv has only R (x2-3) MMAs per 16-channel chunk
     // (~200-600 cycles of tensor pipe) against ~1000 cycles of per-visit work of the issuer, so its chunks are visited in
     // groups; their stages are small, the rings just get deeper (2 groups in flight + 1 chunk of slack).
     static constexpr int GRP = TAPS == 1 ? (R == 1 ? 4 : (R == 2 ? 2 : 1)) : 1;
-    // 3x3: up to 4 activation chunks in flight as long as five weight stages still fit next to them
-    static constexpr int SA_FIT = (BUDGET - (2 * TGC - 1) * B_STAGE) / A_STAGE;
-    static constexpr int SA = TAPS == 1 ? 2 * GRP + 1 : (SA_FIT >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : (SA_FIT >= 3 ? 3 : 2));
+    // 3x3: 3 activation chunks in flight if five weight stages still fit next to them, else 2
+    static constexpr int SA = TAPS == 1 ? 2 * GRP + 1
+                                        : ((BUDGET - (2 * TGC - 1) * B_STAGE) / A_STAGE >= B200_CONV_SA_MAX ? B200_CONV_SA_MAX : 2);
     static_assert(SA <= 12, "barrier block holds 12 slots per ring");
     static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
     static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;   // weight ring: as deep as shared memory allows
@@ -448,12 +448,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_start = dbg ? clock64() : 0;
-        // per-CTA channel sum / sum-of-squares partials [2][BN], updated with shared-memory atomics by all epilogue warps
-        // (one array instead of one per warp: the 3.5 KB it returns are what lets the BN = 64, R = 2 tiles stage FOUR
-        // activation chunks -- the full-resolution operands stream from HBM and three were not enough to hide its latency)
-        float* sst = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG);
-        for (int i = ew * 32 + lane; i < 2 * BN; i += C::EW * 32) sst[i] = 0.f;
-        named_bar_sync(1, C::EW * 32);
+        float* sst = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG) + ew * (2 * BN);   // [2][BN] of this warp
+        for (int i = lane; i < 2 * BN; i += 32) sst[i] = 0.f;
+        __syncwarp();
         int cur_b = -1, cur_nt = -1;
         // flush the CTA's per-channel partial sums: ONE fp64 atomic pair per channel per (batch, n-tile) change instead of
         // one per warp x row x tile (same-address atomics serialise at L2: 1024 of them per address cost ~100 us)
@@ -462,9 +459,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             if (cur_b >= 0) {
                 float* all = reinterpret_cast<float*>(smem + C::OFF_EPI + C::EPI_STG);
                 for (int ch = ew * 32 + lane; ch < BN; ch += C::EW * 32) {
-                    const float a = all[ch], q = all[BN + ch];
-                    all[ch] = 0.f;
-                    all[BN + ch] = 0.f;
+                    float a = 0.f, q = 0.f;
+#pragma unroll
+                    for (int w = 0; w < C::EW; ++w) {
+                        a += all[w * 2 * BN + ch];
+                        q += all[w * 2 * BN + BN + ch];
+                        all[w * 2 * BN + ch] = 0.f;
+                        all[w * 2 * BN + BN + ch] = 0.f;
+                    }
                     double* st = p.stats + ((size_t)cur_b * p.Cout + cur_nt * BN + ch) * 2;
                     atomicAdd(st, (double)a);
                     atomicAdd(st + 1, (double)q);
@@ -563,8 +565,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                             const int ch = sl * 32 + col4 * 4;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                atomicAdd(sst + ch + e, s1[e]);
-                                atomicAdd(sst + BN + ch + e, s2[e]);
+                                sst[ch + e] += s1[e];
+                                sst[BN + ch + e] += s2[e];
                             }
                         }
                     }
