@@ -91,6 +91,34 @@ def planes(parts: int) -> int:
 
 
 _TUNE_CACHE: dict = {}
+_TUNE_FILE_LOADED = False
+
+
+def _tune_file():
+    """B200_TUNE_FILE=path.json: persist the measured (bn, rows) choices, so that a second process (e.g. the same bench
+    under ncu, where timing launches is distorted by the profiler) runs exactly the tiles the first one measured."""
+    return os.environ.get("B200_TUNE_FILE", "")
+
+
+def _load_tune_file():
+    global _TUNE_FILE_LOADED
+    if _TUNE_FILE_LOADED:
+        return
+    _TUNE_FILE_LOADED = True
+    path = _tune_file()
+    if path and os.path.exists(path):
+        import json
+        for k, v in json.load(open(path)).items():
+            _TUNE_CACHE[tuple(json.loads(k))] = tuple(v)
+
+
+def _save_tune_file():
+    path = _tune_file()
+    if path:
+        import json
+        with open(path, "w") as f:
+            json.dump({json.dumps([int(x) if not isinstance(x, bool) else x for x in k]): list(v)
+                       for k, v in _TUNE_CACHE.items()}, f)
 
 
 def tile_candidates(B: int, H: int, W: int, Cout: int, parts: int):
@@ -280,6 +308,7 @@ class PlanBuilder:
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
         key = (self.B, H, W, Cin, Cout, taps, self.p.parts, res is not None)
+        _load_tune_file()
         if key in _TUNE_CACHE:
             return _TUNE_CACHE[key]
         if self.p.device.type != "cuda":
@@ -295,19 +324,21 @@ class PlanBuilder:
                     Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
             for _ in range(2):                           # warm-up (function attributes, caches, clocks)
                 self.lib.conv_tc(*args)
-            # minimum of several individually timed launches: a sum over a few launches let power-cap / clock noise
-            # pick a slower tile now and then (seen in an ncu capture: R = 1 chosen for a full-resolution 64 -> 64 conv)
+            # best of 3 batches of 5 back-to-back launches: one batch let power-cap / clock noise pick a slower tile now
+            # and then, single launches are dominated by the launch gap (and by the interception cost under a profiler)
             ms = float("inf")
-            for _ in range(7):
+            for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                self.lib.conv_tc(*args)
+                for _ in range(5):
+                    self.lib.conv_tc(*args)
                 e1.record()
                 e1.synchronize()
                 ms = min(ms, e0.elapsed_time(e1))
             if best is None or ms < best[0]:
                 best = (ms, bn, rows)
         _TUNE_CACHE[key] = (best[1], best[2])
+        _save_tune_file()
         return _TUNE_CACHE[key]
 
     # ---- GroupNorm(+AdaGN)+SiLU -> fp16 operand ----
