@@ -360,9 +360,9 @@ def main():
     ach = (d_by / (d_ms / 1e3) / 1e9) if bound == "hbm" else (d_fl / (d_ms / 1e3) / 1e12)
     peak = pk["hbm_gbs"] if bound == "hbm" else pk["tf"]
     # DRAM traffic of this shape from the committed ncu --set full capture (profiles/), per launch; None if unknown
-    # (profiles/r01s2_ncu_summary.md: 99.9 MB without / 182.6 MB with the residual read, 6 launches each per step; the writes
+    # (profiles/r01s2_ncu_summary.md: 101.8 MB without / 182.2 MB with the residual read, 6 launches each per step; the writes
     # of a launch that are still in L2 when it ends are not in dram__bytes_write)
-    ncu_traffic = {(32, 1024, 64, 64, 9): 1.41e8}.get(dk)
+    ncu_traffic = {(32, 1024, 64, 64, 9): 1.42e8}.get(dk)
     roof = {"bound": bound, "kernel": "conv_tc_kernel %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
                 dk + (dv[3], 100 * dv[0] / tot_ms)),
             "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
