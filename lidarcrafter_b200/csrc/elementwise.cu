@@ -509,6 +509,60 @@ __global__ void __launch_bounds__(256) fir_kernel(const float* __restrict__ x, f
     if (stats) block_channel_reduce(s1, s2, C, b, stats, red);
 }
 
+// FIR x1/2 downsample, two horizontally adjacent outputs per thread: their 4 x 4 input windows share two columns, so the
+// pair needs 24 instead of 32 16-byte loads (the one-output version was load-issue bound: 16 loads per 16 fma4).  Per output
+// the taps are accumulated in the same order with the same weights as fir_kernel<false> (bit-identical results).
+__global__ void __launch_bounds__(256) fir_down_pair_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            double* __restrict__ stats, int H, int W, int C, int ring,
+                                                            int pairs_per_block) {
+    __shared__ float red[256 * 8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Ho = H / 2, Wo = W / 2, Wp = Wo / 2;           // Wo is even (host check)
+    const int b = blockIdx.y;
+    const int c4n = C / 4;
+    const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
+    const int p0 = blockIdx.x * pairs_per_block;
+    const int p1 = min(p0 + pairs_per_block, Ho * Wp);
+    const float* xb = x + (size_t)b * H * W * C + c4 * 4;
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    const float kk[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    for (int pp = p0 + poff; pp < p1; pp += pstep) {
+        const int oh = pp / Wp, ow = (pp - oh * Wp) * 2;
+        float4 acc0 = make_float4(0, 0, 0, 0), acc1 = make_float4(0, 0, 0, 0);
+        int iws[6];
+        bool ok[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            int iw = 2 * ow - 1 + c;
+            ok[c] = true;
+            if (iw < 0) { if (ring) iw += W; else ok[c] = false; }
+            else if (iw >= W) { if (ring) iw -= W; else ok[c] = false; }
+            iws[c] = iw;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ih = 2 * oh - 1 + a;
+            if (ih < 0 || ih >= H) continue;
+            float4 v[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v[c] = ok[c] ? ld4(xb + ((size_t)ih * W + iws[c]) * C) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (ok[c]) fma4(acc0, kk[a] * kk[c], v[c]);
+                if (ok[c + 2]) fma4(acc1, kk[a] * kk[c], v[c + 2]);
+            }
+        }
+        float* yo = y + ((size_t)b * Ho * Wo + (size_t)oh * Wo + ow) * C + c4 * 4;
+        *reinterpret_cast<float4*>(yo) = acc0;
+        *reinterpret_cast<float4*>(yo + C) = acc1;
+        s1.x += acc0.x + acc1.x; s1.y += acc0.y + acc1.y; s1.z += acc0.z + acc1.z; s1.w += acc0.w + acc1.w;
+        s2.x += acc0.x * acc0.x + acc1.x * acc1.x; s2.y += acc0.y * acc0.y + acc1.y * acc1.y;
+        s2.z += acc0.z * acc0.z + acc1.z * acc1.z; s2.w += acc0.w * acc0.w + acc1.w * acc1.w;
+    }
+    if (stats) block_channel_reduce(s1, s2, C, b, stats, red);
+}
+
 // FIR x2 upsample written DIRECTLY as the next conv's operand (Block.forward: Resample(up) -> ring conv,
 // efficient_unet.py:176-190): same taps / summation order as fir_kernel<true>, no fp32 round trip through HBM and no
 // separate cast launch.  Block = one 128-pixel tile of one output row; warp item = 8 pixels x 32 channels.
@@ -1259,6 +1313,16 @@ extern "C" int b200_fir_resample(const float* x, float* y, double* stats, int B,
     int ppb = ST_PIX_PER_BLOCK;
     const int pmin = 256 / (C / 4) > 8 ? 256 / (C / 4) : 8;   // at least one pixel per thread row
     while (ppb > pmin && (long long)cdiv(npo, ppb) * B < 4 * 148) ppb >>= 1;
+    if (!up && (W / 2) % 2 == 0) {      // two outputs per thread
+        const int npairs = npo / 2;
+        int pb = ST_PIX_PER_BLOCK / 2;
+        const int pbmin = 256 / (C / 4) > 4 ? 256 / (C / 4) : 4;
+        while (pb > pbmin && (long long)cdiv(npairs, pb) * B < 4 * 148) pb >>= 1;
+        launch_pdl(fir_down_pair_kernel, dim3(cdiv(npairs, pb), B), dim3(256), 0, (cudaStream_t)stream, x, y, stats, H, W, C,
+                   ring, pb);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     dim3 grid(cdiv(npo, ppb), B);
     if (up) launch_pdl(fir_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, stats, H, W, C, ring, ppb);
     else launch_pdl(fir_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, x, y, stats, H, W, C, ring, ppb);
