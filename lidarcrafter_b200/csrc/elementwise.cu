@@ -785,63 +785,68 @@ constexpr int IC_PIX = 128;
 __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ cst, int cst_batched,
                                                            float* __restrict__ out, double* __restrict__ stats, int H,
-                                                           int W, int Cx, int Cout, int ring) {
+                                                           int W, int Cx, int Cout, int ring, int rows_per_block) {
     __shared__ float red[256 * 8];
     __shared__ float sw[4 * 9 * 128];                 // [ci][tap][co], Cout <= 128
     __shared__ float sx[4 * 3 * (IC_PIX + 2)];        // [ci][dy][pixel + 1]
     pdl_launch_dependents();
     pdl_wait();
-    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * IC_PIX;
+    const int b = blockIdx.z, w0 = blockIdx.x * IC_PIX;
     for (int i = threadIdx.x; i < Cx * 9 * Cout; i += blockDim.x) {
         const int co = i % Cout, r = i / Cout;
         const int tap = r % 9, ci = r / 9;
         sw[i] = w[((size_t)co * Cx + ci) * 9 + tap];
     }
     const int HW = H * W;
-    for (int i = threadIdx.x; i < Cx * 3 * (IC_PIX + 2); i += blockDim.x) {
-        const int px = i % (IC_PIX + 2), r = i / (IC_PIX + 2);
-        const int dy = r % 3, ci = r / 3;
-        const int gh = h + dy - 1;
-        int gw = w0 + px - 1;
-        bool ok = gh >= 0 && gh < H;
-        if (gw < 0) { if (ring) gw += W; else ok = false; }
-        else if (gw >= W) { if (ring) gw -= W; else ok = false; }
-        sx[i] = ok ? x[((size_t)b * Cx + ci) * HW + (size_t)gh * W + gw] : 0.f;
-    }
-    __syncthreads();
     // thread = 4 output channels x (128 / pstep) pixels px = poff + i * pstep: every weight float4 read from shared
     // memory feeds all of the thread's pixels (one-pixel-at-a-time was LDS-bound: ncu l1tex 69 %, 75 us on B200)
     const int c4n = Cout / 4;
     const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
     constexpr int PB = 8;                              // pixels per register batch
-    for (int pb = poff; pb < IC_PIX; pb += PB * pstep) {
-        float4 acc[PB];
-#pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            const int px = pb + i * pstep;
-            acc[i] = px < IC_PIX ? ld4(cst + ((size_t)(cst_batched ? b : 0) * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4)
-                                 : make_float4(0, 0, 0, 0);
+    // several image rows per block: the weight staging above and the statistics reduction below are paid once
+    const int h_end = min((int)(blockIdx.y + 1) * rows_per_block, H);
+    for (int h = blockIdx.y * rows_per_block; h < h_end; ++h) {
+        __syncthreads();                               // the previous row's sx has been consumed
+        for (int i = threadIdx.x; i < Cx * 3 * (IC_PIX + 2); i += blockDim.x) {
+            const int px = i % (IC_PIX + 2), r = i / (IC_PIX + 2);
+            const int dy = r % 3, ci = r / 3;
+            const int gh = h + dy - 1;
+            int gw = w0 + px - 1;
+            bool ok = gh >= 0 && gh < H;
+            if (gw < 0) { if (ring) gw += W; else ok = false; }
+            else if (gw >= W) { if (ring) gw -= W; else ok = false; }
+            sx[i] = ok ? x[((size_t)b * Cx + ci) * HW + (size_t)gh * W + gw] : 0.f;
         }
-        for (int ci = 0; ci < Cx; ++ci) {
+        __syncthreads();
+        for (int pb = poff; pb < IC_PIX; pb += PB * pstep) {
+            float4 acc[PB];
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const float4 wv = *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4);
-                const float* xr = sx + (ci * 3 + tap / 3) * (IC_PIX + 2) + tap % 3;
+            for (int i = 0; i < PB; ++i) {
+                const int px = pb + i * pstep;
+                acc[i] = px < IC_PIX ? ld4(cst + ((size_t)(cst_batched ? b : 0) * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4)
+                                     : make_float4(0, 0, 0, 0);
+            }
+            for (int ci = 0; ci < Cx; ++ci) {
 #pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    const int px = pb + i * pstep;
-                    if (px < IC_PIX) fma4(acc[i], xr[px], wv);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float4 wv = *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4);
+                    const float* xr = sx + (ci * 3 + tap / 3) * (IC_PIX + 2) + tap % 3;
+#pragma unroll
+                    for (int i = 0; i < PB; ++i) {
+                        const int px = pb + i * pstep;
+                        if (px < IC_PIX) fma4(acc[i], xr[px], wv);
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < PB; ++i) {
-            const int px = pb + i * pstep;
-            if (px >= IC_PIX) continue;
-            *reinterpret_cast<float4*>(out + ((size_t)b * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4) = acc[i];
-            s1.x += acc[i].x; s1.y += acc[i].y; s1.z += acc[i].z; s1.w += acc[i].w;
-            s2.x += acc[i].x * acc[i].x; s2.y += acc[i].y * acc[i].y; s2.z += acc[i].z * acc[i].z; s2.w += acc[i].w * acc[i].w;
+            for (int i = 0; i < PB; ++i) {
+                const int px = pb + i * pstep;
+                if (px >= IC_PIX) continue;
+                *reinterpret_cast<float4*>(out + ((size_t)b * HW + (size_t)h * W + w0 + px) * Cout + c4 * 4) = acc[i];
+                s1.x += acc[i].x; s1.y += acc[i].y; s1.z += acc[i].z; s1.w += acc[i].w;
+                s2.x += acc[i].x * acc[i].x; s2.y += acc[i].y * acc[i].y; s2.z += acc[i].z * acc[i].z; s2.w += acc[i].w * acc[i].w;
+            }
         }
     }
     if (stats) block_channel_reduce(s1, s2, Cout, b, stats, red);
@@ -1363,9 +1368,11 @@ extern "C" int b200_in_conv(const float* x, const float* w, const float* cst, in
     B200_CHECK_ARG(x && w && cst && out);
     B200_CHECK_ARG(Cx >= 1 && Cx <= 4 && Cout <= 256 && c4_ok(Cout));
     if (W % IC_PIX == 0 && Cout <= 128) {
-        dim3 grid(W / IC_PIX, H, B);
+        int rpb = 4;                                   // rows per block, as long as the grid still fills the GPU twice
+        while (rpb > 1 && (long long)(W / IC_PIX) * cdiv(H, rpb) * B < 2 * 148) rpb >>= 1;
+        dim3 grid(W / IC_PIX, cdiv(H, rpb), B);
         launch_pdl(in_conv_rows_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, w, cst, cst_batched, out, stats, H, W,
-                   Cx, Cout, ring);
+                   Cx, Cout, ring, rpb);
         B200_CHECK_LAUNCH();
         return B200_OK;
     }

@@ -127,3 +127,25 @@ def test_repaint_matches_reference(emu, nres, jump):
                      rng=torch.Generator().manual_seed(55))
     ref = torch.from_numpy(golden("repaint_mini")[f"repaint_{nres}_{jump}"])
     assert rel_l2(x, ref) < 1e-3
+
+
+def test_tile_choices_persist_through_the_tune_file(tmp_path, monkeypatch):
+    """B200_TUNE_FILE: the measured (bn, rows) choices survive a process boundary (a profiled run must execute the
+    tiles the plain run measured); keys are (B, H, W, Cin, Cout, taps, parts, has_residual)."""
+    from lidarcrafter_b200 import engine
+    path = tmp_path / "tiles.json"
+    monkeypatch.setenv("B200_TUNE_FILE", str(path))
+    saved = dict(engine._TUNE_CACHE)
+    try:
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_CACHE[(8, 32, 1024, 64, 64, 9, 2, True)] = (64, 2)
+        engine._TUNE_CACHE[(8, 4, 128, 512, 512, 9, 2, False)] = (128, 1)
+        engine._save_tune_file()
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_FILE_LOADED = False
+        engine._load_tune_file()
+        assert engine._TUNE_CACHE == {(8, 32, 1024, 64, 64, 9, 2, True): (64, 2), (8, 4, 128, 512, 512, 9, 2, False): (128, 1)}
+    finally:
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_CACHE.update(saved)
+        engine._TUNE_FILE_LOADED = False
