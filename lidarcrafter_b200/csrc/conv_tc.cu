@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // everything above (barriers, TMEM) overlapped the previous kernel's tail; so does the weight producer's first ring
-    // fill: packed weights and the zero page are constants of the plan, every other role touches the previous kernels'
-    // outputs and waits for them here
-    if (warp != 6) pdl_wait();
+    // everything above (barriers, TMEM) overlapped the previous kernel's tail.  (Letting the weight producer skip this wait
+    // -- packed weights are constants of a plan -- measured no gain and would be wrong when a conv directly follows the
+    // kernel that packs its weights, as in the tile autotune and the kernel tests.)
+    pdl_wait();
 
     const int ablate = g_conv_ablate;
     (void)ablate;
