@@ -248,6 +248,9 @@ class PlanBuilder:
         # (profiles/r01_fused_gn_tail.txt): the tail runs with 12 warps/SM from L2 and costs what the separate gn_act
         # launch costs (step 4.07 ms fused vs 3.92 ms unfused), so the default keeps the separate launch.
         self.fuse_gn = os.environ.get("B200_FUSE_GN", "0") == "1"
+        # B200_FUSE_GN_MAX_PIX=n: fuse only where B*H*W <= n (the small levels, where a separate gn_act launch is mostly
+        # launch latency); measured in profiles/r01s2_fuse_gn_levels.txt
+        self.fuse_gn_max_pix = int(os.environ.get("B200_FUSE_GN_MAX_PIX", "0"))
 
     # ---- conv on tensor cores (or the FFMA cross-check path) ----
     def conv(self, a16: torch.Tensor, H: int, W: int, weight, bias, res: torch.Tensor | None, scale: float,
@@ -272,7 +275,8 @@ class PlanBuilder:
             self.p.bufs.append(pc)
             base = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale), 1.0 / pc.wscale, _ptr(out),
                     _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows, self.p.parts)
-            if gn is not None and self.fuse_gn and bn % (Cout // gn["groups"]) == 0:
+            fuse = self.fuse_gn or (self.fuse_gn_max_pix > 0 and npix <= self.fuse_gn_max_pix)
+            if gn is not None and fuse and bn % (Cout // gn["groups"]) == 0:
                 y = self.p.operand(H, W, Cout)
                 g = None if gn.get("gamma") is None else gn["gamma"].detach().float().contiguous()
                 b = None if gn.get("beta") is None else gn["beta"].detach().float().contiguous()

@@ -1,3 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 300 -p no:cacheprovider -k "in_conv or out_conv" 2>&1 | tail -2
-timeout 600 python -m pytest tests/test_gpu_unet.py tests/test_gpu_layout.py -m gpu -q -x --timeout 300 -p no:cacheprovider 2>&1 | tail -2
-python bench.py --steps 30 --warmup 3 --no-cpu-baseline --profile-ops 2>/tmp/err.txt | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'])"; grep "fir_resample\|in_conv \|out_conv " /tmp/err.txt
+for v in "B200_FUSE_GN_MAX_PIX=0" "B200_FUSE_GN_MAX_PIX=4096" "B200_FUSE_GN_MAX_PIX=16384" "B200_FUSE_GN_MAX_PIX=65536" "B200_FUSE_GN_MAX_PIX=0"; do
+  echo "== $v"; env $v python bench.py --steps 30 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['kernels_per_step'], d['clocks'])"
+done
