@@ -185,3 +185,22 @@ def test_sampler_coefficient_kernel_vs_torch_expressions(schedule, kw):
         assert torch.allclose(lt.cpu(), lt_ref, rtol=2e-5, atol=2e-5)
         # (c2 = sqrt(1 - a_s^2 - c1^2) is NaN on both sides where rounding makes the argument slightly negative)
         assert torch.allclose(coef.cpu(), coef_ref, rtol=1e-4, atol=2e-6, equal_nan=True), (coef.cpu() - coef_ref).abs().max()
+
+
+@pytest.mark.parametrize("res,B", [((64, 1024), 1), ((16, 2048), 3), ((32, 1024), 1)])
+def test_other_resolutions_and_batch_sizes_vs_oracle(res, B):
+    """The kernels are generic in H, W % 128 == 0 and B: the KITTI range image (64 x 1024, lidargen/metrics DATASET_CONFIG),
+    a wide 16 x 2048 image with an odd batch, and the one-sample-per-GPU case of configs[4] -- against the CPU oracle
+    (pinned to the reference by tests/golden), same 1e-3 tolerance."""
+    nres = (1, 1, 1, 1)
+    m, sd = make_unet(res, nres, seed=3)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, 2, *res, generator=g)
+    t = torch.linspace(-6.0, 7.0, B)
+    y = m(x.cuda(), t.cuda()).cpu()
+    cfg = O.EfficientUNetCfg(resolution=res, num_residual_blocks=nres)
+    ref = O.efficient_unet_forward(sd, x, t, cfg)
+    err = rel_l2(y, ref)
+    print(res, B, "rel-L2 vs oracle:", err)
+    assert err < TOL
