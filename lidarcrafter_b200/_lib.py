@@ -127,6 +127,11 @@ def set_test_lib(lib) -> None:
     _TEST_LIB = lib
 
 
+def compute_device() -> str:
+    """"cuda" on the product path; "cpu" only while tests/ have injected the C-ABI emulator (set_test_lib)."""
+    return "cuda" if _TEST_LIB is None else "cpu"
+
+
 def current_stream(device) -> int:
     import torch
     if _TEST_LIB is not None and device.type != "cuda":

@@ -27,13 +27,13 @@ DATASET_CONFIG = {'kitti': {'size': [64, 1024], 'fov': [3, -25], 'depth_range': 
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return 0 if _lib.compute_device() == "cpu" else torch.cuda.current_stream().cuda_stream
 
 
 def _dev(x, dtype=torch.float32):
     is_np = isinstance(x, np.ndarray)
     t = torch.from_numpy(np.ascontiguousarray(x)) if is_np else x
-    return t.to(device="cuda", dtype=dtype).contiguous(), is_np
+    return t.to(device=_lib.compute_device(), dtype=dtype).contiguous(), is_np
 
 
 def _ret(t, is_np):
@@ -187,7 +187,7 @@ def pcd2bev_sum(data_type, *args, voxel_size=VOXEL_SIZE):
     for data in args:
         is_np = len(data) > 0 and isinstance(data[0], np.ndarray)
         clouds = [_dev(p)[0] for p in data]
-        vol = torch.zeros(shape, dtype=torch.float32, device="cuda")
+        vol = torch.zeros(shape, dtype=torch.float32, device=_lib.compute_device())
         if clouds:
             lens = [int(c.shape[0]) for c in clouds]
             stride = min(int(c.shape[1]) for c in clouds)

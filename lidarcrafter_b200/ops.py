@@ -9,10 +9,14 @@ import torch
 from . import _lib
 
 
+def _stream():
+    return 0 if _lib.compute_device() == "cpu" else torch.cuda.current_stream().cuda_stream
+
+
 def _dev(x, dtype=torch.float32):
     is_np = isinstance(x, np.ndarray)
     t = torch.from_numpy(np.ascontiguousarray(x)) if is_np else x
-    return t.to(device="cuda", dtype=dtype).contiguous(), is_np
+    return t.to(device=_lib.compute_device(), dtype=dtype).contiguous(), is_np
 
 
 def load_points_as_images(point_path: str = None, points=None, scan_unfolding: bool = False, H: int = 64, W: int = 2048,
@@ -38,7 +42,7 @@ def load_points_as_images(point_path: str = None, points=None, scan_unfolding: b
     grid = torch.empty(F, M, 2, dtype=torch.int32, device=pts.device) if return_grid else None
     _lib.get_lib().range_project(pts.data_ptr(), 0, out.data_ptr(), 0 if grid is None else grid.data_ptr(),
                                  zbuf.data_ptr(), F, M, H, W, float(min_depth), float(max_depth), float(fov_up),
-                                 float(fov_down), torch.cuda.current_stream().cuda_stream)
+                                 float(fov_down), _stream())
     if single:
         out = out[0]
         grid = None if grid is None else grid[0]
@@ -61,7 +65,7 @@ def points_in_boxes_cpu(points, boxes):
     out = torch.zeros(bx.shape[0], pts.shape[0], dtype=torch.int32, device=pts.device)
     if bx.shape[0] and pts.shape[0]:
         _lib.get_lib().points_in_boxes(pts.data_ptr(), bx.data_ptr(), out.data_ptr(), bx.shape[0], pts.shape[0],
-                                       torch.cuda.current_stream().cuda_stream)
+                                       _stream())
     return out.cpu().numpy() if is_np else out
 
 
@@ -73,7 +77,7 @@ def points_in_boxes_gpu(points, boxes):
     B, M, _ = pts.shape
     out = torch.full((B, M), -1, dtype=torch.int32, device=pts.device)
     _lib.get_lib().points_in_boxes_first(pts.data_ptr(), bx.data_ptr(), out.data_ptr(), B, bx.shape[1], M,
-                                         torch.cuda.current_stream().cuda_stream)
+                                         _stream())
     return out
 
 
@@ -84,5 +88,5 @@ def voxel_index(points, rois, out_size):
     ox, oy, oz = (out_size,) * 3 if isinstance(out_size, int) else out_size
     out = torch.empty(bx.shape[0], pts.shape[0], dtype=torch.int32, device=pts.device)
     _lib.get_lib().voxel_index(pts.data_ptr(), bx.data_ptr(), out.data_ptr(), bx.shape[0], pts.shape[0], ox, oy, oz,
-                               torch.cuda.current_stream().cuda_stream)
+                               _stream())
     return out.cpu().numpy() if is_np else out

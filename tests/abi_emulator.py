@@ -437,3 +437,140 @@ class EmulatedLib:
             o = a_s * (xt * (1 - cc) / a_t + cc * x0) + s_s * cc.sqrt() * f32(noise, B, n)
         f32(x_s, B, n).copy_(o)
         return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# point-cloud side of the ABI (K6 / K7 / K8): backed by the C oracle (oracle/lidar_ops.c, oracle/metrics_ops.c),
+# so that the HOST mirrors (lidarcrafter_b200/ops.py, metric_utils.py: batching, bounds, list / dtype handling,
+# workspace sizing) run end to end without a GPU.
+# ---------------------------------------------------------------------------------------------------------
+def i64(ptr, *shape):
+    t = _arr(ptr, math.prod(shape), ctypes.c_int64, np.int64)
+    return None if t is None else t.view(*shape)
+
+
+def _host_ints(obj, n):
+    """a ctypes int32 array (host pointer argument of the ABI) -> list of python ints"""
+    return [int(obj[i]) for i in range(n)]
+
+
+def _install_pointcloud_entries():
+    from oracle import lidar_ops as LO
+    from oracle import metrics_ops as MO
+
+    def range_project(self, points, npts, out, grid, zbuf, F, M, H, W, min_d, max_d, fov_up, fov_down, stream):
+        self._rec("range_project")
+        pts, o = f32(points, F, M, 4), f32(out, F, H, W, 6)
+        g = i32(grid, F, M, 2)
+        for f in range(F):
+            img, gr, _ = LO.range_project(pts[f].numpy(), H, W, min_d, max_d, fov_up, fov_down)
+            o[f] = torch.from_numpy(img)
+            if g is not None:
+                g[f] = torch.from_numpy(gr)
+        return 0
+
+    def points_in_boxes(self, pts, boxes, out, N, M, stream):
+        self._rec("points_in_boxes")
+        i32(out, N, M).copy_(torch.from_numpy(LO.points_in_boxes(f32(pts, M, 3).numpy(), f32(boxes, N, 7).numpy())))
+        return 0
+
+    def points_in_boxes_first(self, pts, boxes, out, B, N, M, stream):
+        self._rec("points_in_boxes_first")
+        i32(out, B, M).copy_(torch.from_numpy(LO.points_in_boxes_first(f32(pts, B, M, 3).numpy(), f32(boxes, B, N, 7).numpy())))
+        return 0
+
+    def voxel_index(self, pts, rois, out, N, M, ox, oy, oz, stream):
+        self._rec("voxel_index")
+        i32(out, N, M).copy_(torch.from_numpy(LO.voxel_index(f32(pts, M, 3).numpy(), f32(rois, N, 7).numpy(), (ox, oy, oz))))
+        return 0
+
+    def pcd2range(self, pcd, npts, feature, proj_range, proj_feature, zbuf, F, M, H, W, fov_up, fov_down, dmin, dmax, fill,
+                  stream):
+        self._rec("pcd2range")
+        p, ft = f32(pcd, F, M, 3), f32(feature, F, M)
+        r, pf = f32(proj_range, F, H, W), f32(proj_feature, F, H, W)
+        for f in range(F):
+            rr, ff, _ = MO.pcd2range(p[f].numpy(), (H, W), (fov_up, fov_down), (dmin, dmax),
+                                     feature=None if ft is None else ft[f].numpy(), fill=fill)
+            r[f] = torch.from_numpy(rr)
+            if pf is not None:
+                pf[f] = torch.from_numpy(ff)
+        return 0
+
+    def range2xyz(self, img, xyz, F, H, W, fov_up, fov_down, dmin, dmax, depth_scale, log_scale, stream):
+        self._rec("range2xyz")
+        im, o = f32(img, F, H, W), f64(xyz, F, 3, H, W)
+        for f in range(F):
+            o[f] = torch.from_numpy(MO.range2xyz(im[f].numpy(), (fov_up, fov_down), (dmin, dmax), depth_scale, bool(log_scale)))
+        return 0
+
+    def quantize_coords(self, coords, is_f64, M, D, stride, v0, v1, v2, div_f32, voxel, minmax, stream):
+        self._rec("quantize_coords")
+        c = (f64 if is_f64 else f32)(coords, M, stride)[:, :D].numpy()
+        v = MO.quantize(np.ascontiguousarray(c), (v0, v1, v2)[:D], bool(div_f32))
+        i32(voxel, M, D).copy_(torch.from_numpy(v))
+        mm = i32(minmax, 6)
+        mm[:D] = torch.from_numpy(v.min(0))
+        mm[3:3 + D] = torch.from_numpy(v.max(0))
+        return 0
+
+    def sparse_quantize_workspace(self, minmax_host, D, M):
+        mm = _host_ints(minmax_host, 6)
+        cells = 1
+        for d in range(D):
+            cells *= mm[3 + d] - mm[d] + 1
+        return 0 if cells > (1 << 35) else 256 + 8 * M       # the emulator sorts; it only mirrors the size limit
+
+    def ravel_hash(self, voxel, M, D, minmax_host, out, stream):
+        self._rec("ravel_hash")
+        keys, _, _, _ = MO.sparse_quantize(i32(voxel, M, D).numpy())
+        i64(out, M).copy_(torch.from_numpy(keys.view(np.int64)))
+        return 0
+
+    def sparse_quantize(self, voxel, M, D, minmax_host, ws, ws_bytes, uniq, indices, inverse, n_unique, stream):
+        self._rec("sparse_quantize")
+        _, u, idx, inv = MO.sparse_quantize(i32(voxel, M, D).numpy())
+        n = len(u)
+        i32(n_unique, 1)[0] = n
+        if uniq:
+            i32(uniq, M, D)[:n] = torch.from_numpy(u)
+        if indices:
+            i64(indices, M)[:n] = torch.from_numpy(idx)
+        if inverse:
+            i64(inverse, M).copy_(torch.from_numpy(inv))
+        return 0
+
+    def bev_occupancy_sum(self, pcd, offsets, n_clouds, max_pts, stride, x0, x1, y0, y1, voxel, mbx, mby, X, Y, bitmap_ws,
+                          volume_sum, stream):
+        self._rec("bev_occupancy_sum")
+        off = i32(offsets, n_clouds + 1).numpy()
+        base = int(off[0])
+        pts = f32(pcd, int(off[-1]), stride).numpy()
+        clouds = [pts[off[c]:off[c + 1]] for c in range(n_clouds)]
+        lo, hi = np.array([x0, y0], np.float32), np.array([x1, y1], np.float32)
+        vol = np.zeros((X, Y), np.float32)
+        cat = np.ascontiguousarray(np.concatenate(clouds), dtype=np.float32) if clouds else np.zeros((0, stride), np.float32)
+        o = (off - base).astype(np.int32)
+        LO.lib().oracle_bev_sum(LO._p(cat), LO._p(o), n_clouds, stride, LO._p(lo), LO._p(hi), ctypes.c_float(voxel),
+                                LO._p(np.array([mbx, mby], np.int32)), LO._p(np.array([X, Y], np.int32)), LO._p(vol))
+        f32(volume_sum, X, Y).add_(torch.from_numpy(vol))
+        return 0
+
+    def voxel_occupancy(self, pcd, M, stride, lohi_host, voxel, minb_host, dims_host, vol, stream):
+        self._rec("voxel_occupancy")
+        lohi = [float(lohi_host[i]) for i in range(6)]
+        minb, dims = _host_ints(minb_host, 3), _host_ints(dims_host, 3)
+        pts = np.ascontiguousarray(f32(pcd, M, stride).numpy(), dtype=np.float32)
+        out = np.zeros(dims, np.float32)
+        LO.lib().oracle_voxel_full(LO._p(pts), M, stride, LO._p(np.array(lohi[0::2], np.float32)),
+                                   LO._p(np.array(lohi[1::2], np.float32)), ctypes.c_float(voxel),
+                                   LO._p(np.array(minb, np.int32)), LO._p(np.array(dims, np.int32)), LO._p(out))
+        f32(vol, *dims).copy_(torch.from_numpy(out))
+        return 0
+
+    for fn in (range_project, points_in_boxes, points_in_boxes_first, voxel_index, pcd2range, range2xyz, quantize_coords,
+               sparse_quantize_workspace, ravel_hash, sparse_quantize, bev_occupancy_sum, voxel_occupancy):
+        setattr(EmulatedLib, fn.__name__, fn)
+
+
+_install_pointcloud_entries()
