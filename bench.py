@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["fp16x3", "fp16f8", "fp16"])
+    ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU,
+                    help="frames per GPU (default 8 = BASELINE configs[1]; other values are side measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--profiler-range", action="store_true",
@@ -186,8 +188,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    B = BATCH_PER_GPU
-    cfg = {"workload": "configs[1]: EfficientUNet (nuscenes-unet-uncond) 32x1024, DDIM eta=0, batch 8 per GPU",
+    B = args.batch_per_gpu
+    cfg = {"workload": f"configs[1]: EfficientUNet (nuscenes-unet-uncond) 32x1024, DDIM eta=0, batch {B} per GPU",
            "batch_per_gpu": B, "global_batch": B * world, "resolution": list(RES),
            "l2": "per-step working set ~3 GB of activations per GPU >> 126 MB L2 (inputs larger than L2)"}
 

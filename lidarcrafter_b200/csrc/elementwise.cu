@@ -1349,16 +1349,19 @@ extern "C" int b200_time_embed(const float* t, const float* w1, const float* b1,
                                const float* temb_add, const float* wp, const float* bp, float* temb, float* ada, int B,
                                int Cs, int E, int P, void* stream) {
     B200_CHECK_ARG(t && w1 && b1 && w2 && b2 && temb);
-    B200_CHECK_ARG(B > 0 && B <= ADA_MAX_B && Cs % 2 == 0 && Cs >= 4);
+    B200_CHECK_ARG(B > 0 && B <= 65535 && Cs % 2 == 0 && Cs >= 4);
     launch_pdl(temb_kernel, dim3(B, cdiv(E, TEMB_EO)), dim3(256), (Cs + E) * sizeof(float), (cudaStream_t)stream, t, w1, b1,
                w2, b2, temb_add, temb, Cs, E);
     B200_CHECK_LAUNCH();
     if (P > 0) {
         B200_CHECK_ARG(wp && bp && ada);
-        B200_CHECK_ARG((size_t)B * E * sizeof(float) <= 48 * 1024);
-        launch_pdl(ada_proj_kernel, dim3(cdiv(P, ADA_ROWS_PER_BLOCK)), dim3(256), (size_t)B * E * sizeof(float),
-                   (cudaStream_t)stream, (const float*)temb, wp, bp, ada, B, E, P);
-        B200_CHECK_LAUNCH();
+        B200_CHECK_ARG((size_t)ADA_MAX_B * E * sizeof(float) <= 48 * 1024);
+        for (int b0 = 0; b0 < B; b0 += ADA_MAX_B) {      // the kernel keeps one accumulator per sample in registers
+            const int nb = B - b0 < ADA_MAX_B ? B - b0 : ADA_MAX_B;
+            launch_pdl(ada_proj_kernel, dim3(cdiv(P, ADA_ROWS_PER_BLOCK)), dim3(256), (size_t)nb * E * sizeof(float),
+                       (cudaStream_t)stream, (const float*)temb + (size_t)b0 * E, wp, bp, ada + (size_t)b0 * P, nb, E, P);
+            B200_CHECK_LAUNCH();
+        }
     }
     return B200_OK;
 }

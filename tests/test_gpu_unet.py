@@ -187,10 +187,11 @@ def test_sampler_coefficient_kernel_vs_torch_expressions(schedule, kw):
         assert torch.allclose(coef.cpu(), coef_ref, rtol=1e-4, atol=2e-6, equal_nan=True), (coef.cpu() - coef_ref).abs().max()
 
 
-@pytest.mark.parametrize("res,B", [((64, 1024), 1), ((16, 2048), 3), ((32, 1024), 1)])
+@pytest.mark.parametrize("res,B", [((64, 1024), 1), ((16, 2048), 3), ((32, 1024), 1), ((8, 1024), 24)])
 def test_other_resolutions_and_batch_sizes_vs_oracle(res, B):
     """The kernels are generic in H, W % 128 == 0 and B: the KITTI range image (64 x 1024, lidargen/metrics DATASET_CONFIG),
-    a wide 16 x 2048 image with an odd batch, and the one-sample-per-GPU case of configs[4] -- against the CPU oracle
+    a wide 16 x 2048 image with an odd batch, the one-sample-per-GPU case of configs[4], and a batch above the 16 samples
+    one AdaGN-projection launch handles -- against the CPU oracle
     (pinned to the reference by tests/golden), same 1e-3 tolerance."""
     nres = (1, 1, 1, 1)
     m, sd = make_unet(res, nres, seed=3)
