@@ -389,7 +389,7 @@ def main():
             "gpu_launches": K * (plan.plan.n_kernels + 1), "kernels_per_step": plan.plan.n_kernels + 1,
             "roofline": roof,
             "algorithmic_gflop_per_sample_step": plan.plan.flops / B / 1e9}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         v, dt, cores = cpu_reference_run(1, 1, B)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"1 DDIM step at batch {B} after 1 warm-up step ({dt:.1f} s)"}
