@@ -150,8 +150,8 @@ def ravel_hash(x):
 
 def sparse_quantize(coords, voxel_size=1, *, return_index: bool = False, return_inverse: bool = False):
     """metric_utils.py:44-62 (torchsparse semantics): unique voxel coordinates in ravel-hash order."""
-    c, is_np = _dev(coords, dtype=torch.float64 if (isinstance(coords, np.ndarray) and coords.dtype == np.float64) or
-                    (torch.is_tensor(coords) and coords.dtype == torch.float64) else torch.float32)
+    is_f64 = coords.dtype in (np.float64, torch.float64)      # fp64 coordinates are quantised in fp64, everything else in fp32
+    c, is_np = _dev(coords, dtype=torch.float64 if is_f64 else torch.float32)
     if isinstance(voxel_size, (float, int)):
         voxel_size = tuple(repeat(voxel_size, c.shape[1]))
     assert isinstance(voxel_size, tuple) and len(voxel_size) in [2, 3]
