@@ -4,8 +4,8 @@ lidargen/models/diffusion/{base,continuous_time,continuous_time_cond}.py).
 Public surface kept from the reference: constructor kwargs, ``sampling_shape``, ``device``, ``randn`` /
 ``randn_like`` (None | Generator | per-sample list), ``log_snr``, ``q_step_from_x_0``, ``q_step``,
 ``p_step`` and ``sample`` with the exact reference signatures; ``p_sample_loop`` is an alias of
-``sample`` (BASELINE.json's wording).  Training (``forward`` / ``p_loss``) is out of scope for the
-hot path and raises.
+``sample`` (BASELINE.json's wording).  ``forward`` / ``p_loss`` EVALUATE the training loss (no gradient:
+the kernel plans have no backward; training itself is SURVEY section 8f rank 4, out of scope).
 
 One denoiser step = the model's static kernel plan + one fused sampler-update kernel; ``sample``
 captures that step in a CUDA graph and replays it ``num_steps`` times.
@@ -106,10 +106,31 @@ class GaussianDiffusion(nn.Module):
     def setup_parameters(self) -> None:
         raise NotImplementedError
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("training loss / backward is out of scope of the B200 hot path (SURVEY 8f-4)")
+    # ---- loss EVALUATION (base.py:119-151): forward only -- the kernel plans have no backward, so this is the validation
+    # loss of a checkpoint, not a training step (SURVEY 8f-4 stays out of scope) ----
+    def _criterion(self, prediction: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if isinstance(self.loss_type, nn.Module):
+            return self.loss_type(prediction, target)
+        if self.loss_type == "l2":
+            return (prediction - target) ** 2
+        if self.loss_type == "l1":
+            return (prediction - target).abs()
+        return nn.functional.smooth_l1_loss(prediction, target, reduction="none")      # "huber" (base.py:45-46)
 
-    p_loss = forward
+    @torch.inference_mode()
+    def p_loss(self, x_0: torch.Tensor, steps: torch.Tensor, loss_mask: torch.Tensor | None = None) -> torch.Tensor:
+        loss_mask = torch.ones_like(x_0) if loss_mask is None else loss_mask
+        x_t, noise = self.q_step_from_x_0(x_0, steps)
+        prediction = self.model(x_t, self.get_network_condition(steps))
+        loss = self._criterion(prediction, self.get_target(x_0, steps, noise))       # (B,C,H,W)
+        loss = (loss * loss_mask).flatten(1).sum(dim=1, keepdim=True)
+        loss = loss / loss_mask.flatten(1).sum(dim=1, keepdim=True).add(1e-8)         # (B,1)
+        return (loss * self.get_loss_weight(steps)).mean()
+
+    @torch.inference_mode()
+    def forward(self, x_0: torch.Tensor, loss_mask: torch.Tensor | None = None) -> torch.Tensor:
+        steps = self.sample_timesteps(x_0.shape[0], x_0.device)
+        return self.p_loss(x_0, steps, loss_mask)
 
 
 class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
@@ -156,6 +177,25 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
 
     def get_network_condition(self, steps):
         return self.log_snr(steps)[:, 0, 0, 0]
+
+    def get_target(self, x_0, step_t, noise):
+        """continuous_time.py:142-153"""
+        if self.objective == "eps":
+            return noise
+        if self.objective == "x_0":
+            return x_0
+        alpha, sigma = _log_snr_to_alpha_sigma(self.log_snr(step_t))
+        return alpha * noise - sigma * x_0
+
+    def get_loss_weight(self, steps):
+        """continuous_time.py:155-169 (min-SNR-gamma weighting); shape [B,1,1,1] like the reference"""
+        snr = self.log_snr(steps).exp()
+        clipped = snr.clamp(max=self.min_snr_gamma) if self.min_snr_loss_weight else snr
+        if self.objective == "eps":
+            return clipped / snr
+        if self.objective == "x_0":
+            return clipped
+        return clipped / (snr + 1)
 
     def q_step_from_x_0(self, x_0, step_t, rng=None):
         noise = self.randn_like(x_0, rng=rng)
@@ -371,6 +411,12 @@ class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
         self.w_loss_weight = w_loss_weight
         if self.cond_mode == "concat":
             self.sampling_shape = (self.model.in_channels - condition_model.out_channels, *self.sampling_shape[1:])
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("the layout-conditioned training loss (continuous_time_cond.py:414-455) is not part of the "
+                                  "B200 hot path (SURVEY 8f-4)")
+
+    p_loss = forward
 
     def get_network_condition(self, steps=None, input_dict=None, only_custom_condition=False):
         other_condition = self.condition_model(input_dict)

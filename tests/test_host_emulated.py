@@ -149,3 +149,26 @@ def test_tile_choices_persist_through_the_tune_file(tmp_path, monkeypatch):
         engine._TUNE_CACHE.clear()
         engine._TUNE_CACHE.update(saved)
         engine._TUNE_FILE_LOADED = False
+
+
+@pytest.mark.parametrize("objective,criterion,minsnr", [("eps", "l2", True), ("v", "l1", True), ("x_0", "huber", False)])
+def test_loss_evaluation_matches_reference(emu, objective, criterion, minsnr):
+    """forward() / p_loss() (no gradient) against the reference's loss values (tests/golden/loss_mini.npz): same RNG draw
+    order (timesteps, then noise), same min-SNR weighting and -- deliberately -- the reference's [B,1] x [B,1,1,1] broadcast
+    of loss and weight (base.py:150)."""
+    res, nres, B = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres)
+    d = golden("loss_mini")
+    ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type=objective, loss_type=criterion, noise_schedule="cosine",
+                                             min_snr_loss_weight=minsnr)
+    x0 = torch.randn(B, 2, *res, generator=torch.Generator().manual_seed(99)).clamp(-1, 1)
+    mask = (torch.rand(B, 2, *res, generator=torch.Generator().manual_seed(98)) > 0.3).float()
+    key = f"{objective}_{criterion}"
+    torch.manual_seed(4321)
+    assert abs(float(ddpm(x0)) - d[key + "_forward"][0]) < 2e-4 * abs(d[key + "_forward"][0])
+    torch.manual_seed(4321)
+    assert abs(float(ddpm(x0, loss_mask=mask)) - d[key + "_forward_masked"][0]) < 2e-4 * abs(d[key + "_forward_masked"][0])
+    steps = torch.tensor([0.25, 0.8])
+    torch.manual_seed(7)
+    assert abs(float(ddpm.p_loss(x0, steps)) - d[key + "_p_loss"][0]) < 2e-4 * abs(d[key + "_p_loss"][0])
+    assert torch.allclose(ddpm.get_loss_weight(steps).reshape(-1), torch.from_numpy(d[key + "_weight"]), rtol=1e-5)
