@@ -171,6 +171,15 @@ def cpu_reference_run(steps: int, warmup: int, B: int):
     return B * steps / dt, dt, torch.get_num_threads()
 
 
+def conv_shape(name, a):
+    """(H, W, Cin, Cout, taps, bn, rows) of a conv launch of the plan (b200_conv_tc / b200_conv_gn_tc argument lists)"""
+    if name == "conv_tc":
+        return a[9], a[10], a[11], a[12], a[13], a[15], a[16]
+    if name == "conv_gn_tc":
+        return a[21], a[22], a[1] + a[3], a[23], a[24], a[26], a[27]
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,8 +320,8 @@ def main():
     if args.profile_ops:
         shapes = {}
         for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
-            if name == "conv_tc":      # args: a, w, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts
-                key = "conv %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (a[9], a[10], a[11], a[12], a[13], a[15], a[16])
+            if conv_shape(name, a):
+                key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a))
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += 1
             elif name == "gn_act_f16":  # args: x0, C0, x1, C1, st0, st1, g, b, ada, stride, groups, eps, silu, y, parts, B, H, W
                 key = "gn_act %2dx%-4d C%-4d norm%d raw%d" % (a[17], a[18], a[1] + a[3], 1 if a[4] else 0, 1 if a[14] else 0)
@@ -323,7 +332,7 @@ def main():
         waits = {}
         st = torch.cuda.current_stream(dev).cuda_stream
         for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
-            if name != "conv_tc":
+            if not conv_shape(name, a):
                 continue
             dbg.zero_()
             lib.conv_set_debug(dbg.data_ptr())
@@ -332,7 +341,7 @@ def main():
             lib.conv_set_debug(0)
             d = dbg.view(148, 8).double()
             d = d[d[:, 0] > 0]
-            key = "conv %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (a[9], a[10], a[11], a[12], a[13], a[15], a[16])
+            key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a))
             w = waits.setdefault(key, [0.0] * 5)
             w[0] += float(d[:, 0].mean()); w[1] += float(d[:, 1].mean()); w[2] += float(d[:, 2].mean())
             w[3] += float(d[:, 3].mean()); w[4] += float(d[:, 5].mean())
@@ -345,14 +354,14 @@ def main():
         for name, v in sorted(by.items(), key=lambda kv: -kv[1][0]):
             print(f"  {name:20s} n={v[3]:4d} {v[0]:8.3f} ms  {100 * v[0] / tot_ms:5.1f}%  "
                   f"{v[1] / max(v[0], 1e-9) / 1e9:8.1f} TFLOP/s  {v[2] / max(v[0], 1e-9) / 1e6:8.1f} GB/s", file=sys.stderr)
-    c = by.get("conv_tc", [1e-9, 0, 0, 1])
+    c = [sum(by.get(n, [0, 0, 0, 0])[i] for n in ("conv_tc", "conv_gn_tc")) for i in range(4)]
     # tensor-pipe time units per algorithmic product (1 unit = one fp16 MMA; the e4m3 K=32 correction MMA of fp16f8 = 1)
     mma_per_product = {"fp16x3": 3, "fp16f8": 2, "fp16": 1}[args.precision]
     # dominant kernel = the conv shape with the largest share of the step (per-launch numbers)
     dom = {}
     for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
-        if name == "conv_tc":
-            key = (a[9], a[10], a[11], a[12], a[13])
+        if conv_shape(name, a):
+            key = conv_shape(name, a)[:5]
             d = dom.setdefault(key, [0.0, 0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += by_k; d[3] += 1
     dk, dv = max(dom.items(), key=lambda kv: kv[1][0])
     d_ms, d_fl, d_by = dv[0] / dv[3], dv[1] / dv[3], dv[2] / dv[3]

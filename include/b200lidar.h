@@ -60,18 +60,24 @@ const char* b200_last_error(void);
 int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
                  float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
                  int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
-/* b200_conv_tc + fused GroupNorm(+AdaGN)(+SiLU) tail: replaces  conv -> nn.GroupNorm / AdaGN -> SiLU  of
- * ResidualBlock.forward (models/unets/efficient_unet.py:104-111; layout_unet_v1.py:229-243) in ONE launch.  After all tiles
- * are written (out, stats as b200_conv_tc; stats must be non-NULL and zero on entry) the CTAs meet at a grid-wide barrier
- * (the grid is <= one CTA per SM and co-resident by construction), then every CTA re-reads the tiles it produced (L2
- * hits), normalises them with the now complete statistics and writes y = the conv operand (layout above, y_parts planes)
- * that b200_gn_act_f16(out, stats, gamma, beta, ada, ...) would have written -- same arguments, same result.
- * Needs bn % (Cout / groups) == 0 (every group inside one n-tile).                                      */
-int b200_conv_tc_gn(const void* a, const void* wpacked, const float* bias, const float* res,
-                    float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
-                    int Cout, int taps, int ring, int bn, int rows, int parts, const float* gamma,
-                    const float* beta, const float* ada, int ada_stride, int groups, float eps, int silu,
-                    void* y, int y_parts, void* stream);
+/* GroupNorm(+AdaGN)-apply + SiLU + operand split fused IN FRONT of b200_conv_tc: replaces  conv(silu(norm(x)))  of
+ * ResidualBlock.forward (models/unets/efficient_unet.py:104-115, ops.py:176-200; layout_unet_v1.py:229-249), the GroupNorm
+ * -> QKV projection of the attention blocks (efficient_unet.py:46-49) and the plain fp32 -> operand casts in ONE launch.
+ * The A operand never exists in HBM: four transform warps of the conv kernel read the fp32 NHWC activation
+ *   x = x0 [B,H*W,C0] (| x1 [B,H*W,C1], channel concatenation; x1 NULL <=> C1 == 0; C0 % 16 == C1 % 16 == 0),
+ * apply  y = act(x * a_c + b_c)  with the per-(sample, channel) coefficients of GroupNorm(groups, eps)[*gamma + beta]
+ * [*(1 + ada[b, c]) + ada[b, Cin + c]] computed in the kernel from the COMPLETE per-channel statistics stats0 / stats1
+ * (fp64 {sum, sum of squares} [B,C,2], as accumulated by the producing kernel; stats0 NULL: no normalisation, a = 1,
+ * b = 0), act = SiLU if silu else identity, split y into the operand planes of `parts` (2: fp16 hi + lo; 3: fp16 hi +
+ * e4m3 pair) and write them straight into the K-major shared-memory slab (rows above / below the image and non-ring edges
+ * are exact zeros) that the tcgen05 issuers read.  Everything after the operand is b200_conv_tc: same wpacked / bias /
+ * res / out / stats / tiles, Cin = C0 + C1 <= 1024, groups <= 32.  Result == b200_gn_act_f16 followed by b200_conv_tc
+ * (bit-identical operands).  512 threads per CTA, register file re-balanced with setmaxnreg.            */
+int b200_conv_gn_tc(const float* x0, int C0, const float* x1, int C1, const double* stats0,
+                    const double* stats1, const float* gamma, const float* beta, const float* ada,
+                    int ada_stride, int groups, float eps, int silu, const void* wpacked, const float* bias,
+                    const float* res, float out_scale, float w_inv, float* out, double* stats, int B, int H,
+                    int W, int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
 /* profiling aid: device buffer of [#CTAs][8] uint64 cycle counters filled by b200_conv_tc (NULL disables; see
  * conv_tc.cu g_conv_dbg for the slot meaning).  Not used on the product path.                          */
 int b200_conv_set_debug(void* dbg_u64);

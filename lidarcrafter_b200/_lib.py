@@ -24,7 +24,7 @@ PROTOTYPES = {
     "b200_device_check": (I, [I]),
     "b200_last_error": (C.c_char_p, []),
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
-    "b200_conv_tc_gn": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, I, I, F, I, P, I, P]),
+    "b200_conv_gn_tc": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, P]),
     "b200_conv_set_debug": (I, [P]),
     "b200_conv_set_ablate": (I, [I]),
     "b200_packed_weight_elems": (SZ, [I, I, I, I]),

@@ -48,40 +48,20 @@ struct ConvParams {
     float w_inv;  // 1 / (power-of-two scale applied to the packed weights)
     int B, H, W, Cin, Cout, ring;
     int n_tiles;
-    // optional fused tail (b200_conv_tc_gn): after a grid-wide barrier every CTA re-reads the tiles it produced (L2 hits),
-    // applies GroupNorm(+AdaGN)(+SiLU) with the now complete statistics and writes the next conv's operand
-    __half* gn_y;             // nullptr: no tail
+    // fused front end (b200_conv_gn_tc, template FUSE): the A operand is produced IN the kernel from the fp32 NHWC
+    // activation(s) x0 [B,H*W,C0] (| x1 [B,H*W,C1]: channel concat) -- GroupNorm(+AdaGN)-apply with the complete per-channel
+    // statistics st0 / st1 (fp64 {sum, sumsq} [B,C,2]; nullptr: no normalisation), optional SiLU, fp16 hi/lo (or e4m3 pair)
+    // split -- by four transform warps that write the K-major shared-memory slab the MMA issuers read.
+    const float* x0;
+    const float* x1;
+    const double* st0;
+    const double* st1;
     const float* gn_gamma;
     const float* gn_beta;
     const float* gn_ada;
-    int gn_ada_stride, gn_groups, gn_silu, gn_parts;
+    int C0, C1, gn_ada_stride, gn_groups, gn_silu;
     float gn_eps;
-    unsigned* gn_bar;         // {arrival count, generation} of this launch's barrier slot
 };
-
-__device__ unsigned g_gn_bar[64 * 2];   // barrier slots handed out round-robin by the host (one per launch in flight)
-
-// Grid-wide barrier for a grid that is co-resident by construction (<= one CTA per SM, checked on the host).  Bounded
-// spin: a scheduling assumption that does not hold becomes a trap (launch error), not a hung GPU.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n) {
-    volatile unsigned* vgen = bar + 1;
-    const unsigned gen = *vgen;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == n - 1) {
-        bar[0] = 0;
-        __threadfence();
-        atomicAdd(bar + 1, 1u);
-    } else {
-        unsigned spins = 0;
-        while (*vgen == gen) {
-            if (++spins > (1u << 27)) {
-                printf("b200lidar: grid barrier timeout (block %d)\n", blockIdx.x);
-                __trap();
-            }
-        }
-    }
-    __threadfence();
-}
 
 __device__ __align__(128) unsigned char g_zero_page[16384];  // source of zero-padding rows / pixels
 
@@ -103,11 +83,17 @@ __device__ int g_conv_ablate = 0;
 #define DBG_ACC(slot) do { if (dbg) dbg_acc[slot] += clock64() - t0__; } while (0)
 
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
-constexpr int CONV_THREADS = 384;   // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: A producer; 5: MMA; 6: B producer
+constexpr int CONV_THREADS = 384;   // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: A producer; 5, 7: MMA; 6: B producer
+constexpr int FUSE_THREADS = 512;   // fused front end: + warps 12-15 = transform warps (they replace the A producer)
+constexpr int XF_WARPS = 4;
+constexpr int MAX_CIN = 1024;       // per-channel GroupNorm coefficients kept in shared memory by the fused front end
 constexpr int EPI_WARPS_MAX = 8;   // warps 0-3 and 8-11; ConvCfg::EW of them work (BN = 128 tiles: 4, see ConvCfg)
 
-template <int BN, int R, int TAPS, int NP>
+template <int BN, int R, int TAPS, int NP, bool FUSE = false>
 struct ConvCfg {
+    static_assert(!FUSE || NP == 2 || NP == 3, "fused front end: fp16x3 / fp16f8 operands only");
+    static constexpr int THREADS = FUSE ? FUSE_THREADS : CONV_THREADS;
+    static constexpr int COEF = FUSE ? 2 * 4 * MAX_CIN + 256 : 0;   // s_a[MAX_CIN], s_b[MAX_CIN], {mean, rstd}[32]
     static constexpr int PL = NP == 1 ? 1 : 2;    // operand planes (hi | lo or fp8 pair)
     static constexpr bool F8 = NP >= 3;
     static constexpr bool SEP = NP == 4;
@@ -135,7 +121,7 @@ struct ConvCfg {
     static constexpr int EPI_STG = EW * 32 * 36 * 4;            // per-warp transpose staging
     static constexpr int EPI = EPI_STG + EW * 2 * BN * 4;       // + per-warp channel sum / sum-of-squares partials
     static constexpr int BAR_BYTES = 448;                       // 4 rings x 12 mbarriers + 4 accumulator barriers + TMEM slot
-    static constexpr int BUDGET = 227 * 1024 - EPI - BAR_BYTES;
+    static constexpr int BUDGET = 227 * 1024 - EPI - BAR_BYTES - COEF;
 #ifndef B200_CONV_SA_MAX
 #define B200_CONV_SA_MAX 3
 #endif
@@ -154,7 +140,8 @@ struct ConvCfg {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int OFF_EPI = OFF_B + SB * B_STAGE;
-    static constexpr int OFF_BAR = OFF_EPI + EPI;
+    static constexpr int OFF_COEF = OFF_EPI + EPI;
+    static constexpr int OFF_BAR = OFF_COEF + COEF;
     static constexpr int SMEM = OFF_BAR + BAR_BYTES;
     // MERGE (fp16x3 whenever 2 x R x BN accumulator columns fit twice in TMEM): the weight tile keeps hi and lo rows
     // adjacent ([KG][hi|lo][BN][8]) so that a_hi x [w_hi ; w_lo] is ONE N = 2 BN MMA (A is fetched from shared memory
@@ -170,9 +157,245 @@ struct ConvCfg {
     static_assert(ROWB <= 16384, "zero page too small");
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// fused front end (FUSE): GroupNorm(+AdaGN)-apply + SiLU + fp16 hi/lo (or e4m3 pair) split, straight into the A ring
+// ---------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// read-only activation load that does not allocate in the (small: 256 KB - 227 KB of shared memory) L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float* ptr) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+
+// Four transform warps produce every A stage (one 16-channel K chunk of the R + 2 halo rows of a tile):
+//   lane -> (8-channel group g = lane / 16, pixel slot p8 = (lane / 2) % 8, channel quad = lane % 2): one item = 16 pixels x
+//   16 channels = two 16-byte loads per lane (pixels p8 and p8 + 8; a warp-level load covers 8 pixels x 64 contiguous bytes)
+//   and per pixel one 8-byte store into the fp16 hi slab + one 8-byte (lo) or two 4-byte (L8, A8) stores into plane 1 --
+//   every warp-level store covers 128 contiguous bytes of a slab (conflict-free).  Items of a stage: 8 per staged row (body
+//   pixels) + one for the 2 x RA ring-halo pixels.  Loads of the NEXT batch of items are issued before the math of the
+//   current one (register double buffer), across stage / tile boundaries too, so the L2 / HBM latency overlaps the math.
 template <int BN, int R, int TAPS, int NP>
-__global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvParams p) {
-    using C = ConvCfg<BN, R, TAPS, NP>;
+__device__ __forceinline__ void xform_warps(const ConvParams& p, uint8_t* smem, uint32_t sbase, uint32_t bar0, int tw,
+                                            int lane, int tile_lo, int tile_hi) {
+    using C = ConvCfg<BN, R, TAPS, NP, true>;
+    constexpr int RA = C::RA, HALO = C::HALO, KC = C::KC;
+    constexpr int NBODY = RA * 8;
+    constexpr int NIT = NBODY + (TAPS == 9 ? 1 : 0);        // items per stage
+    constexpr int IPW = (NIT + XF_WARPS - 1) / XF_WARPS;    // items per warp and stage
+    constexpr int NU = (IPW % 3 == 0 && IPW % 4 != 0) ? 3 : (IPW < 4 ? IPW : 4);   // items per batch
+    constexpr int NB = (IPW + NU - 1) / NU;                 // batches per stage
+    static_assert(KC == 16 && RA * 2 <= 16, "fused front end geometry");
+    float* s_a = reinterpret_cast<float*>(smem + C::OFF_COEF);
+    float* s_b = s_a + MAX_CIN;
+    float* s_mr = s_b + MAX_CIN;                            // {mean, rstd} per group
+    const int g = lane >> 4, p8 = (lane >> 1) & 7, q = lane & 1;
+    const int co = g * 8 + q * 4;                           // this lane's 4 channels inside the 16-channel chunk
+    const int WT = p.W / PIX, HG = p.H / R, NT = p.Cout / BN, NCH = p.Cin / KC;
+    const int xt = tw * 32 + lane;                          // 0..127 among the transform threads
+    const int Ctot = p.Cin;
+
+    struct Cur { int tile, c, k; };
+    auto advance = [&](Cur c) {
+        if (++c.k == NB) { c.k = 0; if (++c.c == NCH) { c.c = 0; ++c.tile; } }
+        return c;
+    };
+    // geometry of pixel j (0, 1) of item `it`: staged row r, slab position pos, source pixel (gh, ww), write / non-zero flags
+    auto geom = [&](int it, int j, int h0, int w0, int& r, int& pos, int& gh, int& ww, bool& wr, bool& nz) {
+        if (it < NBODY) {
+            r = it >> 3;
+            pos = 1 + ((it & 7) << 4) + j * 8 + p8;
+            ww = w0 + pos - 1;
+            wr = true; nz = true;
+        } else {
+            const int sp = j * 8 + p8;
+            r = sp >> 1;
+            const int side = sp & 1;
+            pos = side ? OPX - 1 : 0;
+            ww = side ? w0 + PIX : w0 - 1;
+            wr = r < RA; nz = wr;
+            if (ww < 0) { ww += p.W; nz = nz && p.ring; }
+            else if (ww >= p.W) { ww -= p.W; nz = nz && p.ring; }
+        }
+        gh = h0 + r - HALO;
+        nz = nz && gh >= 0 && gh < p.H;
+    };
+    auto tile_geom = [&](int tile, int& b, int& h0, int& w0) {
+        int t = tile;
+        const int wt = t % WT; t /= WT;
+        const int hg = t % HG; t /= HG;
+        b = t / NT;
+        h0 = hg * R; w0 = wt * PIX;
+    };
+    auto load = [&](const Cur& cu, float4 (&buf)[NU][2]) {
+        int b, h0, w0;
+        tile_geom(cu.tile, b, h0, w0);
+        const int cbase = cu.c * KC;
+        const float* src;
+        int Cs;
+        if (cbase < p.C0) { src = p.x0 + cbase + co; Cs = p.C0; }
+        else { src = p.x1 + (cbase - p.C0) + co; Cs = p.C1; }
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int it = tw + (cu.k * NU + u) * XF_WARPS;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                buf[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it < NIT) {
+                    int r, pos, gh, ww;
+                    bool wr, nz;
+                    geom(it, j, h0, w0, r, pos, gh, ww, wr, nz);
+                    if (nz) buf[u][j] = ldg_stream_f4(src + ((size_t)(b * p.H + gh) * p.W + ww) * Cs);
+                }
+            }
+        }
+    };
+
+    uint32_t ia = 0;
+    int cur_b = -1;
+    float ca[4] = {1.f, 1.f, 1.f, 1.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+    const int silu = p.gn_silu;
+
+    // per-channel affine coefficients of GroupNorm(+AdaGN) for sample b: y = x * s_a[c] + s_b[c] (same fp32 expression
+    // order as gn_act_kernel: the fused and the separate path give bit-identical operands)
+    auto coefficients = [&](int b) {
+        named_bar_sync(4, XF_WARPS * 32);        // every transform warp is done with the previous sample's coefficients
+        if (p.st0 != nullptr) {
+            const int cpg = Ctot / p.gn_groups;
+            for (int gi = tw; gi < p.gn_groups; gi += XF_WARPS) {      // one warp per group, lanes over its channels
+                double su = 0.0, ss = 0.0;
+                for (int i = lane; i < cpg; i += 32) {
+                    const int c = gi * cpg + i;
+                    const double* st = c < p.C0 ? p.st0 + ((size_t)b * p.C0 + c) * 2 : p.st1 + ((size_t)b * p.C1 + (c - p.C0)) * 2;
+                    su += st[0];
+                    ss += st[1];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    su += __shfl_xor_sync(0xffffffffu, su, o);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                }
+                if (lane == 0) {
+                    const double n = (double)p.H * p.W * cpg;
+                    const double mean = su / n;
+                    double var = ss / n - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    s_mr[2 * gi] = (float)mean;
+                    s_mr[2 * gi + 1] = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+                }
+            }
+            named_bar_sync(4, XF_WARPS * 32);
+            for (int c = xt; c < Ctot; c += XF_WARPS * 32) {
+                const int gi = c / cpg;
+                float a = s_mr[2 * gi + 1], bb = -s_mr[2 * gi] * s_mr[2 * gi + 1];
+                float ga = 1.f, be = 0.f, sc = 1.f, sh = 0.f;
+                if (p.gn_gamma) { ga = p.gn_gamma[c]; be = p.gn_beta[c]; }
+                if (p.gn_ada) {
+                    sc = 1.f + p.gn_ada[(size_t)b * p.gn_ada_stride + c];
+                    sh = p.gn_ada[(size_t)b * p.gn_ada_stride + Ctot + c];
+                }
+                a *= ga; bb = bb * ga + be;
+                a *= sc; bb = bb * sc + sh;
+                s_a[c] = a;
+                s_b[c] = bb;
+            }
+        } else {
+            for (int c = xt; c < Ctot; c += XF_WARPS * 32) { s_a[c] = 1.f; s_b[c] = 0.f; }
+        }
+        named_bar_sync(4, XF_WARPS * 32);
+    };
+
+    auto compute = [&](const Cur& cu, float4 (&buf)[NU][2]) {
+        int b, h0, w0;
+        tile_geom(cu.tile, b, h0, w0);
+        const uint32_t s = ia % C::SA;
+        if (cu.k == 0) {
+            if (b != cur_b) {            // (tiles of a CTA are contiguous: a few sample changes per launch at most)
+                coefficients(b);
+                cur_b = b;
+            }
+            mbar_wait(bar0 + 96u + 8u * s, ((ia / C::SA) & 1) ^ 1);       // EMPTY_A(s)
+            const float4 a4 = *reinterpret_cast<const float4*>(s_a + cu.c * KC + co);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b + cu.c * KC + co);
+            ca[0] = a4.x; ca[1] = a4.y; ca[2] = a4.z; ca[3] = a4.w;
+            cb[0] = b4.x; cb[1] = b4.y; cb[2] = b4.z; cb[3] = b4.w;
+        }
+        const uint32_t stage = sbase + C::OFF_A + s * C::A_STAGE;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int it = tw + (cu.k * NU + u) * XF_WARPS;
+            if (it >= NIT) continue;                 // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int r, pos, gh, ww;
+                bool wr, nz;
+                geom(it, j, h0, w0, r, pos, gh, ww, wr, nz);
+                const float4 x4 = buf[u][j];
+                float y[4] = {fmaf(x4.x, ca[0], cb[0]), fmaf(x4.y, ca[1], cb[1]), fmaf(x4.z, ca[2], cb[2]),
+                              fmaf(x4.w, ca[3], cb[3])};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (silu) y[e] = silu_f(y[e]);
+                    if (!nz) y[e] = 0.f;             // zero padding (rows outside the image, non-ring edges) is exact
+                }
+                const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const float lo[4] = {y[0] - f01.x, y[1] - f01.y, y[2] - f23.x, y[3] - f23.y};
+                if (!wr) continue;
+                const uint32_t row = stage + r * C::ROWB + pos * 16;
+                sts_v2(row + g * C::SLAB + q * 8, *reinterpret_cast<const uint32_t*>(&h01),
+                       *reinterpret_cast<const uint32_t*>(&h23));
+                if (NP == 2) {
+                    const __half2 l01 = __floats2half2_rn(lo[0], lo[1]), l23 = __floats2half2_rn(lo[2], lo[3]);
+                    sts_v2(row + C::A_PART + g * C::SLAB + q * 8, *reinterpret_cast<const uint32_t*>(&l01),
+                           *reinterpret_cast<const uint32_t*>(&l23));
+                } else {
+                    // plane 1 of a 16-channel chunk: slab 0 = L8 = e4m3(lo * 2^11), slab 1 = A8 = e4m3(x), 16 bytes per pixel each
+                    sts_b32(row + C::A_PART + co, f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE,
+                                                       lo[3] * F8_LO_SCALE));
+                    sts_b32(row + C::A_PART + C::SLAB + co, f8x4(y[0], y[1], y[2], y[3]));
+                }
+            }
+        }
+        if (cu.k == NB - 1) {
+            fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8u * s);                    // FULL_A(s): one arrival per transform warp
+            ++ia;
+        }
+    };
+
+    Cur cu{tile_lo, 0, 0};
+    float4 buf0[NU][2], buf1[NU][2];
+    if (cu.tile < tile_hi) load(cu, buf0);
+    while (cu.tile < tile_hi) {
+        Cur nx = advance(cu);
+        if (nx.tile < tile_hi) load(nx, buf1);
+        compute(cu, buf0);
+        cu = nx;
+        if (cu.tile >= tile_hi) break;
+        nx = advance(cu);
+        if (nx.tile < tile_hi) load(nx, buf0);
+        compute(cu, buf1);
+        cu = nx;
+    }
+}
+
+template <int BN, int R, int TAPS, int NP, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc_kernel(const ConvParams p) {
+    using C = ConvCfg<BN, R, TAPS, NP, FUSE>;
     constexpr int KC = C::KC;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -196,7 +419,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::SA; ++s) {
-            mbar_init(FULL_A(s), 1);
+            mbar_init(FULL_A(s), FUSE ? XF_WARPS : 1);   // fused: one arrival per transform warp; else the expect_tx of the TMA producer
             mbar_init(EMPTY_A(s), 1);
         }
         for (int s = 0; s < C::SB; ++s) {
@@ -222,7 +445,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 
     const int ablate = g_conv_ablate;
     (void)ablate;
-    if (warp == 4) {
+    // Role dispatch by WARPGROUP first: the fused variant re-balances the register file with setmaxnreg (65536 / 512 = 128
+    // per thread at launch; the epilogue warpgroups need ~168: 32 accumulator + 2 x 32 residual prefetch registers; the
+    // issuers / weight producer ~56; the transform warps 120), and every warp of a warpgroup must execute the same
+    // setmaxnreg, which must dominate the code that uses the registers.
+    const int wg = warp >> 2;
+    if (wg == 3) {
+        if constexpr (FUSE) {
+            reg_dealloc<120>();
+            xform_warps<BN, R, TAPS, NP>(p, smem, sbase, bar0, warp - 12, lane, tile_lo, tile_hi);
+        }
+    } else if (wg == 1) {
+    if constexpr (FUSE) reg_dealloc<56>();
+    if (warp == 4 && !FUSE) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
         uint32_t ia = 0;
         unsigned long long* dbg = g_conv_dbg;
@@ -436,7 +671,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
                 dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
             }
         }
-    } else if (warp < 4 || C::EW == 8) {
+    }
+    } else {
+    if constexpr (FUSE) reg_alloc<168>();
+    if (warp < 4 || C::EW == 8) {
         // ------------------------------ epilogue: warps 0-3 and 8-11; warp w reads TMEM lanes 32*(w%4) .. +31 ------------------------------
         // the two warps of a lane quarter split the (row, 32-column slice) work items of a tile between them
         const int ew = warp < 4 ? warp : warp - 4;       // 0..7: epilogue warp index
@@ -584,103 +822,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
             dbg[blockIdx.x * 8 + 5] = dbg_acc[5];
         }
     }
+    }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         __syncwarp();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
-    }
-    if (p.gn_y != nullptr) {
-        // ------------------------------ fused GroupNorm(+AdaGN)+SiLU tail ------------------------------
-        __threadfence();           // this CTA's output stores and statistics atomics are visible device-wide ...
-        __syncthreads();
-        if (threadIdx.x == 0) grid_barrier(p.gn_bar, gridDim.x);   // ... before anyone reads the complete statistics
-        __syncthreads();
-        float* s_a = reinterpret_cast<float*>(smem + C::OFF_EPI);   // [BN] (the epilogue staging area is free now)
-        float* s_b = s_a + BN;                                      // [BN]
-        float* s_mr = s_b + BN;                                     // [2 * BN / cpg] mean, rstd
-        const int cpg = p.Cout / p.gn_groups;                       // BN % cpg == 0 (host check)
-        const int WTo = p.W / OTW, c8n = p.Cout / 8;
-        const size_t lo_off = (size_t)p.B * p.H * WTo * c8n * OPX * 8;
-        const int px = lane >> 2, g = lane & 3;
-        constexpr int QN = BN / 32, NIT = R * 16 * QN, NW = CONV_THREADS / 32;
-        int cur_b = -1, cur_nt = -1;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
-            int t = tile;
-            const int wt = t % WT; t /= WT;
-            const int hg = t % HG; t /= HG;
-            const int nt = t % NT;
-            const int b = t / NT;
-            const int h0 = hg * R, n0 = nt * BN;
-            if (b != cur_b || nt != cur_nt) {      // per-channel affine coefficients of (sample b, channels n0 .. n0 + BN)
-                cur_b = b; cur_nt = nt;
-                __syncthreads();
-                if ((int)threadIdx.x < BN / cpg) {
-                    const double* st = p.stats + ((size_t)b * p.Cout + n0 + threadIdx.x * cpg) * 2;
-                    double su = 0.0, ss = 0.0;
-                    for (int c = 0; c < cpg; ++c) { su += __ldcg(st + 2 * c); ss += __ldcg(st + 2 * c + 1); }
-                    const double n = (double)p.H * p.W * cpg;
-                    const double mean = su / n;
-                    double var = ss / n - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    s_mr[2 * threadIdx.x] = (float)mean;
-                    s_mr[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)p.gn_eps));
-                }
-                __syncthreads();
-                if ((int)threadIdx.x < BN) {
-                    const int c = n0 + threadIdx.x, gi = threadIdx.x / cpg;
-                    float a = s_mr[2 * gi + 1], bb = -s_mr[2 * gi] * s_mr[2 * gi + 1];
-                    if (p.gn_gamma) { a *= p.gn_gamma[c]; bb = bb * p.gn_gamma[c] + p.gn_beta[c]; }
-                    if (p.gn_ada) {
-                        const float sc = 1.f + p.gn_ada[(size_t)b * p.gn_ada_stride + c];
-                        const float sh = p.gn_ada[(size_t)b * p.gn_ada_stride + p.Cout + c];
-                        a *= sc; bb = bb * sc + sh;
-                    }
-                    s_a[threadIdx.x] = a;
-                    s_b[threadIdx.x] = bb;
-                }
-                __syncthreads();
-            }
-            // warp item = 8 pixels x 32 channels of one tile row (lane -> pixel lane/4, 8-channel group lane%4); TNU
-            // items (2 x 16-byte loads per lane each) in flight: only 12 warps per SM hide the L2 latency here
-            constexpr int TNU = 6;
-            for (int it0 = warp; it0 < NIT; it0 += TNU * NW) {
-                float4 ld[TNU][2];
-#pragma unroll
-                for (int u = 0; u < TNU; ++u) {
-                    const int it = it0 + u * NW;
-                    if (it < NIT) {
-                        const int o = it / (16 * QN), r = it - o * 16 * QN;
-                        const int q = r >> 4, pg = r & 15;
-                        const float* src = p.out + ((size_t)(b * p.H + h0 + o) * p.W + wt * OTW + pg * 8 + px) * p.Cout +
-                                           n0 + q * 32 + g * 8;
-                        ld[u][0] = __ldcg(reinterpret_cast<const float4*>(src));
-                        ld[u][1] = __ldcg(reinterpret_cast<const float4*>(src + 4));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < TNU; ++u) {
-                    const int it = it0 + u * NW;
-                    if (it >= NIT) continue;
-                    const int o = it / (16 * QN), r = it - o * 16 * QN;
-                    const int q = r >> 4, pg = r & 15;
-                    const int cl = q * 32 + g * 8, c8 = (n0 + cl) >> 3, tp = pg * 8 + px;
-                    const size_t bh = (size_t)b * p.H + h0 + o;
-                    const size_t oi = operand_unit(bh, WTo, c8n, wt, c8, tp + 1) * 8;
-                    size_t oi2 = 0;
-                    bool dup = false;
-                    if (tp == 0) { dup = true; oi2 = operand_unit(bh, WTo, c8n, wt == 0 ? WTo - 1 : wt - 1, c8, OPX - 1) * 8; }
-                    else if (tp == OTW - 1) { dup = true; oi2 = operand_unit(bh, WTo, c8n, wt == WTo - 1 ? 0 : wt + 1, c8, 0) * 8; }
-                    float v[8] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w};
-                    const float4 a0 = *reinterpret_cast<const float4*>(s_a + cl), a1 = *reinterpret_cast<const float4*>(s_a + cl + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(s_b + cl), b1 = *reinterpret_cast<const float4*>(s_b + cl + 4);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    gn_apply_store(v, av, bv, p.gn_silu, p.gn_parts, p.gn_y, lo_off, oi, oi2, dup, lane);
-                }
-            }
-        }
     }
 #undef FULL_A
 #undef EMPTY_A
@@ -690,12 +838,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const ConvPara
 #undef ACC_EMPTY
 }
 
-template <int BN, int R, int TAPS, int NP>
+template <int BN, int R, int TAPS, int NP, bool FUSE>
 static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
-    using C = ConvCfg<BN, R, TAPS, NP>;
+    using C = ConvCfg<BN, R, TAPS, NP, FUSE>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, R, TAPS, NP>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, R, TAPS, NP, FUSE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) {
             set_error("conv_tc: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM, cudaGetErrorString(e));
@@ -707,7 +855,7 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     const int tpc = (p.n_tiles + grid - 1) / grid;
     grid = (p.n_tiles + tpc - 1) / tpc;     // no empty CTAs with contiguous chunks
-    launch_pdl_if(pdl_enabled_conv(), conv_tc_kernel<BN, R, TAPS, NP>, dim3(grid), dim3(CONV_THREADS), (size_t)C::SMEM, st, p);
+    launch_pdl_if(pdl_enabled_conv(), conv_tc_kernel<BN, R, TAPS, NP, FUSE>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM, st, p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -970,19 +1118,25 @@ extern "C" int b200_pack_conv_weight_plain(const float* w, void* w16, int Cout, 
     return B200_OK;
 }
 
-struct GnTail {
-    void* y = nullptr;
+// fused front end description (b200_conv_gn_tc); x0 == nullptr: the A operand comes pre-built (b200_conv_tc)
+struct GnFront {
+    const float* x0 = nullptr;
+    const float* x1 = nullptr;
+    const double* st0 = nullptr;
+    const double* st1 = nullptr;
     const float* gamma = nullptr;
     const float* beta = nullptr;
     const float* ada = nullptr;
-    int ada_stride = 0, groups = 0, silu = 0, parts = 0;
+    int C0 = 0, C1 = 0, ada_stride = 0, groups = 1, silu = 0;
     float eps = 0.f;
 };
 
-static int conv_tc_impl(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
-                        float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps, int ring,
-                        int bn, int rows, int parts, const GnTail& gn, void* stream) {
-    B200_CHECK_ARG(a && wpacked && out);
+static int conv_tc_impl(const void* a, const GnFront& gn, const void* wpacked, const float* bias, const float* res,
+                        float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout,
+                        int taps, int ring, int bn, int rows, int parts, void* stream) {
+    const bool fuse = gn.x0 != nullptr;
+    B200_CHECK_ARG((a != nullptr) != fuse);
+    B200_CHECK_ARG(wpacked && out);
     B200_CHECK_ARG(B > 0 && H > 0 && W > 0);
     B200_CHECK_ARG(taps == 9 || taps == 1);
     B200_CHECK_ARG(parts >= 1 && parts <= 4);
@@ -990,24 +1144,24 @@ static int conv_tc_impl(const void* a, const void* wpacked, const float* bias, c
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
     B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
     B200_CHECK_ARG(rows * bn <= 256);   // two TMEM accumulator sets <= 512 columns (merged mode is chosen when 2x fits)
-    ConvParams p{(const __half*)a, (const __half*)wpacked, bias, res, out, stats, out_scale, w_inv,
-                 B, H, W, Cin, Cout, ring, 0};
-    p.gn_y = nullptr;
-    if (gn.y) {
-        B200_CHECK_ARG(stats != nullptr);                                   // the tail normalises with THIS launch's statistics
-        B200_CHECK_ARG(gn.groups > 0 && Cout % gn.groups == 0 && bn % (Cout / gn.groups) == 0);   // groups inside an n-tile
-        B200_CHECK_ARG(gn.parts >= 1 && gn.parts <= 3 && (gn.gamma == nullptr) == (gn.beta == nullptr));
-        static unsigned slot = 0;
-        unsigned* bars = nullptr;
-        if (cudaGetSymbolAddress((void**)&bars, g_gn_bar) != cudaSuccess) {
-            set_error("conv_tc_gn: cudaGetSymbolAddress failed");
-            return B200_E_CUDA;
-        }
-        p.gn_y = (__half*)gn.y;
+    ConvParams p{};
+    p.a = (const __half*)a; p.w = (const __half*)wpacked; p.bias = bias; p.res = res; p.out = out; p.stats = stats;
+    p.out_scale = out_scale; p.w_inv = w_inv; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ring = ring;
+    p.x0 = nullptr; p.x1 = nullptr; p.st0 = nullptr; p.st1 = nullptr;
+    p.gn_gamma = nullptr; p.gn_beta = nullptr; p.gn_ada = nullptr;
+    p.C0 = p.C1 = p.gn_ada_stride = p.gn_silu = 0; p.gn_groups = 1; p.gn_eps = 0.f;
+    if (fuse) {
+        B200_CHECK_ARG(parts == 2 || parts == 3);                               // fp16x3 / fp16f8 operands
+        B200_CHECK_ARG(gn.C0 > 0 && gn.C1 >= 0 && gn.C0 + gn.C1 == Cin && Cin <= MAX_CIN);
+        B200_CHECK_ARG(gn.C0 % 16 == 0 && gn.C1 % 16 == 0);                     // a 16-channel K chunk never straddles the concat
+        B200_CHECK_ARG((gn.C1 > 0) == (gn.x1 != nullptr));
+        B200_CHECK_ARG(gn.st0 == nullptr || gn.C1 == 0 || gn.st1 != nullptr);
+        B200_CHECK_ARG(gn.groups > 0 && gn.groups <= 32 && Cin % gn.groups == 0);
+        B200_CHECK_ARG((gn.gamma == nullptr) == (gn.beta == nullptr));
+        p.x0 = gn.x0; p.x1 = gn.x1; p.st0 = gn.st0; p.st1 = gn.st1;
         p.gn_gamma = gn.gamma; p.gn_beta = gn.beta; p.gn_ada = gn.ada;
-        p.gn_ada_stride = gn.ada_stride; p.gn_groups = gn.groups; p.gn_silu = gn.silu; p.gn_parts = gn.parts;
+        p.C0 = gn.C0; p.C1 = gn.C1; p.gn_ada_stride = gn.ada_stride; p.gn_groups = gn.groups; p.gn_silu = gn.silu;
         p.gn_eps = gn.eps;
-        p.gn_bar = bars + 2 * (slot++ % 64);
     }
     cudaStream_t st = (cudaStream_t)stream;
     static int num_sms = 0;
@@ -1017,9 +1171,12 @@ static int conv_tc_impl(const void* a, const void* wpacked, const float* bias, c
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
-#define B200_CONV_CASE(BN_, R_, NP_)                                                                              \
-    if (bn == BN_ && rows == R_ && parts == NP_)                                                                      \
-        return taps == 9 ? launch_conv<BN_, R_, 9, NP_>(p, num_sms, st) : launch_conv<BN_, R_, 1, NP_>(p, num_sms, st);
+#define B200_CONV_CASE(BN_, R_, NP_)                                                                                  \
+    if (!fuse && bn == BN_ && rows == R_ && parts == NP_)                                                             \
+        return taps == 9 ? launch_conv<BN_, R_, 9, NP_, false>(p, num_sms, st) : launch_conv<BN_, R_, 1, NP_, false>(p, num_sms, st);
+#define B200_FUSE_CASE(BN_, R_, NP_)                                                                                  \
+    if (fuse && bn == BN_ && rows == R_ && parts == NP_)                                                              \
+        return taps == 9 ? launch_conv<BN_, R_, 9, NP_, true>(p, num_sms, st) : launch_conv<BN_, R_, 1, NP_, true>(p, num_sms, st);
     B200_CONV_CASE(64, 1, 1)
     B200_CONV_CASE(64, 2, 1)
     B200_CONV_CASE(64, 4, 1)
@@ -1038,29 +1195,43 @@ static int conv_tc_impl(const void* a, const void* wpacked, const float* bias, c
     B200_CONV_CASE(64, 1, 4)
     B200_CONV_CASE(64, 2, 4)
     B200_CONV_CASE(128, 1, 4)
+    B200_FUSE_CASE(64, 1, 2)
+    B200_FUSE_CASE(64, 2, 2)
+    B200_FUSE_CASE(64, 4, 2)
+    B200_FUSE_CASE(128, 1, 2)
+    B200_FUSE_CASE(128, 2, 2)
+    B200_FUSE_CASE(64, 1, 3)
+    B200_FUSE_CASE(64, 2, 3)
+    B200_FUSE_CASE(64, 4, 3)
+    B200_FUSE_CASE(128, 1, 3)
+    B200_FUSE_CASE(128, 2, 3)
 #undef B200_CONV_CASE
-    set_error("conv_tc: unsupported tile bn=%d rows=%d (need rows*bn <= 256)", bn, rows);
+#undef B200_FUSE_CASE
+    set_error("conv_tc: unsupported tile bn=%d rows=%d parts=%d fused=%d (need rows*bn <= 256)", bn, rows, parts, (int)fuse);
     return B200_E_ARG;
 }
 
 extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
                             float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
                             int ring, int bn, int rows, int parts, void* stream) {
-    return conv_tc_impl(a, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
-                        parts, GnTail{}, stream);
+    B200_CHECK_ARG(a != nullptr);
+    return conv_tc_impl(a, GnFront{}, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn,
+                        rows, parts, stream);
 }
 
-extern "C" int b200_conv_tc_gn(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
-                               float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout, int taps,
-                               int ring, int bn, int rows, int parts, const float* gamma, const float* beta,
-                               const float* ada, int ada_stride, int groups, float eps, int silu, void* y, int y_parts,
-                               void* stream) {
-    B200_CHECK_ARG(y != nullptr);
-    GnTail gn;
-    gn.y = y; gn.gamma = gamma; gn.beta = beta; gn.ada = ada; gn.ada_stride = ada_stride; gn.groups = groups;
-    gn.eps = eps; gn.silu = silu; gn.parts = y_parts;
-    return conv_tc_impl(a, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows,
-                        parts, gn, stream);
+// GroupNorm(+AdaGN)-apply + SiLU + operand split fused IN FRONT of the conv: replaces the gn_act launch and the operand
+// round trip through HBM (reference: efficient_unet.py:104-115 `conv(silu(norm(x)))`, ops.py:176-200, layout_unet_v1.py:229-249)
+extern "C" int b200_conv_gn_tc(const float* x0, int C0, const float* x1, int C1, const double* stats0, const double* stats1,
+                               const float* gamma, const float* beta, const float* ada, int ada_stride, int groups,
+                               float eps, int silu, const void* wpacked, const float* bias, const float* res,
+                               float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cout,
+                               int taps, int ring, int bn, int rows, int parts, void* stream) {
+    B200_CHECK_ARG(x0 != nullptr);
+    GnFront gn;
+    gn.x0 = x0; gn.x1 = x1; gn.st0 = stats0; gn.st1 = stats1; gn.gamma = gamma; gn.beta = beta; gn.ada = ada;
+    gn.C0 = C0; gn.C1 = C1; gn.ada_stride = ada_stride; gn.groups = groups; gn.silu = silu; gn.eps = eps;
+    return conv_tc_impl(nullptr, gn, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, C0 + C1, Cout, taps, ring,
+                        bn, rows, parts, stream);
 }
 
 extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias, const float* res, float out_scale,
@@ -1071,8 +1242,9 @@ extern "C" int b200_conv_ffma(const void* a, const void* w16, const float* bias,
     B200_CHECK_ARG(parts >= 1 && parts <= 3);
     B200_CHECK_ARG(Cin % (parts == 3 ? 16 : 8) == 0 && Cout % 32 == 0 && W % OTW == 0);
     B200_CHECK_ARG(!stats || (H * W) % 32 == 0);
-    ConvParams p{(const __half*)a, (const __half*)w16, bias, res, out, stats, out_scale, w_inv,
-                 B, H, W, Cin, Cout, ring, 0};
+    ConvParams p{};
+    p.a = (const __half*)a; p.w = (const __half*)w16; p.bias = bias; p.res = res; p.out = out; p.stats = stats;
+    p.out_scale = out_scale; p.w_inv = w_inv; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ring = ring;
     const long long npix = (long long)B * H * W;
     dim3 grid((unsigned)((npix + 31) / 32), Cout / 32);
     conv_ffma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, taps, parts);

@@ -324,19 +324,17 @@ class EfficientUNetPlan:
         G, eps = m.gn_num_groups, m.gn_eps
         H, W = srcs[0].H, srcs[0].W
         has_skip = not isinstance(rb.skip, nn.Identity)
-        a1 = pb.gn_act(srcs, rb.norm1.weight, rb.norm1.bias, G, eps, True, also_raw=has_skip)
-        if has_skip:
-            a1, x16 = a1
-        # conv1 -> AdaGN(norm2) -> SiLU in one launch (fused tail); a2 = the operand of conv2
-        hmid, st_h, a2 = pb.conv(a1, H, W, rb.conv1.weight, rb.conv1.bias, None, 1.0, True,
-                                 gn=dict(gamma=None, beta=None, groups=G, eps=eps, silu=True, ada=self.ada,
-                                         ada_stride=self.P, ada_off=self.ada_off[id(rb)]))
+        # conv1(silu(norm1(x))): GroupNorm-apply + SiLU + operand split run inside the conv launch (b200_conv_gn_tc)
+        hmid, st_h = pb.conv_gn(srcs, rb.conv1.weight, rb.conv1.bias, None, 1.0, True, gamma=rb.norm1.weight,
+                                beta=rb.norm1.bias, groups=G, eps=eps, silu=True)
         if not has_skip:
             assert len(srcs) == 1
             res = srcs[0].t
-        else:
-            res, _ = pb.conv(x16, H, W, rb.skip.weight, rb.skip.bias, None, 1.0, False)
-        out, st = pb.conv(a2, H, W, rb.conv2.weight, rb.conv2.bias, res, float(rb.scale), True)
+        else:           # 1x1 skip conv on the raw (un-normalised) input
+            res, _ = pb.conv_gn(srcs, rb.skip.weight, rb.skip.bias, None, 1.0, False, normalize=False)
+        # conv2(silu(AdaGN(h, temb))) + skip, * 1/sqrt(2)
+        out, st = pb.conv_gn([Act(hmid, H, W, rb.cout, st_h)], rb.conv2.weight, rb.conv2.bias, res, float(rb.scale), True,
+                             groups=G, eps=eps, silu=True, ada=self.ada, ada_stride=self.P, ada_off=self.ada_off[id(rb)])
         return Act(out, H, W, rb.cout, st)
 
     def _attention(self, ab: _SelfAttnP, x: Act) -> Act:
@@ -344,9 +342,9 @@ class EfficientUNetPlan:
         pb, m = self.pb, self.m
         E, nh = x.C, ab.heads
         T = x.H * x.W
-        an = pb.gn_act([x], ab.norm.weight, ab.norm.bias, m.gn_num_groups, m.gn_eps, False)
         w_qkv = ab.attn.in_proj_weight.detach().reshape(3 * E, E, 1, 1)
-        qkv, _ = pb.conv(an, x.H, x.W, w_qkv, ab.attn.in_proj_bias, None, 1.0, False)
+        qkv, _ = pb.conv_gn([x], w_qkv, ab.attn.in_proj_bias, None, 1.0, False, gamma=ab.norm.weight, beta=ab.norm.bias,
+                            groups=m.gn_num_groups, eps=m.gn_eps, silu=False)
         att = self.plan.operand(x.H, x.W, E)
         d = E // nh
         self.plan.add(self.lib.flash_attention, _ptr(qkv), E, _ptr(att), x.W, self.plan.parts, self.B, nh, T,
@@ -363,8 +361,7 @@ class EfficientUNetPlan:
             assert len(srcs) == 1
             x = srcs[0]
             conv = blk.downsample[0]
-            x16 = pb.cast16([x])
-            y, _ = pb.conv(x16, x.H, x.W, conv.weight, conv.bias, None, 1.0, False)
+            y, _ = pb.conv_gn([x], conv.weight, conv.bias, None, 1.0, False, normalize=False)
             h = pb.fir(Act(y, x.H, x.W, conv.weight.shape[0]), up=False, want_stats=True)
             srcs = [h]
         for rb in blk.residual_blocks:

@@ -244,50 +244,30 @@ class PlanBuilder:
         self.ring = 1 if ring else 0
         self.stream = stream
         self.B = plan.B
-        # conv -> GroupNorm -> conv chains in one launch (b200_conv_tc_gn): opt-in with B200_FUSE_GN=1.  Measured on B200
-        # (profiles/r01_fused_gn_tail.txt): the tail runs with 12 warps/SM from L2 and costs what the separate gn_act
-        # launch costs (step 4.07 ms fused vs 3.92 ms unfused), so the default keeps the separate launch.
-        self.fuse_gn = os.environ.get("B200_FUSE_GN", "0") == "1"
-        # B200_FUSE_GN_MAX_PIX=n: fuse only where B*H*W <= n (the small levels, where a separate gn_act launch is mostly
-        # launch latency); measured in profiles/r01s2_fuse_gn_levels.txt
-        self.fuse_gn_max_pix = int(os.environ.get("B200_FUSE_GN_MAX_PIX", "0"))
+        # GroupNorm(+AdaGN)+SiLU+operand split fused IN FRONT of the conv (b200_conv_gn_tc): the default.  B200_FUSE_FRONT=0
+        # falls back to the separate gn_act launch + operand round trip (A/B measurements, profiles/r02_*).
+        self.fuse_front = os.environ.get("B200_FUSE_FRONT", "1") != "0"
 
     # ---- conv on tensor cores (or the FFMA cross-check path) ----
     def conv(self, a16: torch.Tensor, H: int, W: int, weight, bias, res: torch.Tensor | None, scale: float,
-             want_stats: bool, gn: dict | None = None):
-        """-> (out, stats slot); with ``gn`` (dict(gamma, beta, groups, eps, silu, ada, ada_stride, ada_off)) the
-        GroupNorm(+AdaGN)(+SiLU) of the output is applied by the same launch (b200_conv_tc_gn: grid barrier + tail) and
-        the normalised conv operand is returned as a third value -- the separate gn_act launch and its HBM read of
-        ``out`` disappear."""
+             want_stats: bool):
+        """conv of a pre-built operand (attention output, FIR-upsampled operand) -> (out, stats slot)"""
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
         out = self.p.f32(self.B, H * W, Cout)
-        st = self.p.new_stats(Cout) if (want_stats or gn is not None) else None
+        st = self.p.new_stats(Cout) if want_stats else None
         fl = 2.0 * self.B * H * W * taps * Cin * Cout
         self.p.flops += fl
         npix = self.B * H * W
         by = npix * (2.0 * planes(self.p.parts) * Cin + 4.0 * Cout * (2 if res is not None else 1)) \
             + 2.0 * planes(self.p.parts) * taps * Cin * Cout
-        y = None
         if self.p.conv_impl == "tc":
             bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
             pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             self.p.bufs.append(pc)
-            base = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale), 1.0 / pc.wscale, _ptr(out),
-                    _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows, self.p.parts)
-            fuse = self.fuse_gn or (self.fuse_gn_max_pix > 0 and npix <= self.fuse_gn_max_pix)
-            if gn is not None and fuse and bn % (Cout // gn["groups"]) == 0:
-                y = self.p.operand(H, W, Cout)
-                g = None if gn.get("gamma") is None else gn["gamma"].detach().float().contiguous()
-                b = None if gn.get("beta") is None else gn["beta"].detach().float().contiguous()
-                self.p.bufs += [g, b]
-                ada = gn.get("ada")
-                ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * gn.get("ada_off", 0)
-                self.p.add(self.lib.conv_tc_gn, *base, _ptr(g), _ptr(b), ada_ptr, gn.get("ada_stride", 0), gn["groups"],
-                           float(gn["eps"]), 1 if gn["silu"] else 0, _ptr(y), self.p.parts, name="conv_tc", flops=fl,
-                           nbytes=by + npix * 2.0 * planes(self.p.parts) * Cout)
-            else:
-                self.p.add(self.lib.conv_tc, *base, name="conv_tc", flops=fl, nbytes=by)
+            self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
+                       1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
+                       self.p.parts, name="conv_tc", flops=fl, nbytes=by)
         else:
             w = weight.detach().float().contiguous()
             ws = weight_scale(w, self.p.parts)
@@ -298,20 +278,58 @@ class PlanBuilder:
             self.p.add(self.lib.conv_ffma, _ptr(a16), _ptr(w16), _ptr(b32), _ptr(res), float(scale), 1.0 / ws,
                        _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, self.p.parts,
                        name="conv_ffma", flops=fl, nbytes=by)
-        if gn is None:
-            return out, st
-        if y is None:     # unfused: separate GroupNorm-apply launch (cross-check path / groups crossing n-tiles)
-            y = self.gn_act([Act(out, H, W, Cout, st)], gn.get("gamma"), gn.get("beta"), gn["groups"], gn["eps"],
-                            gn["silu"], ada=gn.get("ada"), ada_stride=gn.get("ada_stride", 0), ada_off=gn.get("ada_off", 0))
-        return out, st, y
+        return out, st
 
-    def tune_tile(self, a16, H, W, weight, bias, res, out):
-        """(bn, rows) of b200_conv_tc for this shape: measured once per shape on the device (CUDA events, best of the
-        candidate tiles), cached for the process; the analytic pick_tile() is only the no-GPU fallback of the planner
-        (emulator tests)."""
+    def conv_gn(self, srcs: list[Act], weight, bias, res: torch.Tensor | None, scale: float, want_stats: bool,
+                gamma=None, beta=None, groups: int = 1, eps: float = 0.0, silu: bool = False, ada=None, ada_stride: int = 0,
+                ada_off: int = 0, normalize: bool = True):
+        """conv(act(GroupNorm[+AdaGN](cat(srcs)))) -> (out, stats slot) in ONE launch (b200_conv_gn_tc): the transform warps
+        of the conv kernel normalise / activate / split the fp32 activation(s) straight into the tensor-core operand slab.
+        ``normalize=False``: plain fp32 -> operand conversion (1x1 skip conv of a ResBlock, conv in front of a down-sampler).
+        The cross-check paths (conv_impl "ffma", single-pass fp16, B200_FUSE_FRONT=0) run gn_act + conv instead."""
+        a0 = srcs[0]
+        a1 = srcs[1] if len(srcs) > 1 else None
+        H, W = a0.H, a0.W
+        Cout, Cin, kh, kw = weight.shape
+        assert Cin == a0.C + (a1.C if a1 else 0)
+        fused = (self.p.conv_impl == "tc" and self.fuse_front and self.p.parts in (2, 3) and a0.C % 16 == 0
+                 and (a1 is None or a1.C % 16 == 0) and Cin <= 1024 and groups <= 32)
+        if not fused:
+            a16 = self.gn_act(srcs, gamma, beta, groups, eps, silu, ada=ada, ada_stride=ada_stride, ada_off=ada_off,
+                              normalize=normalize)
+            return self.conv(a16, H, W, weight, bias, res, scale, want_stats)
+        if normalize:
+            assert a0.stats is not None and (a1 is None or a1.stats is not None)
+        taps = kh * kw
+        out = self.p.f32(self.B, H * W, Cout)
+        st = self.p.new_stats(Cout) if want_stats else None
+        fl = 2.0 * self.B * H * W * taps * Cin * Cout
+        self.p.flops += fl
+        npix = self.B * H * W
+        by = npix * (4.0 * Cin + 4.0 * Cout * (2 if res is not None else 1)) + 2.0 * planes(self.p.parts) * taps * Cin * Cout
+        g = None if gamma is None else gamma.detach().float().contiguous()
+        b = None if beta is None else beta.detach().float().contiguous()
+        self.p.bufs += [g, b]
+        ada_ptr = 0 if ada is None else ada.data_ptr() + 4 * ada_off
+        front = (_ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0,
+                 _sp(a0.stats) if normalize else 0, _sp(a1.stats) if (normalize and a1) else 0, _ptr(g), _ptr(b), ada_ptr,
+                 ada_stride, groups, float(eps), 1 if silu else 0)
+        bn, rows = self.tune_tile(None, H, W, weight, bias, res, out, front=(_ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0,
+                                                                             a1.C if a1 else 0))
+        pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
+        self.p.bufs.append(pc)
+        self.p.add(self.lib.conv_gn_tc, *front, _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale), 1.0 / pc.wscale,
+                   _ptr(out), _sp(st), self.B, H, W, Cout, taps, self.ring, bn, rows, self.p.parts, name="conv_gn_tc",
+                   flops=fl, nbytes=by)
+        return out, st
+
+    def tune_tile(self, a16, H, W, weight, bias, res, out, front=None):
+        """(bn, rows) of b200_conv_tc / b200_conv_gn_tc for this shape: measured once per shape on the device (CUDA events,
+        best of the candidate tiles), cached for the process; the analytic pick_tile() is only the no-GPU fallback of the
+        planner (emulator tests).  ``front`` = (x0, C0, x1, C1) of the fused front end (timed with SiLU, no statistics)."""
         Cout, Cin, kh, kw = weight.shape
         taps = kh * kw
-        key = (self.B, H, W, Cin, Cout, taps, self.p.parts, res is not None)
+        key = (self.B, H, W, Cin, Cout, taps, self.p.parts, res is not None, front is not None)
         _load_tune_file()
         if key in _TUNE_CACHE:
             return _TUNE_CACHE[key]
@@ -324,10 +342,16 @@ class PlanBuilder:
             if pk not in packed:
                 packed[pk] = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             pc = packed[pk]
-            args = (_ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), 1.0, 1.0 / pc.wscale, _ptr(out), 0, self.B, H, W,
-                    Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
+            tail = (_ptr(pc.packed), _ptr(pc.bias), _ptr(res), 1.0, 1.0 / pc.wscale, _ptr(out), 0, self.B, H, W)
+            if front is None:
+                fn = self.lib.conv_tc
+                args = (_ptr(a16),) + tail + (Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
+            else:
+                fn = self.lib.conv_gn_tc
+                args = tuple(front) + (0, 0, 0, 0, 0, 0, 1, 0.0, 1) + tail + (Cout, taps, self.ring, bn, rows, self.p.parts,
+                                                                             self.stream)
             for _ in range(2):                           # warm-up (function attributes, caches, clocks)
-                self.lib.conv_tc(*args)
+                fn(*args)
             # best of 3 batches of 5 back-to-back launches: one batch let power-cap / clock noise pick a slower tile now
             # and then, single launches are dominated by the launch gap (and by the interception cost under a profiler)
             ms = float("inf")
@@ -335,7 +359,7 @@ class PlanBuilder:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(5):
-                    self.lib.conv_tc(*args)
+                    fn(*args)
                 e1.record()
                 e1.synchronize()
                 ms = min(ms, e0.elapsed_time(e1))

@@ -272,28 +272,26 @@ class LayoutUnetPlan:
             xr = pb.fir(x0, up=rb.up, want_stats=False)
             if rb.up:       # Resample(up) written straight into conv1's operand
                 a1, H, W = pb.fir_up_operand(Act(t, H, W, x0.C))
-            else:
+                hmid, st_h = pb.conv(a1, H, W, conv1.weight, conv1.bias, None, 1.0, True)
+            else:           # Resample(down) in fp32, converted to the operand inside the conv launch
                 tr = pb.fir(Act(t, H, W, x0.C), up=False, want_stats=False)
-                a1 = pb.cast16([tr])
                 H, W = tr.H, tr.W
+                hmid, st_h = pb.conv_gn([tr], conv1.weight, conv1.bias, None, 1.0, True, normalize=False)
             res = xr.t
         else:
-            has_skip = not isinstance(rb.skip_connection, nn.Identity)
-            a1 = pb.gn_act(srcs, n1.weight, n1.bias, GN_GROUPS, GN_EPS, True, also_raw=has_skip)
-            if has_skip:
-                a1, x16 = a1
-            res = None
-        # conv1 -> GroupNorm32 * (1 + scale) + shift -> SiLU in one launch (fused tail); a2 = the operand of conv2
-        hmid, st_h, a2 = pb.conv(a1, H, W, conv1.weight, conv1.bias, None, 1.0, True,
-                                 gn=dict(gamma=n2.weight, beta=n2.bias, groups=GN_GROUPS, eps=GN_EPS, silu=True,
-                                         ada=self.ada, ada_stride=self.P, ada_off=self.ada_off[id(rb)]))
-        if res is None:
+            # conv1(silu(GN32(x))) with the normalisation fused in front of the conv (b200_conv_gn_tc)
+            hmid, st_h = pb.conv_gn(srcs, conv1.weight, conv1.bias, None, 1.0, True, gamma=n1.weight, beta=n1.bias,
+                                    groups=GN_GROUPS, eps=GN_EPS, silu=True)
             if isinstance(rb.skip_connection, nn.Identity):
                 assert len(srcs) == 1
                 res = x0.t
             else:
-                res, _ = pb.conv(x16, H, W, rb.skip_connection.weight, rb.skip_connection.bias, None, 1.0, False)
-        out, st = pb.conv(a2, H, W, conv2.weight, conv2.bias, res, 1.0, True)
+                res, _ = pb.conv_gn(srcs, rb.skip_connection.weight, rb.skip_connection.bias, None, 1.0, False,
+                                    normalize=False)
+        # conv2(silu(GN32(h) * (1 + scale) + shift)) + skip
+        out, st = pb.conv_gn([Act(hmid, H, W, rb.cout, st_h)], conv2.weight, conv2.bias, res, 1.0, True, gamma=n2.weight,
+                             beta=n2.bias, groups=GN_GROUPS, eps=GN_EPS, silu=True, ada=self.ada, ada_stride=self.P,
+                             ada_off=self.ada_off[id(rb)])
         return Act(out, H, W, rb.cout, st)
 
     def _attention(self, ab: _OAAttnP, x: Act) -> Act:
@@ -301,9 +299,9 @@ class LayoutUnetPlan:
         pb, plan, B = self.pb, self.plan, self.B
         C, nh, T = x.C, ab.num_heads, x.H * x.W
         L2 = 13
-        an = pb.gn_act([x], ab.norm_for_qkv.weight, ab.norm_for_qkv.bias, GN_GROUPS, GN_EPS, False)
         wq = ab.qkv_projector.weight.detach().reshape(3 * C, C, 1, 1)
-        qkv, _ = pb.conv(an, x.H, x.W, wq, ab.qkv_projector.bias, None, 1.0, False)
+        qkv, _ = pb.conv_gn([x], wq, ab.qkv_projector.bias, None, 1.0, False, gamma=ab.norm_for_qkv.weight,
+                            beta=ab.norm_for_qkv.bias, groups=GN_GROUPS, eps=GN_EPS, silu=False)
         bufs = dict(pos_p=plan.f32(B, T, C), kl=plan.f32(B, L2, C), pos_l=plan.f32(B, L2, C), vl=plan.f32(B, L2, C))
         res_key = f"image_patch_bbox_embedding_for_resolution{self.m.image_size // (self.H // x.H)}"
         self.attn_consts.append((ab, res_key, bufs))

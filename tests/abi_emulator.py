@@ -231,18 +231,21 @@ class EmulatedLib:
         self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
         return 0
 
-    def conv_tc_gn(self, a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts,
-                   gamma, beta, ada, ada_stride, groups, eps, silu, y, y_parts, stream):
-        """conv_tc, then the GroupNorm(+AdaGN)(+SiLU) of its output written as the next conv's operand"""
-        assert stats and bn % (Cout // groups) == 0
-        self.conv_tc(a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts,
-                     stream)
-        self.calls[-1] = "conv_tc_gn"
+    def conv_gn_tc(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, wpacked, bias, res,
+                   scale, w_inv, out, stats, B, H, W, Cout, taps, ring, bn, rows, parts, stream):
+        """GroupNorm(+AdaGN)-apply + SiLU + operand split fused in front of conv_tc: == gn_act_f16 into a scratch operand,
+        then conv_tc (the kernel builds the same operand in shared memory)"""
+        assert parts in (2, 3) and C0 % 16 == 0 and C1 % 16 == 0 and C0 + C1 <= 1024 and groups <= 32
+        Cin = C0 + C1
         n0 = self.n_launches
-        self.gn_act_f16(out, Cout, 0, 0, stats, 0, gamma, beta, ada, ada_stride, groups, eps, silu, y, 0, y_parts, B, H, W,
-                        stream)
+        scratch = torch.zeros(n_planes(parts) * operand_elems(B, H, W, Cin), dtype=torch.float16)
+        self.gn_act_f16(x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, scratch.data_ptr(), 0,
+                        parts, B, H, W, stream)
         self.calls.pop()
-        self.n_launches = n0
+        self.conv_tc(scratch.data_ptr(), wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn,
+                     rows, parts, stream)
+        self.calls[-1] = "conv_gn_tc"
+        self.n_launches = n0 + 1
         return 0
 
     def conv_ffma(self, a, w16, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts, stream):

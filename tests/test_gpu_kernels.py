@@ -125,40 +125,67 @@ def test_conv_tc_matches_contract(parts, taps, bn, rows, Cin, Cout, H, W, B):
 
 
 @pytest.mark.parametrize("parts", [2, 3])
-@pytest.mark.parametrize("bn,rows,Cin,Cout,H,W,B,groups,affine", [
-    (64, 2, 64, 64, 8, 256, 2, 8, False),
-    (64, 2, 64, 64, 32, 1024, 3, 8, False),       # several tiles per CTA, sample changes inside a CTA's tile range
-    (128, 2, 128, 256, 16, 512, 2, 32, True),
-    (128, 1, 256, 128, 4, 128, 3, 8, False),
+@pytest.mark.parametrize("taps,bn,rows,C0,C1,Cout,H,W,B,groups,mode,ring", [
+    (9, 64, 2, 64, 0, 64, 8, 256, 2, 8, "gn", 1),
+    (9, 64, 2, 64, 0, 64, 32, 1024, 3, 8, "ada", 1),       # several tiles per CTA, sample changes inside a CTA's tile range
+    (9, 64, 4, 64, 64, 64, 8, 256, 2, 8, "gn", 1),         # channel concat (up path), 4-row tiles
+    (9, 64, 1, 32, 32, 64, 4, 128, 1, 8, "gn", 0),         # zero padding in W, concat inside one GroupNorm group layout
+    (9, 128, 2, 128, 0, 256, 16, 512, 2, 32, "gn_ada", 1),
+    (9, 128, 1, 256, 256, 128, 4, 128, 3, 8, "gn", 1),
+    (9, 128, 1, 512, 512, 512, 4, 128, 1, 32, "gn_ada", 1),    # Cin = 1024 (LayoutUnetV1 output block 0)
+    (1, 64, 4, 128, 0, 64, 8, 256, 2, 8, "raw", 1),        # 1x1 skip conv on the un-normalised input
+    (1, 128, 2, 256, 0, 768, 4, 128, 2, 8, "gn_nosilu", 1),    # GroupNorm -> QKV projection
+    (1, 64, 1, 64, 64, 64, 4, 128, 2, 8, "raw", 1),
+    (1, 64, 2, 64, 0, 128, 4, 256, 1, 8, "raw", 1),
+    (1, 128, 1, 512, 0, 128, 4, 128, 2, 32, "gn_nosilu", 1),
 ])
-def test_conv_tc_gn_fused_tail(parts, bn, rows, Cin, Cout, H, W, B, groups, affine):
-    """conv + (grid barrier) + GroupNorm(+AdaGN)+SiLU tail in one launch == conv_tc followed by gn_act_f16"""
+def test_conv_gn_tc_fused_front(parts, taps, bn, rows, C0, C1, Cout, H, W, B, groups, mode, ring):
+    """GroupNorm(+AdaGN)-apply + SiLU + operand split by the conv kernel's transform warps (b200_conv_gn_tc) vs the
+    emulator (gn_act_f16 -> conv_tc on the CPU), and vs the separate GPU launches gn_act_f16 -> conv_tc: the fused kernel
+    builds the same operand bits in shared memory and issues the same MMAs, so the outputs must be bit-identical."""
     h = Both()
-    taps = 9
-    w = h.t(randn(Cout, Cin, 3, 3, seed=1, scale=1 / math.sqrt(Cin * taps)))
-    a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
+    Cin = C0 + C1
+    k = 3 if taps == 9 else 1
+    w = h.t(randn(Cout, Cin, k, k, seed=1, scale=1 / math.sqrt(Cin * taps)))
+    x0 = h.t(randn(B, H, W, C0, seed=2) * 1.7 + 0.3)
+    x1 = h.t(randn(B, H, W, C1, seed=8) * 0.6 - 0.2) if C1 else None
     bias = h.t(randn(Cout, seed=3, scale=0.1))
+    res = h.t(randn(B, H, W, Cout, seed=4))
     wp = h.t(wp_zeros(Cout, Cin, taps, parts))
     out = h.t(torch.zeros(B, H, W, Cout))
+    out2 = h.t(torch.zeros(B, H, W, Cout))
     st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
-    gam, bet = h.t(1 + 0.1 * randn(Cout, seed=5)), h.t(0.1 * randn(Cout, seed=6))
-    P = 2 * Cout + 16
+    st2 = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    s0 = h.t(torch.zeros(B, C0, 2, dtype=torch.float64))
+    s1 = h.t(torch.zeros(B, C1, 2, dtype=torch.float64)) if C1 else None
+    gam, bet = h.t(1 + 0.1 * randn(Cin, seed=5)), h.t(0.1 * randn(Cin, seed=6))
+    P = 2 * Cin + 16
     ada = h.t(0.3 * randn(B, P, seed=7))
-    y = h.t(operand_zeros(parts, B, H, W, Cout))
+    y = h.t(operand_zeros(parts, B, H, W, Cin))
     wscale = 64.0 if parts < 3 else 2.0 ** 16
+    norm = mode != "raw"
+    affine = mode in ("gn", "gn_ada", "gn_nosilu")
+    use_ada = mode in ("ada", "gn_ada")
+    silu = 0 if mode in ("raw", "gn_nosilu") else 1
     h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, rows, parts, wscale])
-    h.call("conv_tc_gn", [("t", a), ("t", wp), ("t", bias), None, 1.0, 1.0 / wscale, ("t", out), ("t", st), B, H, W, Cin,
-                          Cout, taps, 1, bn, rows, parts, ("t", gam) if affine else None, ("t", bet) if affine else None,
-                          ("t", ada), P, groups, 1e-6, 1, ("t", y), parts])
-    assert rel(*h.out(out)) < 1e-5
+    if norm:
+        h.call("channel_stats", [("t", x0), ("t", s0), B, H * W, C0])
+        if C1:
+            h.call("channel_stats", [("t", x1), ("t", s1), B, H * W, C1])
+    front = [("t", x0), C0, ("t", x1) if C1 else None, C1, ("t", s0) if norm else None,
+             ("t", s1) if (norm and C1) else None, ("t", gam) if affine else None, ("t", bet) if affine else None,
+             ("t", ada) if use_ada else None, P, groups, 1e-6, silu]
+    h.call("conv_gn_tc", front + [("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out), ("t", st), B, H, W,
+                                  Cout, taps, ring, bn, rows, parts])
+    g, c = h.out(out)
+    assert rel(g, c) < 2e-5, rel(g, c)
     assert rel(*h.out(st)) < 2e-5
-    g, c = h.out(y)
-    pg, pc = load_operand(g.data_ptr(), parts, B, H, W, Cout), load_operand(c.data_ptr(), parts, B, H, W, Cout)
-    val = (lambda p_: p_[0] + p_[1]) if parts == 2 else (lambda p_: p_[0] + p_[1] / 2048.0)
-    assert rel(val(pg), val(pc)) < 1e-4          # the normalised values inherit the conv's fp32 accumulation-order noise
-    raw = g.view(torch.int16).view(n_planes(parts), B, H, W // OTW, Cout // 8, OPX, 8)
-    assert torch.equal(raw[..., 0, :], torch.roll(raw, 1, dims=3)[..., OTW, :])          # halo duplicates
-    assert torch.equal(raw[..., OPX - 1, :], torch.roll(raw, -1, dims=3)[..., 1, :])
+    # the separate launches on the GPU
+    h.call("gn_act_f16", front + [("t", y), None, parts, B, H, W])
+    h.call("conv_tc", [("t", y), ("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out2), ("t", st2), B, H, W,
+                       Cin, Cout, taps, ring, bn, rows, parts])
+    g2, _ = h.out(out2)
+    assert torch.equal(g, g2), float((g - g2).abs().max())
 
 
 def test_conv_tc_zero_pad_no_bias_no_res():
