@@ -321,7 +321,7 @@ def main():
         shapes = {}
         for (fn, a), (name, ms_k, fl, by_k) in zip(plan.plan.ops, prof):
             if conv_shape(name, a):
-                key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a))
+                key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % ((("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a)))
                 d = shapes.setdefault(key, [0.0, 0.0, 0]); d[0] += ms_k; d[1] += fl; d[2] += 1
             elif name == "gn_act_f16":  # args: x0, C0, x1, C1, st0, st1, g, b, ada, stride, groups, eps, silu, y, parts, B, H, W
                 key = "gn_act %2dx%-4d C%-4d norm%d raw%d" % (a[17], a[18], a[1] + a[3], 1 if a[4] else 0, 1 if a[14] else 0)
@@ -341,7 +341,7 @@ def main():
             lib.conv_set_debug(0)
             d = dbg.view(148, 8).double()
             d = d[d[:, 0] > 0]
-            key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % (("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a))
+            key = ("conv%s %2dx%-4d Cin%-4d Cout%-4d taps%d bn%d R%d" % ((("+gn" if name == "conv_gn_tc" else "   "),) + conv_shape(name, a)))
             w = waits.setdefault(key, [0.0] * 5)
             w[0] += float(d[:, 0].mean()); w[1] += float(d[:, 1].mean()); w[2] += float(d[:, 2].mean())
             w[3] += float(d[:, 3].mean()); w[4] += float(d[:, 5].mean())

@@ -1116,9 +1116,11 @@ __global__ void __launch_bounds__(OG_THREADS) out_conv_gather_kernel(const float
 // ---------------------------------------------------------------------------------------------------------
 // sampler update (continuous_time.py:205-231)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void sampler_update_kernel(const float* __restrict__ x_t, const float* __restrict__ pred,
+// x_t and x_s MAY ALIAS (the captured denoiser step updates the sampler state in place): no __restrict__ on them; every
+// thread reads element gi before it writes element gi.
+__global__ void sampler_update_kernel(const float* x_t, const float* __restrict__ pred,
                                       const float* __restrict__ noise, const float* __restrict__ coef,
-                                      float* __restrict__ x_s, int n, int mode, int objective, float clip) {
+                                      float* x_s, int n, int mode, int objective, float clip) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;

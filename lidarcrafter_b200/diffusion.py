@@ -147,7 +147,6 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
                          noise_schedule=noise_schedule, min_snr_loss_weight=min_snr_loss_weight,
                          min_snr_gamma=min_snr_gamma, sampling_resolution=sampling_resolution,
                          clip_sample=clip_sample, clip_sample_range=clip_sample_range)
-        self._graphs: dict = {}
         self.use_cuda_graph = True
 
     def setup_parameters(self) -> None:
@@ -235,7 +234,12 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         c2 = (1 - a_s ** 2 - c1 ** 2).sqrt()
         cc = -torch.special.expm1(lt - ls)
         coef = torch.stack([a_t, s_t, a_s, s_s, c1, c2, cc, torch.zeros_like(cc)], dim=-1).float().contiguous()
-        return lt.float().contiguous(), coef
+        lt = lt.float().contiguous()
+        if out is not None:           # (emulator / CPU path) honour the caller's buffers like the kernel does
+            out[0].copy_(lt)
+            out[1].copy_(coef)
+            return out
+        return lt, coef
 
     def _predict(self, x_t: torch.Tensor, log_snr_t: torch.Tensor) -> torch.Tensor:
         return self.model(x_t, log_snr_t)
@@ -246,20 +250,27 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         """continuous_time.py:194-234: one reverse step (model forward + fused update kernel)."""
         if mode not in ("ddpm", "ddim"):
             raise ValueError(f"invalid mode {mode}")
-        if self.use_cuda_graph and x_t.is_cuda and hasattr(self.model, "get_plan"):
+        plan = self.model.get_plan(x_t.shape[0]) if hasattr(self.model, "get_plan") else None
+        return self._p_step_plan(plan, x_t, step_t, step_s, rng, mode, ddim_eta)
+
+    def _p_step_plan(self, plan, x_t, step_t, step_s, rng, mode, ddim_eta, predict=None):
+        """one reverse step on a kernel plan whose condition (if any) is already folded"""
+        if plan is not None and self.use_cuda_graph and x_t.is_cuda:
             # the same captured step (model plan + fused update) that sample() replays: one graph launch per call
-            plan = self.model.get_plan(x_t.shape[0])
             entry = self._step_graph(plan, x_t.shape[0], mode)
             if entry["graph"] is not None:
                 plan.x_in.copy_(x_t)
-                self._coefficients(step_t, step_s, ddim_eta, out=(plan.t_in, entry["coef"]))   # straight into the graph's inputs
+                # straight into the graph's inputs (step tensors follow x_t's device: a CPU step tensor must not leave the
+                # captured coefficient buffers stale)
+                self._coefficients(step_t.to(x_t.device), step_s.to(x_t.device), ddim_eta, out=(plan.t_in, entry["coef"]))
                 noise = self.randn_like(x_t, rng=rng)      # drawn every step like the reference (RNG stream parity)
                 if mode == "ddpm" or ddim_eta != 0.0:
                     entry["noise"].copy_(noise)
                 entry["graph"].replay()
                 return plan.x_in.clone()
+        step_t, step_s = step_t.to(x_t.device), step_s.to(x_t.device)
         lt, coef = self._coefficients(step_t, step_s, ddim_eta)
-        pred = self._predict(x_t, lt).contiguous()
+        pred = (plan(x_t, lt) if plan is not None else (predict or self._predict)(x_t, lt)).contiguous()
         noise = self.randn_like(x_t, rng=rng).contiguous()
         x_t = x_t.contiguous()
         x_s = torch.empty_like(x_t)
@@ -273,9 +284,13 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
 
     # ---- fast path: one CUDA graph per (batch, mode) replayed num_steps times ----
     def _step_graph(self, plan, B: int, mode: str):
-        key = (id(plan), B, mode, self.objective, self.clip_sample, self.clip_sample_range)
-        if key in self._graphs:
-            return self._graphs[key]
+        # the captured step lives ON the plan (it references the plan's buffers): a plan dropped by the model -- new
+        # weights, coords, precision, .to() -- takes its graphs and activation arena with it instead of leaking them
+        graphs = plan.__dict__.setdefault("_step_graphs", {})
+        key = (B, mode, self.objective, self.clip_sample, self.clip_sample_range, tuple(self.sampling_shape),
+               bool(self.use_cuda_graph))
+        if key in graphs:
+            return graphs[key]
         dev = plan.dev
         lib = _lib.get_lib()
         coef = torch.zeros(B, 8, device=dev)
@@ -305,7 +320,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
                 step()
             plan.x_in.copy_(x_keep)
             entry["graph"] = g
-        self._graphs[key] = entry
+        graphs[key] = entry
         return entry
 
     @torch.inference_mode()
@@ -412,11 +427,39 @@ class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
         if self.cond_mode == "concat":
             self.sampling_shape = (self.model.in_channels - condition_model.out_channels, *self.sampling_shape[1:])
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("the layout-conditioned training loss (continuous_time_cond.py:414-455) is not part of the "
-                                  "B200 hot path (SURVEY 8f-4)")
+    @torch.inference_mode()
+    def p_loss(self, input_dict: dict, steps: torch.Tensor, loss_mask: torch.Tensor | None = None) -> torch.Tensor:
+        """continuous_time_cond.py:414-436, EVALUATED (forward only, no gradient: the kernel plans have no backward)"""
+        x_0 = input_dict["x_0"]
+        loss_mask = torch.ones_like(x_0) if loss_mask is None else loss_mask
+        x_t, noise = self.q_step_from_x_0(x_0, steps)
+        condition = self.get_network_condition(steps, input_dict)
+        self._reject_tensor_condition(condition["other_condition"])
+        prediction = self.model(x_t, condition)
+        loss = self._criterion(prediction, self.get_target(x_0, steps, noise))
+        loss = (loss * loss_mask).flatten(1).sum(dim=1, keepdim=True)
+        loss = loss / loss_mask.flatten(1).sum(dim=1, keepdim=True).add(1e-8)
+        return (loss * self.get_loss_weight(steps)).mean()
 
-    p_loss = forward
+    @torch.inference_mode()
+    def forward(self, input_dict: dict) -> torch.Tensor:
+        """continuous_time_cond.py:438-455"""
+        x_0 = input_dict["x_0"]
+        steps = self.sample_timesteps(x_0.shape[0], x_0.device)
+        loss_mask = None
+        if self.w_loss_weight:
+            loss_mask = input_dict.get("scene_loss_weight_map", None)        # [B,H,W]
+            if loss_mask is not None:
+                loss_mask = loss_mask.unsqueeze(1).repeat(1, x_0.shape[1], 1, 1)
+        return self.p_loss(input_dict, steps, loss_mask)
+
+    def _reject_tensor_condition(self, other):
+        if self.cond_mode == "concat" and isinstance(other, torch.Tensor):
+            # continuous_time_cond.py:223-226 calls model(cat([x_t, cond]), {"time_condition"}) here; neither denoiser of the
+            # hot path accepts that call in the reference either (LayoutUnetV1.forward reads cond_dict["other_condition"],
+            # layout_unet_v1.py:869; EfficientUNet.forward takes a timestep tensor) -- it serves the out-of-scope HDiT models
+            raise NotImplementedError("tensor-valued concat condition: wrap it as {'concat_cond': tensor, ...} "
+                                      "(every nuScenes layout config passes the encoder's dict)")
 
     def get_network_condition(self, steps=None, input_dict=None, only_custom_condition=False):
         other_condition = self.condition_model(input_dict)
@@ -427,24 +470,16 @@ class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
     @torch.inference_mode()
     def p_step(self, x_t: torch.Tensor, condition_dict: dict, step_t: torch.Tensor, step_s: torch.Tensor, rng=None,
                mode: Literal["ddpm", "ddim"] = "ddpm", ddim_eta: float = 0.0) -> torch.Tensor:
-        """continuous_time_cond.py:206-253."""
+        """continuous_time_cond.py:206-253: folds the condition into the denoiser plan (every call: the dict may have
+        changed), then runs the captured step (model plan + fused update kernel)."""
         if mode not in ("ddpm", "ddim"):
             raise ValueError(f"invalid mode {mode}")
-        lt, coef = self._coefficients(step_t, step_s, ddim_eta)
-        condition_dict.update(dict(time_condition=lt))
         other = condition_dict["other_condition"]
-        if self.cond_mode == "concat" and isinstance(other, torch.Tensor):
-            raise NotImplementedError("tensor-valued concat condition: wrap it as {'concat_cond': tensor, ...} "
-                                      "(every nuScenes layout config passes the encoder's dict)")
-        pred = self.model(x_t, condition_dict).contiguous()
-        noise = self.randn_like(x_t, rng=rng).contiguous()
-        x_t = x_t.contiguous()
-        x_s = torch.empty_like(x_t)
-        _lib.get_lib().sampler_update(x_t.data_ptr(), pred.data_ptr(), noise.data_ptr(), coef.data_ptr(), x_s.data_ptr(),
-                                      x_t.shape[0], x_t[0].numel(), 0 if mode == "ddim" else 1, _OBJ[self.objective],
-                                      float(self.clip_sample_range) if self.clip_sample else 0.0,
-                                      _lib.current_stream(x_t.device))
-        return x_s
+        self._reject_tensor_condition(other)
+        condition_dict.update(dict(time_condition=self.log_snr(step_t)[:, 0, 0, 0]))     # the reference mutates the dict
+        plan = self.model.get_plan(x_t.shape[0])
+        plan.set_condition(other)
+        return self._p_step_plan(plan, x_t, step_t, step_s, rng, mode, ddim_eta)
 
     @torch.inference_mode()
     def sample(self, batch_dict: dict, batch_size: int, num_steps: int, progress: bool = True, rng=None,
@@ -468,8 +503,11 @@ class CondContinuousTimeGaussianDiffusion(ContinuousTimeGaussianDiffusion):
         ``step_t`` to ``q_step`` in the resampling branch, :337 -- only reached for num_resample_steps > 1; here
         q_step gets the step tensors it is declared with.)"""
         cond = self.get_network_condition(input_dict=batch_dict, only_custom_condition=True)
-        return self._repaint_loop(lambda x, t, s, r: self.p_step(x, cond, t, s, rng=r), known, mask, num_steps,
-                                  num_resample_steps, jump_length, progress, rng, return_all)
+        self._reject_tensor_condition(cond["other_condition"])
+        plan = self.model.get_plan(known.shape[0])
+        plan.set_condition(cond["other_condition"])          # folded ONCE for the whole loop (not per reverse step)
+        return self._repaint_loop(lambda x, t, s, r: self._p_step_plan(plan, x, t, s, r, "ddpm", 0.0), known, mask,
+                                  num_steps, num_resample_steps, jump_length, progress, rng, return_all)
 
     @torch.inference_mode()
     def repaint(self, known, mask, batch_dict, num_steps, **kw):

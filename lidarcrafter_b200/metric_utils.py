@@ -50,7 +50,11 @@ def pcd2range(pcd, size, fov, depth_range, remission=None, labels=None, **kwargs
     single = pts.dim() == 2
     if single:
         pts = pts[None]
-    pts = pts[..., :3].contiguous()
+    if pts.shape[-1] != 3:
+        # the reference takes the depth as the norm over ALL columns (np.linalg.norm(pcd, 2, axis=1), metric_utils.py:72):
+        # an [M,4] cloud with intensity would silently change every range value -- pass xyz only
+        raise ValueError(f"pcd2range expects xyz columns only, got {pts.shape[-1]} columns")
+    pts = pts.contiguous()
     F, M, _ = pts.shape
     H, W = int(size[0]), int(size[1])
     feat, fill = None, 0.0
@@ -85,7 +89,7 @@ def range2xyz(range_img, fov, depth_range, depth_scale=None, log_scale=True, **k
 def preprocess_pcd(pcd, **kwargs):
     """metric_utils.py:309-313"""
     pts, is_np = _dev(pcd)
-    depth = torch.linalg.vector_norm(pts[:, :3], dim=1)
+    depth = torch.linalg.vector_norm(pts, dim=1)          # over ALL columns, like the reference (metric_utils.py:310)
     out = pts[(depth > kwargs['depth_range'][0]) & (depth < kwargs['depth_range'][1])]
     return _ret(out, is_np)
 

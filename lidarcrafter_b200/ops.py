@@ -60,8 +60,10 @@ def points_in_boxes_cpu(points, boxes):
     bx, _ = _dev(boxes)
     bx = bx.clone()
     bx[:, 3:6] += 0.2
-    if not isinstance(boxes, np.ndarray):
-        boxes[:, 3:6] += 0.2          # the reference mutates the caller's tensor in place
+    if not isinstance(boxes, np.ndarray) or boxes.dtype == np.float32:
+        # the reference enlarges the caller's boxes IN PLACE: torch tensors always, NumPy arrays when they are float32
+        # (check_numpy_to_torch: torch.from_numpy(x).float() shares memory with a float32 array, dataset/utils.py:13-16)
+        boxes[:, 3:6] += 0.2
     out = torch.zeros(bx.shape[0], pts.shape[0], dtype=torch.int32, device=pts.device)
     if bx.shape[0] and pts.shape[0]:
         _lib.get_lib().points_in_boxes(pts.data_ptr(), bx.data_ptr(), out.data_ptr(), bx.shape[0], pts.shape[0],

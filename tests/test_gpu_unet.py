@@ -252,3 +252,24 @@ def test_50_step_ddim_trajectory_vs_oracle(precision):
     json.dump(rec, open(os.path.join(out, f"trajectory_{precision}.json"), "w"))
     assert max(per_step) < TOL, rec
     assert drift[-1] < TOL, rec
+
+
+@pytest.mark.parametrize("nres,jump", [(1, 1), (2, 2)])
+def test_repaint_on_gpu_vs_reference_golden(nres, jump):
+    """RePaint (continuous_time.py:262-319) through the public repaint() on the B200 against the UNMODIFIED
+    reference's output (tests/golden/repaint_mini.npz); the reference drew from a CPU generator, so the same stream is
+    drawn on the host and copied over."""
+    res, nres_blocks, _ = CASES["eunet_mini"]
+    m, _ = make_unet(res, nres_blocks)
+    ddpm = L.ContinuousTimeGaussianDiffusion(m, prediction_type="eps", noise_schedule="cosine").cuda()
+    g = torch.Generator().manual_seed(31)
+    known = torch.rand(2, 2, 8, 1024, generator=g) * 2 - 1
+    mask = (torch.rand(2, 1, 8, 1024, generator=g) > 0.5).float()
+    g55 = torch.Generator().manual_seed(55)
+    ddpm.randn = lambda *shape, rng=None, **kw: torch.randn(*shape, generator=g55).to(kw.get("device", "cpu"))
+    ddpm.randn_like = lambda x, rng=None: torch.randn(*x.shape, generator=g55).to(x.device)
+    x = ddpm.repaint(known.cuda(), mask.cuda(), num_steps=2, num_resample_steps=nres, jump_length=jump, progress=False).cpu()
+    ref = torch.from_numpy(golden("repaint_mini")[f"repaint_{nres}_{jump}"])
+    err = rel_l2(x, ref)
+    print("repaint", nres, jump, err)
+    assert err < TOL
