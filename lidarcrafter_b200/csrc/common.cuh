@@ -95,26 +95,39 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait WITH a suspend-time hint: the hardware parks the warp until the phase completes (or the hint, in ns, expires).
+// Without the hint the wait returns after a short system-defined time and the poll loop re-issues at a high rate: measured
+// in the fused conv (transform warps doing FP32 / MUFU work next to ~10 polling warps), the pollers took so many issue slots
+// that the transform ran 2.8x slower than with the barriers already complete (profiles/r02_fused_front_ablation.txt).
+constexpr uint32_t MBAR_SUSPEND_NS = 10000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+// Bounded wait (~2^18 x 10 us): a protocol bug becomes a trap (launch error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (++spins > (1u << 18)) {
             printf("b200lidar: mbarrier timeout (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x,
                    blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
             __trap();
         }
+    }
+}
+
+// same bound, no printf: a CALL inside a register-heavy loop makes ptxas spill everything that is live across it
+__device__ __forceinline__ void mbar_wait_quiet(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 18)) __trap();
     }
 }
 
@@ -249,8 +262,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x * sigmoid(x); fast reciprocal (~2 ulp) -- the result is rounded to fp16 hi + lo right after
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)) with the two MUFU approximations (~2 ulp) in their flush-to-zero form: 3 FP + 2
+// MUFU instructions (the non-ftz __expf / __fdividef forms carry a denormal fix-up per call); identical results wherever
+// the intermediate values are normal, and 1 + denormal == 1 either way.  The result is rounded to fp16 hi + lo right after.
+__device__ __forceinline__ float silu_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 // ---- "fp16 + fp8 correction" operand encoding (conv precision mode parts = 3) ----
 //   x = hi16 + lo,  lo ~ 2^-11 |x|:   plane 0 keeps hi16 (fp16);  plane 1 keeps, per 16-channel chunk, two 16-byte

@@ -33,6 +33,8 @@
 //     5 MMA issuer (single thread, tcgen05.mma kind::f16, M=128 N=BN K=16) + TMEM owner.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -84,8 +86,8 @@ __device__ int g_conv_ablate = 0;
 
 constexpr int PIX = 128;  // pixels per tile row (= MMA M)
 constexpr int CONV_THREADS = 384;   // warps 0-3 and 8-11: epilogue (two per TMEM lane quarter); 4: A producer; 5, 7: MMA; 6: B producer
-constexpr int FUSE_THREADS = 512;   // fused front end: + warps 12-15 = transform warps (they replace the A producer)
-constexpr int XF_WARPS = 4;
+constexpr int FUSE_THREADS = 640;   // fused front end: + warps 12-19 = transform warps (they replace the A producer)
+constexpr int XF_WARPS = 8;
 constexpr int MAX_CIN = 1024;       // per-channel GroupNorm coefficients kept in shared memory by the fused front end
 constexpr int EPI_WARPS_MAX = 8;   // warps 0-3 and 8-11; ConvCfg::EW of them work (BN = 128 tiles: 4, see ConvCfg)
 
@@ -180,124 +182,39 @@ __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t a) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 
-// Four transform warps produce every A stage (one 16-channel K chunk of the R + 2 halo rows of a tile):
-//   lane -> (8-channel group g = lane / 16, pixel slot p8 = (lane / 2) % 8, channel quad = lane % 2): one item = 16 pixels x
-//   16 channels = two 16-byte loads per lane (pixels p8 and p8 + 8; a warp-level load covers 8 pixels x 64 contiguous bytes)
-//   and per pixel one 8-byte store into the fp16 hi slab + one 8-byte (lo) or two 4-byte (L8, A8) stores into plane 1 --
-//   every warp-level store covers 128 contiguous bytes of a slab (conflict-free).  Items of a stage: 8 per staged row (body
-//   pixels) + one for the 2 x RA ring-halo pixels.  Loads of the NEXT batch of items are issued before the math of the
-//   current one (register double buffer), across stage / tile boundaries too, so the L2 / HBM latency overlaps the math.
-template <int BN, int R, int TAPS, int NP>
-__device__ __forceinline__ void xform_warps(const ConvParams& p, uint8_t* smem, uint32_t sbase, uint32_t bar0, int tw,
-                                            int lane, int tile_lo, int tile_hi) {
-    using C = ConvCfg<BN, R, TAPS, NP, true>;
-    constexpr int RA = C::RA, HALO = C::HALO, KC = C::KC;
-    constexpr int NBODY = RA * 8;
-    constexpr int NIT = NBODY + (TAPS == 9 ? 1 : 0);        // items per stage
-    constexpr int IPW = (NIT + XF_WARPS - 1) / XF_WARPS;    // items per warp and stage
-    constexpr int NU = (IPW % 3 == 0 && IPW % 4 != 0) ? 3 : (IPW < 4 ? IPW : 4);   // items per batch
-    constexpr int NB = (IPW + NU - 1) / NU;                 // batches per stage
-    static_assert(KC == 16 && RA * 2 <= 16, "fused front end geometry");
-    float* s_a = reinterpret_cast<float*>(smem + C::OFF_COEF);
-    float* s_b = s_a + MAX_CIN;
-    float* s_mr = s_b + MAX_CIN;                            // {mean, rstd} per group
-    const int g = lane >> 4, p8 = (lane >> 1) & 7, q = lane & 1;
-    const int co = g * 8 + q * 4;                           // this lane's 4 channels inside the 16-channel chunk
-    const int WT = p.W / PIX, HG = p.H / R, NT = p.Cout / BN, NCH = p.Cin / KC;
-    const int xt = tw * 32 + lane;                          // 0..127 among the transform threads
+// per-channel affine coefficients of GroupNorm(+AdaGN) for sample b: y = x * s_a[c] + s_b[c] (same fp32 expression order
+// as gn_act_kernel).  Run by the COEFFICIENT WARP (warp 4 of the fused variant, the idle TMA-producer slot) -- not by the
+// transform warps: their unit loop keeps a stage of prefetched activations in registers and must not contain calls or
+// fp64 code.  One lane per group (<= 32 groups): the 32 group statistics are reduced in parallel (the first version
+// walked the groups serially with a warp reduction each: ~3 us in front of the first operand stage of every launch).
+// Handshake: COEF_FULL (1 arrival: coefficients of the next sample are in shared memory) / COEF_EMPTY (XF_WARPS arrivals:
+// every transform warp is done with the current ones).
+__device__ __forceinline__ void coef_warp(const ConvParams& p, float* s_a, float* s_b, float* s_mr, uint32_t bar_full,
+                                          uint32_t bar_empty, int b_lo, int b_hi, int lane) {
     const int Ctot = p.Cin;
-
-    struct Cur { int tile, c, k; };
-    auto advance = [&](Cur c) {
-        if (++c.k == NB) { c.k = 0; if (++c.c == NCH) { c.c = 0; ++c.tile; } }
-        return c;
-    };
-    // geometry of pixel j (0, 1) of item `it`: staged row r, slab position pos, source pixel (gh, ww), write / non-zero flags
-    auto geom = [&](int it, int j, int h0, int w0, int& r, int& pos, int& gh, int& ww, bool& wr, bool& nz) {
-        if (it < NBODY) {
-            r = it >> 3;
-            pos = 1 + ((it & 7) << 4) + j * 8 + p8;
-            ww = w0 + pos - 1;
-            wr = true; nz = true;
-        } else {
-            const int sp = j * 8 + p8;
-            r = sp >> 1;
-            const int side = sp & 1;
-            pos = side ? OPX - 1 : 0;
-            ww = side ? w0 + PIX : w0 - 1;
-            wr = r < RA; nz = wr;
-            if (ww < 0) { ww += p.W; nz = nz && p.ring; }
-            else if (ww >= p.W) { ww -= p.W; nz = nz && p.ring; }
-        }
-        gh = h0 + r - HALO;
-        nz = nz && gh >= 0 && gh < p.H;
-    };
-    auto tile_geom = [&](int tile, int& b, int& h0, int& w0) {
-        int t = tile;
-        const int wt = t % WT; t /= WT;
-        const int hg = t % HG; t /= HG;
-        b = t / NT;
-        h0 = hg * R; w0 = wt * PIX;
-    };
-    auto load = [&](const Cur& cu, float4 (&buf)[NU][2]) {
-        int b, h0, w0;
-        tile_geom(cu.tile, b, h0, w0);
-        const int cbase = cu.c * KC;
-        const float* src;
-        int Cs;
-        if (cbase < p.C0) { src = p.x0 + cbase + co; Cs = p.C0; }
-        else { src = p.x1 + (cbase - p.C0) + co; Cs = p.C1; }
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int it = tw + (cu.k * NU + u) * XF_WARPS;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                buf[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (it < NIT) {
-                    int r, pos, gh, ww;
-                    bool wr, nz;
-                    geom(it, j, h0, w0, r, pos, gh, ww, wr, nz);
-                    if (nz) buf[u][j] = ldg_stream_f4(src + ((size_t)(b * p.H + gh) * p.W + ww) * Cs);
-                }
-            }
-        }
-    };
-
-    uint32_t ia = 0;
-    int cur_b = -1;
-    float ca[4] = {1.f, 1.f, 1.f, 1.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
-    const int silu = p.gn_silu;
-
-    // per-channel affine coefficients of GroupNorm(+AdaGN) for sample b: y = x * s_a[c] + s_b[c] (same fp32 expression
-    // order as gn_act_kernel: the fused and the separate path give bit-identical operands)
-    auto coefficients = [&](int b) {
-        named_bar_sync(4, XF_WARPS * 32);        // every transform warp is done with the previous sample's coefficients
+    for (int b = b_lo, k = 0; b <= b_hi; ++b, ++k) {
+        mbar_wait(bar_empty, (k & 1) ^ 1);
         if (p.st0 != nullptr) {
             const int cpg = Ctot / p.gn_groups;
-            for (int gi = tw; gi < p.gn_groups; gi += XF_WARPS) {      // one warp per group, lanes over its channels
+            if (lane < p.gn_groups) {
+                const int gi = lane;
                 double su = 0.0, ss = 0.0;
-                for (int i = lane; i < cpg; i += 32) {
+                for (int i = 0; i < cpg; ++i) {
                     const int c = gi * cpg + i;
-                    const double* st = c < p.C0 ? p.st0 + ((size_t)b * p.C0 + c) * 2 : p.st1 + ((size_t)b * p.C1 + (c - p.C0)) * 2;
-                    su += st[0];
-                    ss += st[1];
+                    const double2 st = *reinterpret_cast<const double2*>(
+                        c < p.C0 ? p.st0 + ((size_t)b * p.C0 + c) * 2 : p.st1 + ((size_t)b * p.C1 + (c - p.C0)) * 2);
+                    su += st.x;
+                    ss += st.y;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    su += __shfl_xor_sync(0xffffffffu, su, o);
-                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                }
-                if (lane == 0) {
-                    const double n = (double)p.H * p.W * cpg;
-                    const double mean = su / n;
-                    double var = ss / n - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    s_mr[2 * gi] = (float)mean;
-                    s_mr[2 * gi + 1] = (float)(1.0 / sqrt(var + (double)p.gn_eps));
-                }
+                const double n = (double)p.H * p.W * cpg;
+                const double mean = su / n;
+                double var = ss / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mr[2 * gi] = (float)mean;
+                s_mr[2 * gi + 1] = (float)(1.0 / sqrt(var + (double)p.gn_eps));
             }
-            named_bar_sync(4, XF_WARPS * 32);
-            for (int c = xt; c < Ctot; c += XF_WARPS * 32) {
+            __syncwarp();
+            for (int c = lane; c < Ctot; c += 32) {
                 const int gi = c / cpg;
                 float a = s_mr[2 * gi + 1], bb = -s_mr[2 * gi] * s_mr[2 * gi + 1];
                 float ga = 1.f, be = 0.f, sc = 1.f, sh = 0.f;
@@ -312,84 +229,283 @@ __device__ __forceinline__ void xform_warps(const ConvParams& p, uint8_t* smem, 
                 s_b[c] = bb;
             }
         } else {
-            for (int c = xt; c < Ctot; c += XF_WARPS * 32) { s_a[c] = 1.f; s_b[c] = 0.f; }
+            for (int c = lane; c < Ctot; c += 32) { s_a[c] = 1.f; s_b[c] = 0.f; }
         }
-        named_bar_sync(4, XF_WARPS * 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full);
+    }
+}
+
+// Eight transform warps (two per SM sub-partition) produce every A stage = one 16-channel K chunk of the RA = R + 2 halo
+// rows of a tile.  The elementwise work (GroupNorm-apply, SiLU, split: ~10 instructions per element, two of them MUFU) on
+// halo-duplicated rows is 30-40 % of the SM's issue slots while the tensor pipe runs a stage, so the role is written for
+// instruction count AND instruction-level parallelism (two transform warps per scheduler cannot hide a ~200-cycle
+// FFMA -> EX2 -> RCP -> F2FP -> STS chain per unit by multithreading: the first version, one unit at a time with a
+// branch per unit, needed ~3.5 us per stage against ~1 us of MMAs):
+//   * unit = 8 pixels x 16 channels = ONE 16-byte load per lane: lane -> (8-channel group g = lane / 16, pixel p8 =
+//     (lane / 2) % 8, channel quad q = lane % 2); a warp-level load covers 8 pixels x 64 contiguous bytes; per pixel one
+//     8-byte store into the fp16 hi slab and one 8-byte (lo) or two 4-byte (L8, A8) stores into plane 1 -- every
+//     warp-level store covers 128 contiguous bytes of a slab (conflict-free);
+//   * warp w owns the pixel groups w and w + 8 of EVERY staged row: 2 RA units per stage with compile-time (row, group)
+//     -> all shared-memory offsets are immediates on one per-lane base;
+//   * units are processed in branch-free groups of XF_ILP (straight-line code: the compiler interleaves the chains);
+//     rows outside the image (first / last tile row only) take a second copy of the loop that selects zeros;
+//   * (3x3) the 8 RA ring-halo quads of a stage (RA rows x 2 sides x 4 channel quads) are ONE more unit; the warps take
+//     it in turns (stage i: warp i % 8), so a warp does 8 1/8 units per stage on average instead of 9;
+//   * memory-level parallelism: the units of stage s + 1 are loaded into the register slots of stage s as these are
+//     consumed (one whole stage, 32 KB per SM, in flight), across tile boundaries too.
+constexpr int XF_ILP = 4;
+
+template <int NP, bool SILU, bool SEL>
+__device__ __forceinline__ void xf_store(const float4 x4, const float (&ca)[4], const float (&cb)[4], bool valid,
+                                         uint32_t a_hi, uint32_t a_p1, uint32_t a_p1b, int ablate = 0) {
+    float y[4] = {fmaf(x4.x, ca[0], cb[0]), fmaf(x4.y, ca[1], cb[1]), fmaf(x4.z, ca[2], cb[2]), fmaf(x4.w, ca[3], cb[3])};
+    if (SILU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y[e] = silu_f(y[e]);
+    }
+    const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const float lo[4] = {y[0] - f01.x, y[1] - f01.y, y[2] - f23.x, y[3] - f23.y};
+    uint32_t w0 = *reinterpret_cast<const uint32_t*>(&h01), w1 = *reinterpret_cast<const uint32_t*>(&h23), w2, w3;
+    if (NP == 2) {
+        const __half2 l01 = __floats2half2_rn(lo[0], lo[1]), l23 = __floats2half2_rn(lo[2], lo[3]);
+        w2 = *reinterpret_cast<const uint32_t*>(&l01);
+        w3 = *reinterpret_cast<const uint32_t*>(&l23);
+    } else {
+        // plane 1 of a 16-channel chunk: slab 0 = L8 = e4m3(lo * 2^11), slab 1 = A8 = e4m3(x), 16 bytes per pixel each
+        w2 = f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE, lo[3] * F8_LO_SCALE);
+        w3 = f8x4(y[0], y[1], y[2], y[3]);
+    }
+    if (SEL) {   // zero padding (rows outside the image, non-ring edges) is exact: zeros, not act(b)
+        w0 = valid ? w0 : 0u; w1 = valid ? w1 : 0u; w2 = valid ? w2 : 0u; w3 = valid ? w3 : 0u;
+    }
+    if (ABL(256)) return;
+    if (ABL(1024) && (w0 ^ w1 ^ w2 ^ w3) != 0x5eadbeefu) return;    // keeps the math alive, drops the stores
+    sts_v2(a_hi, w0, w1);
+    if (NP == 2) {
+        sts_v2(a_p1, w2, w3);
+    } else {
+        sts_b32(a_p1, w2);
+        sts_b32(a_p1b, w3);
+    }
+}
+
+template <int BN, int R, int TAPS, int NP, bool SILU>
+__device__ __forceinline__ void xform_warps(const ConvParams& p, uint8_t* smem, uint32_t sbase, uint32_t bar0, int tw,
+                                            int lane, int tile_lo, int tile_hi, int ablate) {
+    using C = ConvCfg<BN, R, TAPS, NP, true>;
+    constexpr int RA = C::RA, HALO = C::HALO, KC = C::KC;
+    constexpr int UPS = 2 * RA;                 // body units per warp and stage
+    (void)ablate;
+    unsigned long long* dbg = (tw == 0 && lane == 0) ? g_conv_dbg : nullptr;
+    unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_start = dbg ? clock64() : 0;
+    constexpr bool HAS_HALO = TAPS == 9;
+    constexpr int HQ = 8 * RA;                  // ring-halo quads of a stage: RA rows x 2 sides x 4 channel quads
+    constexpr int HWN = (HQ + 31) / 32;         // warps on halo duty per stage (1; RA = 6: 2)
+    static_assert(KC == 16 && PIX == 16 * XF_WARPS && HWN <= XF_WARPS, "fused front end geometry");
+    const float* s_a = reinterpret_cast<const float*>(smem + C::OFF_COEF);
+    const float* s_b = s_a + MAX_CIN;
+    const uint32_t bar_coef_full = bar0 + 424u, bar_coef_empty = bar0 + 432u;
+    const int g = lane >> 4, p8 = (lane >> 1) & 7, q = lane & 1;
+    const int co = g * 8 + q * 4;                           // this lane's 4 channels inside the 16-channel chunk
+    const int WT = p.W / PIX, HG = p.H / R, NT = p.Cout / BN, NCH = p.Cin / KC;
+    const int px0 = tw * 8 + p8;                            // this lane's pixel inside the tile (first group; second: + 64)
+    // shared-memory byte offsets of this lane inside a stage: unit (r, e) adds r * ROWB + e * 64 * 16
+    const uint32_t so_hi = sbase + C::OFF_A + g * C::SLAB + (1 + px0) * 16 + q * 8;
+    const uint32_t so_p1 = sbase + C::OFF_A + C::A_PART + (NP == 2 ? g * C::SLAB + (1 + px0) * 16 + q * 8 : (1 + px0) * 16 + co);
+
+    // position in the stage stream: tile coordinates (order: wt fastest, then hg, n-tile, sample) + K chunk
+    struct Cur { int tile, c, wt, hg, nt, b; };
+    auto advance = [&](Cur& cu) {
+        if (++cu.c == NCH) {
+            cu.c = 0;
+            ++cu.tile;
+            if (++cu.wt == WT) {
+                cu.wt = 0;
+                if (++cu.hg == HG) {
+                    cu.hg = 0;
+                    if (++cu.nt == NT) { cu.nt = 0; ++cu.b; }
+                }
+            }
+        }
+    };
+    // bit r: staged row r of the tile row group hg lies inside the image
+    auto row_mask = [&](int hg) {
+        uint32_t m = 0;
+        const int h0 = hg * R - HALO;
+#pragma unroll
+        for (int r = 0; r < RA; ++r) m |= ((unsigned)(h0 + r) < (unsigned)p.H ? 1u : 0u) << r;
+        return m;
+    };
+    // fp32 source of K chunk c: tensor x0 | x1 (channel concat), its channel count, first channel inside it
+    auto chunk_src = [&](int c, const float*& src, int& Cs) {
+        const int cbase = c * KC;
+        if (cbase < p.C0) { src = p.x0 + cbase; Cs = p.C0; }
+        else { src = p.x1 + (cbase - p.C0); Cs = p.C1; }
+    };
+    float4 ring[UPS + 1];         // [UPS]: the halo unit, when this warp is on halo duty for the stage
+#pragma unroll
+    for (int u = 0; u <= UPS; ++u) ring[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // issue the loads of a whole stage `cu` (warp-uniform position) into the ring; ia_of = its index in this CTA's stream
+    uint32_t l_mask = 0;
+    const char* l_ptr = nullptr;         // this lane's element of staged row 0, pixel group 0
+    uint32_t l_row = 0, l_e = 0;         // byte strides: image row, 64 pixels
+    const float* l_hptr = nullptr;       // this lane's ring-halo quad (halo duty only)
+    bool l_h = false;
+    auto load_ctx = [&](const Cur& cu, uint32_t ia_of) {
+        const bool on = cu.tile < tile_hi;
+        l_mask = on ? row_mask(cu.hg) : 0u;
+        const float* src;
+        int Cs;
+        chunk_src(cu.c, src, Cs);
+        l_row = (uint32_t)(p.W * Cs * 4);
+        l_e = (uint32_t)(64 * Cs * 4);
+        const int h0 = cu.hg * R - HALO;
+        l_ptr = reinterpret_cast<const char*>(src) +
+                (((long long)(cu.b * p.H + h0) * p.W + cu.wt * PIX + px0) * Cs + co) * 4;
+        if (HAS_HALO) {
+            const uint32_t k = ((uint32_t)tw - ia_of * HWN) & (XF_WARPS - 1);      // halo slot of this warp in that stage
+            const int idx = (int)k * 32 + lane;
+            const int row = idx >> 3, side = (idx >> 2) & 1, cq = idx & 3;
+            int ww = cu.wt * PIX + (side ? PIX : -1);
+            bool ok = on && k < HWN && idx < HQ && ((l_mask >> row) & 1u);
+            if (ww < 0) { ww += p.W; ok = ok && p.ring; }
+            else if (ww >= p.W) { ww -= p.W; ok = ok && p.ring; }
+            l_h = ok;
+            l_hptr = src + ((long long)(cu.b * p.H + h0 + row) * p.W + ww) * Cs + cq * 4;
+        }
+    };
+    auto load_unit = [&](int u) {          // u: compile-time
+        if (u < UPS) {
+            const int r = u >> 1, e = u & 1;
+            if (((l_mask >> r) & 1u) && !ABL(64))        // warp-uniform
+                ring[u] = ldg_stream_f4(reinterpret_cast<const float*>(l_ptr + (size_t)(r * l_row + e * l_e)));
+        } else if (l_h) {
+            ring[UPS] = ldg_stream_f4(l_hptr);
+        }
     };
 
-    auto compute = [&](const Cur& cu, float4 (&buf)[NU][2]) {
-        int b, h0, w0;
-        tile_geom(cu.tile, b, h0, w0);
+    if (tile_lo >= tile_hi) return;
+    Cur cp{tile_lo, 0, 0, 0, 0, 0};
+    {
+        int t = tile_lo;
+        cp.wt = t % WT; t /= WT;
+        cp.hg = t % HG; t /= HG;
+        cp.nt = t % NT;
+        cp.b = t / NT;
+    }
+    uint32_t ia = 0, n_coef = 0;
+    load_ctx(cp, 0);
+#pragma unroll
+    for (int u = 0; u <= UPS; ++u)
+        if (u < UPS || HAS_HALO) load_unit(u);
+
+    int cur_b = -1;
+    while (cp.tile < tile_hi) {
         const uint32_t s = ia % C::SA;
-        if (cu.k == 0) {
-            if (b != cur_b) {            // (tiles of a CTA are contiguous: a few sample changes per launch at most)
-                coefficients(b);
-                cur_b = b;
+        if (cp.b != cur_b) {         // (tiles of a CTA are contiguous: a few sample changes per launch at most)
+            if (cur_b >= 0) {        // this warp holds no more coefficients of the previous sample
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_coef_empty);
             }
-            mbar_wait(bar0 + 96u + 8u * s, ((ia / C::SA) & 1) ^ 1);       // EMPTY_A(s)
-            const float4 a4 = *reinterpret_cast<const float4*>(s_a + cu.c * KC + co);
-            const float4 b4 = *reinterpret_cast<const float4*>(s_b + cu.c * KC + co);
+            mbar_wait_quiet(bar_coef_full, n_coef & 1);
+            ++n_coef;
+            cur_b = cp.b;
+        }
+        float ca[4], cb[4];
+        {
+            const float4 a4 = *reinterpret_cast<const float4*>(s_a + cp.c * KC + co);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b + cp.c * KC + co);
             ca[0] = a4.x; ca[1] = a4.y; ca[2] = a4.z; ca[3] = a4.w;
             cb[0] = b4.x; cb[1] = b4.y; cb[2] = b4.z; cb[3] = b4.w;
         }
-        const uint32_t stage = sbase + C::OFF_A + s * C::A_STAGE;
+        const uint32_t vm = row_mask(cp.hg);
+        const uint32_t st_hi = so_hi + s * C::A_STAGE, st_p1 = so_p1 + s * C::A_STAGE;
+        Cur nx = cp;
+        advance(nx);
+        {
+            DBG_T0();
+            mbar_wait_quiet(bar0 + 96u + 8u * s, ((ia / C::SA) & 1) ^ 1);       // EMPTY_A(s)
+            DBG_ACC(6);
+        }
+        load_ctx(nx, ia + 1);                        // the NEXT stage: its units take over the register slots as they free up
+        auto body = [&](auto sel_tag) {
+            constexpr bool SEL = decltype(sel_tag)::value;
 #pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int it = tw + (cu.k * NU + u) * XF_WARPS;
-            if (it >= NIT) continue;                 // warp-uniform
+            for (int u0 = 0; u0 < UPS; u0 += XF_ILP) {
+                float4 x[XF_ILP];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                int r, pos, gh, ww;
-                bool wr, nz;
-                geom(it, j, h0, w0, r, pos, gh, ww, wr, nz);
-                const float4 x4 = buf[u][j];
-                float y[4] = {fmaf(x4.x, ca[0], cb[0]), fmaf(x4.y, ca[1], cb[1]), fmaf(x4.z, ca[2], cb[2]),
-                              fmaf(x4.w, ca[3], cb[3])};
+                for (int j = 0; j < XF_ILP; ++j)
+                    if (u0 + j < UPS) {
+                        x[j] = ring[u0 + j];
+                        load_unit(u0 + j);
+                    }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (silu) y[e] = silu_f(y[e]);
-                    if (!nz) y[e] = 0.f;             // zero padding (rows outside the image, non-ring edges) is exact
+                for (int j = 0; j < XF_ILP; ++j)
+                    if (u0 + j < UPS) {
+                        const int r = (u0 + j) >> 1, e = (u0 + j) & 1;
+                        const uint32_t off = r * C::ROWB + e * 64 * 16;
+                        xf_store<NP, SILU, SEL>(x[j], ca, cb, (vm >> r) & 1u, st_hi + off, st_p1 + off, st_p1 + off + C::SLAB, ablate);
+                    }
+            }
+        };
+#ifdef B200_XF_PROF
+        const long long tb0 = clock64();
+#endif
+        if (ABL(128)) {}
+        else if (vm == (1u << RA) - 1u) body(std::false_type{});
+        else body(std::true_type{});
+#ifdef B200_XF_PROF
+        const long long tb1 = clock64();
+        dbg_acc[1] += tb1 - tb0;
+#endif
+        if (HAS_HALO) {
+            const uint32_t k = ((uint32_t)tw - ia * HWN) & (XF_WARPS - 1);
+            const float4 x4 = ring[UPS];
+            load_unit(UPS);                          // (only if this warp is on halo duty for the next stage)
+            if (k < HWN) {                           // warp-uniform: this warp converts the stage's ring-halo quads
+                const int idx = (int)k * 32 + lane;
+                const int row = idx >> 3, side = (idx >> 2) & 1, cq = idx & 3;
+                const int ww = cp.wt * PIX + (side ? PIX : -1);
+                const bool valid = ((vm >> row) & 1u) && (p.ring || (ww >= 0 && ww < p.W));
+                float ha[4], hb[4];
+                {
+                    const float4 a4 = *reinterpret_cast<const float4*>(s_a + cp.c * KC + cq * 4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_b + cp.c * KC + cq * 4);
+                    ha[0] = a4.x; ha[1] = a4.y; ha[2] = a4.z; ha[3] = a4.w;
+                    hb[0] = b4.x; hb[1] = b4.y; hb[2] = b4.z; hb[3] = b4.w;
                 }
-                const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const float lo[4] = {y[0] - f01.x, y[1] - f01.y, y[2] - f23.x, y[3] - f23.y};
-                if (!wr) continue;
-                const uint32_t row = stage + r * C::ROWB + pos * 16;
-                sts_v2(row + g * C::SLAB + q * 8, *reinterpret_cast<const uint32_t*>(&h01),
-                       *reinterpret_cast<const uint32_t*>(&h23));
-                if (NP == 2) {
-                    const __half2 l01 = __floats2half2_rn(lo[0], lo[1]), l23 = __floats2half2_rn(lo[2], lo[3]);
-                    sts_v2(row + C::A_PART + g * C::SLAB + q * 8, *reinterpret_cast<const uint32_t*>(&l01),
-                           *reinterpret_cast<const uint32_t*>(&l23));
-                } else {
-                    // plane 1 of a 16-channel chunk: slab 0 = L8 = e4m3(lo * 2^11), slab 1 = A8 = e4m3(x), 16 bytes per pixel each
-                    sts_b32(row + C::A_PART + co, f8x4(lo[0] * F8_LO_SCALE, lo[1] * F8_LO_SCALE, lo[2] * F8_LO_SCALE,
-                                                       lo[3] * F8_LO_SCALE));
-                    sts_b32(row + C::A_PART + C::SLAB + co, f8x4(y[0], y[1], y[2], y[3]));
-                }
+                const uint32_t pos = (side ? OPX - 1 : 0) * 16;
+                const uint32_t stage = sbase + C::OFF_A + s * C::A_STAGE + row * C::ROWB;
+                const uint32_t h_hi = stage + (cq >> 1) * C::SLAB + pos + (cq & 1) * 8;
+                const uint32_t h_p1 = stage + C::A_PART + (NP == 2 ? (cq >> 1) * C::SLAB + pos + (cq & 1) * 8 : pos + cq * 4);
+                if (idx < HQ) xf_store<NP, SILU, true>(x4, ha, hb, valid, h_hi, h_p1, h_p1 + C::SLAB);
             }
         }
-        if (cu.k == NB - 1) {
-            fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 8u * s);                    // FULL_A(s): one arrival per transform warp
-            ++ia;
-        }
-    };
-
-    Cur cu{tile_lo, 0, 0};
-    float4 buf0[NU][2], buf1[NU][2];
-    if (cu.tile < tile_hi) load(cu, buf0);
-    while (cu.tile < tile_hi) {
-        Cur nx = advance(cu);
-        if (nx.tile < tile_hi) load(nx, buf1);
-        compute(cu, buf0);
-        cu = nx;
-        if (cu.tile >= tile_hi) break;
-        nx = advance(cu);
-        if (nx.tile < tile_hi) load(nx, buf0);
-        compute(cu, buf1);
-        cu = nx;
+#ifdef B200_XF_PROF
+        const long long tb2 = clock64();
+        dbg_acc[2] += tb2 - tb1;
+#endif
+        if (!ABL(512)) fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * s);                    // FULL_A(s): one arrival per transform warp
+#ifdef B200_XF_PROF
+        dbg_acc[3] += clock64() - tb2;
+#endif
+        ++ia;
+        cp = nx;
+    }
+    if (dbg) {
+        dbg[blockIdx.x * 8 + 6] = dbg_acc[6];
+        dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
+#ifdef B200_XF_PROF
+        dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
+        dbg[blockIdx.x * 8 + 2] = dbg_acc[2];
+        dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
+#endif
     }
 }
 
@@ -430,6 +546,10 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
             mbar_init(ACC_FULL(s), 2);     // one commit from each of the two MMA issuer warps
             mbar_init(ACC_EMPTY(s), C::EW * 32);
         }
+        if (FUSE) {
+            mbar_init(bar0 + 424u, 1);             // COEF_FULL
+            mbar_init(bar0 + 432u, XF_WARPS);      // COEF_EMPTY
+        }
         fence_barrier_init();
     }
     pdl_launch_dependents();   // let the next kernel's CTAs be scheduled while this grid drains
@@ -445,19 +565,29 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
 
     const int ablate = g_conv_ablate;
     (void)ablate;
-    // Role dispatch by WARPGROUP first: the fused variant re-balances the register file with setmaxnreg (65536 / 512 = 128
-    // per thread at launch; the epilogue warpgroups need ~168: 32 accumulator + 2 x 32 residual prefetch registers; the
-    // issuers / weight producer ~56; the transform warps 120), and every warp of a warpgroup must execute the same
-    // setmaxnreg, which must dominate the code that uses the registers.
+    // Role dispatch by WARPGROUP first: the fused variant (640 threads: 96 registers per thread at launch) re-balances the
+    // register file with setmaxnreg -- epilogue warpgroups 120 (32 accumulator + 32 residual prefetch registers; the
+    // next-item residual prefetch of the 384-thread variant is dropped), issuers / weight producer / coefficient warp 56,
+    // transform warpgroups 88 (one stage of prefetched units + coefficients) = 472 of the 480 x 128 registers.  Every warp
+    // of a warpgroup must execute the same setmaxnreg, and it must dominate the code that uses the registers.
     const int wg = warp >> 2;
-    if (wg == 3) {
+    if (wg >= 3) {
         if constexpr (FUSE) {
-            reg_dealloc<120>();
-            xform_warps<BN, R, TAPS, NP>(p, smem, sbase, bar0, warp - 12, lane, tile_lo, tile_hi);
+            reg_dealloc<88>();
+            if (p.gn_silu) xform_warps<BN, R, TAPS, NP, true>(p, smem, sbase, bar0, warp - 12, lane, tile_lo, tile_hi, ablate);
+            else xform_warps<BN, R, TAPS, NP, false>(p, smem, sbase, bar0, warp - 12, lane, tile_lo, tile_hi, ablate);
         }
     } else if (wg == 1) {
     if constexpr (FUSE) reg_dealloc<56>();
-    if (warp == 4 && !FUSE) {
+    if (warp == 4 && FUSE) {
+        // ------------------------------ coefficient warp (fused front end) ------------------------------
+        if (tile_lo < tile_hi) {
+            float* s_a = reinterpret_cast<float*>(smem + C::OFF_COEF);
+            const int tps = WT * HG * NT;        // tiles per sample
+            coef_warp(p, s_a, s_a + MAX_CIN, s_a + 2 * MAX_CIN, bar0 + 424u, bar0 + 432u, tile_lo / tps,
+                      (tile_hi - 1) / tps, lane);
+        }
+    } else if (warp == 4) {
         // ------------------------------ producer warp: TMA-engine bulk copies for A and B ------------------------------
         uint32_t ia = 0;
         unsigned long long* dbg = g_conv_dbg;
@@ -666,14 +796,16 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
             }
             if (dbg) {
                 dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+#ifndef B200_XF_PROF
                 dbg[blockIdx.x * 8 + 1] = dbg_acc[1];
                 dbg[blockIdx.x * 8 + 2] = dbg_acc[2];
                 dbg[blockIdx.x * 8 + 3] = dbg_acc[3];
+#endif
             }
         }
     }
     } else {
-    if constexpr (FUSE) reg_alloc<168>();
+    if constexpr (FUSE) reg_alloc<120>();
     if (warp < 4 || C::EW == 8) {
         // ------------------------------ epilogue: warps 0-3 and 8-11; warp w reads TMEM lanes 32*(w%4) .. +31 ------------------------------
         // the two warps of a lane quarter split the (row, 32-column slice) work items of a tile between them
@@ -760,7 +892,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
                         for (int j = 0; j < 32; ++j) v[j] += v2[j];
                     }
                     float4 rn[8];      // next item's residual: in flight during this item's transpose / stores
-                    if (do_res && item + C::EG < NITEM) {
+                    if (!FUSE && do_res && item + C::EG < NITEM) {
                         const float* rp = res_ptr(item + C::EG);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rn[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
@@ -791,6 +923,13 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
                         s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
                         s2[0] += tv.x * tv.x; s2[1] += tv.y * tv.y; s2[2] += tv.z * tv.z; s2[3] += tv.w * tv.w;
                     }
+                    if (FUSE && do_res && item + C::EG < NITEM) {
+                        // 640-thread variant (120 registers here): the next item's residual is requested as soon as this
+                        // item's has been consumed -- in flight during the statistics and the next TMEM read / transpose
+                        const float* rp = res_ptr(item + C::EG);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (size_t)(4 * i) * p.Cout);
+                    }
                     if (p.stats) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -809,7 +948,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
                         }
                     }
                     __syncwarp();
-                    if (do_res && item + C::EG < NITEM) {
+                    if (!FUSE && do_res && item + C::EG < NITEM) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rv[i] = rn[i];
                     }

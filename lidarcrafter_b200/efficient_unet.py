@@ -185,9 +185,12 @@ class EfficientUNet(nn.Module):
 
         self._plans: dict = {}
         self.conv_impl = "tc"   # "ffma" = CUDA-core cross-check path (tests only)
-        # "fp16x3": error-compensated split (3 MMAs / product, ~fp32 accurate; meets the 1e-3 parity bar)
-        # "fp16"  : one MMA / product (~2e-3 relative through the UNet; 3x less tensor work)
-        self.precision = "fp16x3"
+        # "fp16f8" (default): fp16 MMA + ONE e4m3 MMA for both correction cross terms per product: 5e-5 relative per forward,
+        #           1.3e-4 at the end of a 50-step DDIM trajectory (tolerance 1e-3; measured: tests/test_gpu_unet.py
+        #           the 50-step trajectory test, profiles/r02_trajectory_*.json) at 2/3 of the tensor work
+        # "fp16x3": error-compensated fp16 split (3 MMAs / product, fp32-grade: 2e-6 per forward, 2e-5 after 50 steps)
+        # "fp16"  : one MMA / product (~2e-3 relative through the UNet: outside the tolerance, measurement only)
+        self.precision = "fp16f8"
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
 
     # ------------------------------------------------------------------------------------------

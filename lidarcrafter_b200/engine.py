@@ -91,6 +91,7 @@ def planes(parts: int) -> int:
 
 
 _TUNE_CACHE: dict = {}
+_TUNE_MS: dict = {}          # measured ms per launch of the chosen tile (this process only)
 _TUNE_FILE_LOADED = False
 
 
@@ -244,9 +245,12 @@ class PlanBuilder:
         self.ring = 1 if ring else 0
         self.stream = stream
         self.B = plan.B
-        # GroupNorm(+AdaGN)+SiLU+operand split fused IN FRONT of the conv (b200_conv_gn_tc): the default.  B200_FUSE_FRONT=0
-        # falls back to the separate gn_act launch + operand round trip (A/B measurements, profiles/r02_*).
-        self.fuse_front = os.environ.get("B200_FUSE_FRONT", "1") != "0"
+        # GroupNorm(+AdaGN)+SiLU+operand split fused IN FRONT of the conv (b200_conv_gn_tc) or as a separate gn_act launch +
+        # operand round trip: "auto" (default) measures both per layer shape at plan build and keeps the faster one -- the
+        # fused front end re-does the elementwise work per halo row and per output-channel tile, so it wins where launches
+        # are short (small batch) or the layer has ONE n-tile, and loses on the wide layers (profiles/r02_fused_front_*);
+        # B200_FUSE_FRONT=1 / 0 force one of them (A/B measurements, tests).
+        self.fuse_front = os.environ.get("B200_FUSE_FRONT", "auto")
 
     # ---- conv on tensor cores (or the FFMA cross-check path) ----
     def conv(self, a16: torch.Tensor, H: int, W: int, weight, bias, res: torch.Tensor | None, scale: float,
@@ -292,8 +296,10 @@ class PlanBuilder:
         H, W = a0.H, a0.W
         Cout, Cin, kh, kw = weight.shape
         assert Cin == a0.C + (a1.C if a1 else 0)
-        fused = (self.p.conv_impl == "tc" and self.fuse_front and self.p.parts in (2, 3) and a0.C % 16 == 0
+        fused = (self.p.conv_impl == "tc" and self.fuse_front != "0" and self.p.parts in (2, 3) and a0.C % 16 == 0
                  and (a1 is None or a1.C % 16 == 0) and Cin <= 1024 and groups <= 32)
+        if fused and self.fuse_front == "auto" and self.p.device.type == "cuda":
+            fused = self.tune_front(srcs, weight, bias, res, silu)
         if not fused:
             a16 = self.gn_act(srcs, gamma, beta, groups, eps, silu, ada=ada, ada_stride=ada_stride, ada_off=ada_off,
                               normalize=normalize)
@@ -323,6 +329,52 @@ class PlanBuilder:
                    flops=fl, nbytes=by)
         return out, st
 
+    def tune_front(self, srcs: list[Act], weight, bias, res, silu: bool) -> bool:
+        """True if the fused front end (one b200_conv_gn_tc launch) is faster than gn_act_f16 + b200_conv_tc for this layer
+        shape: both are timed on the device with their own best tile (CUDA events), cached per shape for the process."""
+        a0 = srcs[0]
+        a1 = srcs[1] if len(srcs) > 1 else None
+        H, W = a0.H, a0.W
+        Cout, Cin, kh, kw = weight.shape
+        key = ("front", self.B, H, W, a0.C, a1.C if a1 else 0, Cout, kh * kw, self.p.parts, res is not None, bool(silu))
+        _load_tune_file()
+        if key in _TUNE_CACHE:
+            return bool(_TUNE_CACHE[key][0])
+        out = torch.empty(self.B, H * W, Cout, dtype=torch.float32, device=self.p.device)
+        y = torch.empty(planes(self.p.parts), self.B * H * (W // 128) * (Cin // 8) * 130 * 8, dtype=torch.float16,
+                        device=self.p.device)
+        front = (_ptr(a0.t), a0.C, _ptr(a1.t) if a1 else 0, a1.C if a1 else 0)
+        for fr in (True, False):     # (tiles restored from B200_TUNE_FILE carry no time: measure again)
+            k = (self.B, H, W, Cin, Cout, kh * kw, self.p.parts, res is not None, fr)
+            if k in _TUNE_CACHE and k not in _TUNE_MS:
+                del _TUNE_CACHE[k]
+        self.tune_tile(None, H, W, weight, bias, res, out, front=front)
+        self.tune_tile(y, H, W, weight, bias, res, out)
+        gn_args = tuple(front) + (0, 0, 0, 0, 0, 0, 1, 0.0, 1 if silu else 0, _ptr(y), 0, self.p.parts, self.B, H, W, self.stream)
+        t_gn = self._time(self.lib.gn_act_f16, gn_args)
+        t_fused = _TUNE_MS[(self.B, H, W, Cin, Cout, kh * kw, self.p.parts, res is not None, True)]
+        t_conv = _TUNE_MS[(self.B, H, W, Cin, Cout, kh * kw, self.p.parts, res is not None, False)]
+        _TUNE_CACHE[key] = (1 if t_fused < t_gn + t_conv else 0, 0)
+        _save_tune_file()
+        return bool(_TUNE_CACHE[key][0])
+
+    @staticmethod
+    def _time(fn, args, batches: int = 3, n: int = 5) -> float:
+        """ms per launch: best of `batches` batches of `n` back-to-back launches (one batch lets power-cap / clock noise decide;
+        single launches are dominated by the launch gap, and by the interception cost under a profiler)"""
+        for _ in range(2):                           # warm-up (function attributes, caches, clocks)
+            fn(*args)
+        ms = float("inf")
+        for _ in range(batches):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn(*args)
+            e1.record()
+            e1.synchronize()
+            ms = min(ms, e0.elapsed_time(e1) / n)
+        return ms
+
     def tune_tile(self, a16, H, W, weight, bias, res, out, front=None):
         """(bn, rows) of b200_conv_tc / b200_conv_gn_tc for this shape: measured once per shape on the device (CUDA events,
         best of the candidate tiles), cached for the process; the analytic pick_tile() is only the no-GPU fallback of the
@@ -338,6 +390,8 @@ class PlanBuilder:
         best = None
         packed = {}
         for bn, rows in tile_candidates(self.B, H, W, Cout, self.p.parts):
+            if front is not None and taps == 9 and rows == 4:
+                continue          # 6 staged rows: the transform warps' register-resident prefetch stage does not fit (spills)
             pk = (bn, conv_merged(bn, rows, self.p.parts))
             if pk not in packed:
                 packed[pk] = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
@@ -350,22 +404,11 @@ class PlanBuilder:
                 fn = self.lib.conv_gn_tc
                 args = tuple(front) + (0, 0, 0, 0, 0, 0, 1, 0.0, 1) + tail + (Cout, taps, self.ring, bn, rows, self.p.parts,
                                                                              self.stream)
-            for _ in range(2):                           # warm-up (function attributes, caches, clocks)
-                fn(*args)
-            # best of 3 batches of 5 back-to-back launches: one batch let power-cap / clock noise pick a slower tile now
-            # and then, single launches are dominated by the launch gap (and by the interception cost under a profiler)
-            ms = float("inf")
-            for _ in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    fn(*args)
-                e1.record()
-                e1.synchronize()
-                ms = min(ms, e0.elapsed_time(e1))
+            ms = self._time(fn, args)
             if best is None or ms < best[0]:
                 best = (ms, bn, rows)
         _TUNE_CACHE[key] = (best[1], best[2])
+        _TUNE_MS[key] = best[0]
         _save_tune_file()
         return _TUNE_CACHE[key]
 

@@ -26,6 +26,19 @@ def test_unet_forward_vs_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["eunet_mini", "eunet_full"])
+def test_unet_fp16x3_mode_vs_reference_golden(name):
+    """error-compensated fp16 split (3 MMAs / product): fp32-grade"""
+    res, nres, B = CASES[name]
+    m, _ = make_unet(res, nres)
+    m = m.cuda()
+    m.precision = "fp16x3"
+    x, t, y_ref = golden_inputs(name)
+    err = rel_l2(m(x.cuda(), t.cuda()).cpu(), y_ref)
+    print(name, "fp16x3 rel-L2 vs reference golden:", err)
+    assert err < 5e-5
+
+
+@pytest.mark.parametrize("name", ["eunet_mini", "eunet_full"])
 def test_unet_fp16f8_mode_vs_reference_golden(name):
     """fp16 main term + e4m3 correction MMA: ~5e-5 relative, 20x inside the 1e-3 tolerance"""
     res, nres, B = CASES[name]
@@ -154,10 +167,11 @@ def test_per_sample_generators_and_sampling_shape():
 
 
 def test_unet_fused_front_equals_separate_launches(monkeypatch):
-    """the default plan (GroupNorm + SiLU + operand split inside the conv launches, b200_conv_gn_tc) gives the same forward
-    as B200_FUSE_FRONT=0 (separate gn_act launches writing the operand to HBM)"""
+    """B200_FUSE_FRONT=1 (GroupNorm + SiLU + operand split inside every conv launch, b200_conv_gn_tc) gives the same forward
+    as B200_FUSE_FRONT=0 (separate gn_act launches writing the operand to HBM); the default "auto" picks per layer shape"""
     res, nres, B = CASES["eunet_mini"]
     x, t, y_ref = golden_inputs("eunet_mini")
+    monkeypatch.setenv("B200_FUSE_FRONT", "1")
     m, _ = make_unet(res, nres)
     y0 = m.cuda()(x.cuda(), t.cuda()).cpu()
     assert "conv_gn_tc" in [n for n, _, _ in m.get_plan(B).plan.meta] and "gn_act_f16" not in [n for n, _, _ in m.get_plan(B).plan.meta]

@@ -5,11 +5,19 @@ import pytest
 import torch
 
 from abi_emulator import EmulatedLib
-from helpers import CASES, golden, golden_inputs, make_unet, rel_l2
+from helpers import CASES, golden, golden_inputs, rel_l2
+from helpers import make_unet as _make_unet
 from lidarcrafter_b200 import _lib
 import lidarcrafter_b200 as L
 
 torch.set_grad_enabled(False)
+
+
+def make_unet(res, nres, precision="fp16x3"):
+    """host-logic tests run the fp32-grade mode (their tolerances check wiring, not the fp16f8 default's 5e-5)"""
+    m, sd = _make_unet(res, nres)
+    m.precision = precision
+    return m, sd
 
 
 @pytest.fixture()
