@@ -132,6 +132,66 @@ def build_model(device, precision):
     return m, ddpm
 
 
+# LayoutUnetV1 / LayoutTransformerEncoder of the nuScenes box-layout configs (lidargen/utils/model/option_nusc_box_layout_v3.py
+# ModelConfig.params / ConditionModelConfig.params; the 'nuscenes-auto-reg-v2' variant only differs by in_channels = 13)
+LAYOUT_UNET = {'image_size': 32, 'use_fp16': False, 'use_scale_shift_norm': True, 'out_channels': 2, 'model_channels': 64,
+               'encoder_channels': 64, 'num_head_channels': 32, 'num_heads': -1, 'num_heads_upsample': -1,
+               'num_res_blocks': 2, 'num_attention_blocks': 1, 'resblock_updown': True, 'attention_ds': [4, 8],
+               'channel_mult': [1, 2, 4, 8], 'dropout': 0.1, 'use_checkpoint': False,
+               'use_positional_embedding_for_attention': True, 'attention_block_type': 'ObjectAwareCrossAttention'}
+LAYOUT_ENC = {'feature_map_size': [32, 1024], 'used_condition_types': ['obj_class', 'obj_bbox', 'is_valid_obj'],
+              'layout_length': 13, 'num_classes_for_layout_object': 9, 'mask_size_for_layout_object': 32, 'hidden_dim': 64,
+              'output_dim': 256, 'num_layers': 6, 'num_heads': 4, 'use_final_ln': True, 'use_positional_embedding': False,
+              'not_use_layout_fusion_module': False, 'resolution_to_attention': [4, 8], 'use_key_padding_mask': False,
+              'out_channels': 10}
+CLASS_SIZE = {'car': (4.67, 1.95, 1.74), 'truck': (7.12, 2.54, 2.90), 'construction_vehicle': (6.58, 2.75, 3.22),
+              'bus': (11.23, 2.94, 3.49), 'trailer': (12.02, 2.91, 3.84), 'motorcycle': (2.07, 0.77, 1.44),
+              'bicycle': (1.73, 0.62, 1.32), 'pedestrian': (0.77, 0.69, 1.78)}
+
+
+def build_temporal(device, precision):
+    """first-frame box-layout model + autoregressive model + the clip driver (tools/evaluation/sample_and_save_temporal.py:51-57)"""
+    import lidarcrafter_b200 as L
+    from lidarcrafter_b200.temporal import TemporalSampler
+    pair = []
+    for cin, seed in ((12, 0), (13, 2)):
+        m = L.unets.__all__["layout_unet_v1"](in_channels=cin, resolution=RES, **LAYOUT_UNET)
+        m.coords = L.get_linear_ray_angles(RES[0], RES[1], 10, -30)
+        m.load_state_dict(random_weights(m.state_dict(), seed=seed))
+        if hasattr(m, "precision"):
+            m.precision = precision
+        enc = L.unets.__all__["layout_encoder"](**dict(LAYOUT_ENC, out_channels=cin - 2))    # concat_cond 10 (+ 1 autoregressive depth)
+        enc.load_state_dict(random_weights(enc.state_dict(), seed=seed + 1))
+        pair.append(L.CondContinuousTimeGaussianDiffusion(m.eval(), enc.eval(), prediction_type="eps", noise_schedule="cosine",
+                                                          cond_mode="concat").to(device))
+    lu = L.LiDARUtility(RES, "log_depth", 1.45, 80.0, L.get_linear_ray_angles(RES[0], RES[1], 10, -30)).to(device)
+    return TemporalSampler(pair[0], pair[1], lu, resolution=RES), pair
+
+
+def synth_scenes(n: int, frames: int, seed: int = 0):
+    """12 boxes per sample, centre (x, y) ~ U(-40, 40) outside |.| < 3, z ~ U(-2, 0), class-mean sizes,
+    yaw ~ U(-pi, pi), class ~ U{1..8}; ego motion 0.5 m forward per frame, objects drift U(-0.4, 0.4) m per frame"""
+    import numpy as np
+    names_all = list(CLASS_SIZE)
+    out = []
+    for i in range(n):
+        rs = np.random.RandomState(1000 * seed + i)
+        names = ["ego"] + [names_all[k] for k in rs.randint(0, 8, 12)]
+        boxes = np.zeros((13, 7), np.float32)
+        for j in range(1, 13):
+            while True:
+                xy = rs.uniform(-40, 40, 2)
+                if np.abs(xy).max() >= 3:
+                    break
+            boxes[j, :2], boxes[j, 2] = xy, rs.uniform(-2, 0)
+            boxes[j, 3:6], boxes[j, 6] = CLASS_SIZE[names[j]], rs.uniform(-np.pi, np.pi)
+        trajs = np.zeros((13, max(frames - 1, 1), 2), np.float32)
+        trajs[0, :, 0] = 0.5
+        trajs[1:] = rs.uniform(-0.4, 0.4, (12, trajs.shape[1], 2))
+        out.append(dict(gt_boxes=boxes, gt_names=names, gt_fut_trajs=trajs))
+    return out
+
+
 def cpu_reference_run(steps: int, warmup: int, B: int):
     """The reference's CPU path (oracle port of lidargen EfficientUNet + DDIM update, fp32, all host threads).
     /root/reference is not available on the GPU box, so the port (pinned to the reference by tests/golden) is timed."""
@@ -180,6 +240,83 @@ def conv_shape(name, a):
     return None
 
 
+def run_temporal(args, dev, rank, world, local):
+    """--workload clip | rollout: the composed generation loop (lidarcrafter_b200.temporal.TemporalSampler.generate =
+    tools/evaluation/sample_and_save_temporal.py:203-333): first frame from the box-layout model, then the autoregressive
+    frames with the device-resident glue in between; one all-gather of the clips at the end."""
+    import torch.distributed as dist
+    from lidarcrafter_b200.dist import all_gather_samples, shard_range
+    rollout = args.workload == "rollout"
+    frames = args.frames or (20 if rollout else 5)
+    total = 8 if rollout else 4 * world                 # configs[4]: batch 8 in total (strong scaling); configs[2]: 4 per GPU
+    lo, hi = shard_range(total, rank, world)
+    K, W = args.steps, args.warmup
+    ts, models = build_temporal(dev, args.precision)
+    scenes = synth_scenes(total, frames)[lo:hi]
+    Bl = hi - lo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run(nf, k):
+        if Bl == 0:
+            clips = torch.zeros(0, nf, 5, *RES, device=dev)
+        else:
+            gens = [torch.Generator(device=dev).manual_seed(100 + i) for i in range(lo, hi)]
+            clips = ts.generate(scenes, num_frames=nf, num_steps=k, mode="ddim", temporal_mode="ddim", rng=gens)
+        return all_gather_samples(clips, total)
+    run(min(frames, 2), max(W, 1))                      # warm-up: plans, tile tuning, step graphs of both models
+    barrier()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    clips = run(frames, K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = clk.stop() if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms)
+    assert clips.shape == (total, frames, 5, *RES) and bool(torch.isfinite(clips).all())
+    # e2e: the same public call with the result read back to the host (the reference writes every frame to disk)
+    barrier()
+    t0 = time.perf_counter()
+    host = run(frames, K).cpu()
+    torch.cuda.synchronize(dev)
+    ms_e = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        tms = torch.tensor([ms_e], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e = float(tms)
+    if rank == 0:
+        n_steps = total * frames * K
+        plans = [mm.model.get_plan(Bl) for mm in models] if Bl else []
+        line = {"metric": METRIC, "value": n_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / (frames * K), "higher_is_better": True, "scaling": "strong" if rollout else "weak",
+                "vs_baseline": None, "dtype": DTYPE_NOTE[args.precision], "data": "synthetic",
+                "config": {"workload": ("configs[4]: tri-branch autoregressive rollout, %d frames, batch %d over %d GPU(s)" if rollout else
+                                        "configs[2]: layout-conditioned %d-frame clip, batch %d over %d GPU(s)") % (frames, total, world) +
+                                       f", LayoutUnetV1 + LayoutTransformerEncoder, {K}-step DDIM per frame, 12 boxes per scene",
+                           "frames": frames, "global_batch": total, "batch_per_gpu": Bl, "resolution": list(RES),
+                           "l2": "per-step working set of activations >> 126 MB L2"},
+                "clocks": clocks, "seconds_per_clip_batch": ms / 1e3,
+                "e2e": {"value": n_steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int(host.numel() * 4 / (frames * K)),
+                        "note": "generate() + device->host copy of the clips, wall clock; conditioning (13 boxes per frame) is uploaded inside the call"},
+                "gpu_launches": int(sum(p.plan.n_kernels + 1 for p in plans) / max(len(plans), 1) * frames * K),
+                "kernels_per_step": [p.plan.n_kernels + 1 for p in plans]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +326,10 @@ def main():
     ap.add_argument("--precision", default=DEFAULT_PRECISION, choices=["fp16x3", "fp16f8", "fp16"])
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU,
                     help="frames per GPU (default 8 = BASELINE configs[1]; other values are side measurements)")
+    ap.add_argument("--workload", default="frame", choices=["frame", "clip", "rollout"],
+                    help="frame = BASELINE configs[1] (headline); clip = configs[2] (5-frame layout-conditioned clip, batch 4 per "
+                         "GPU); rollout = configs[4] (20-frame autoregressive rollout, batch 8 in total, split over the GPUs)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per clip (default 5 for clip, 20 for rollout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel time table to stderr")
     ap.add_argument("--profiler-range", action="store_true",
@@ -208,8 +349,10 @@ def main():
         k = max(1, min(args.steps, 2))
         w = 1 if args.warmup > 0 else 0
         v, dt, cores = cpu_reference_run(k, w, B)
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+        # "steps" / "warmup" are what was TIMED (a bounded sample: the CPU path needs ~2 s per batch-8 step), the requested
+        # values ride along
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+                "warmup": w, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{k} DDIM step(s) at batch {B} after {w} warm-up (oracle port of the reference "
@@ -225,32 +368,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
+    if args.workload != "frame":
+        return run_temporal(args, dev, rank, world, local)
+    from lidarcrafter_b200.dist import sample_sharded
     m, ddpm = build_model(dev, args.precision)
     plan = m.get_plan(B)
-    entry = ddpm._step_graph(plan, B, "ddim")
     K, W = args.steps, args.warmup
-    n_tot = K + W
     steps = torch.linspace(1.0, 0.0, 51, device=dev)
-    lts, coefs = [], []
-    for i in range(n_tot):
-        j = i % 50
-        lt, coef = ddpm._coefficients(steps[j].repeat(B), steps[j + 1].repeat(B), 0.0)
-        lts.append(lt); coefs.append(coef)
     x0 = torch.randn(B, 2, *RES, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
-    plan.x_in.copy_(x0)
-
-    def one_step(i):
-        plan.t_in.copy_(lts[i])
-        entry["coef"].copy_(coefs[i])
-        entry["graph"].replay()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(W):
-        one_step(i)
+    # the timed call is the PUBLIC sampler: dist.sample_sharded -> GaussianDiffusion.sample(batch_size, num_steps, mode="ddim")
+    # (continuous_time.py:236-260: initial noise, per-step tables, per-step noise draw, K denoiser steps) + the path's single
+    # collective at the end (all-gather of the final frames, 16 MiB at batch 64)
+    gens = [torch.Generator(device=dev).manual_seed(100 + i) for i in range(B * world)]
+    sample_sharded(ddpm, B * world, num_steps=max(W, 1), rng=gens, mode="ddim")          # W untimed warm-up steps
     barrier()
     clk = ClockSampler(local)
     if rank == 0:
@@ -260,15 +396,12 @@ def main():
     if args.profiler_range:
         torch.cuda.profiler.start()
     e0.record()
-    for i in range(K):
-        one_step(W + i)
-    if world > 1:  # the path's single collective: gather the final frames (16 MiB at batch 64)
-        out = [torch.empty_like(plan.x_in) for _ in range(world)]
-        dist.all_gather(out, plan.x_in)
+    x_final = sample_sharded(ddpm, B * world, num_steps=K, rng=gens, mode="ddim")         # exactly K timed steps
     e1.record()
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.stop()
+    assert x_final.shape[0] == B * world and bool(torch.isfinite(x_final).all())
     ms = e0.elapsed_time(e1)
     clocks = clk.stop() if rank == 0 else None
     if world > 1:
@@ -389,13 +522,39 @@ def main():
             "note": "bound = max(algorithmic FLOPs / measured bf16 peak, algorithmic bytes / measured HBM peak) per launch "
                     "(SURVEY 8d); tensor_pipe_tflops counts the MMAs really issued per algorithmic product "
                     "(fp16x3: 3 fp16; fp16f8: 1 fp16 + 1 e4m3 at K=32; fp16: 1)"}
+    # ---- the north_star's unit: the ResBlock (norm1 -> SiLU -> conv1 -> AdaGN -> SiLU -> conv2 (+1x1 skip) + residual), ALL of
+    # its launches; algorithmic bytes / FLOPs per SURVEY 8d: 4 B (2 Cin + 3 Cout) per pixel + weights, 2 (9 Cin Cout + 9 Cout^2
+    # [+ Cin Cout]) per pixel ----
+    blocks = {}
+    for tag, (name, ms_k, fl, by_k) in zip(plan.plan.tags, prof):
+        if tag.startswith("resblock"):
+            shape = tag.rsplit(" #", 1)[0]
+            d = blocks.setdefault(shape, {"ms": 0.0, "launches": 0, "ids": set()})
+            d["ms"] += ms_k; d["launches"] += 1; d["ids"].add(tag)
+    if blocks:
+        shape, d = max(blocks.items(), key=lambda kv: kv[1]["ms"])
+        hw, chans = shape.split()[1], shape.split()[2]
+        h_, w_ = (int(v) for v in hw.split("x"))
+        ci, co = (int(v) for v in chans.split("->"))
+        skip = shape.endswith("skip")
+        nb = len(d["ids"])
+        by_blk = 4.0 * B * h_ * w_ * (2 * ci + 3 * co) + 4.0 * 9 * (ci + co) * co
+        fl_blk = 2.0 * B * h_ * w_ * (9 * ci * co + 9 * co * co + (ci * co if skip else 0))
+        ms_blk = d["ms"] / nb
+        t_h, t_t = by_blk / (pk["hbm_gbs"] * 1e9) * 1e3, fl_blk / (pk["tf"] * 1e12) * 1e3
+        roof["resblock"] = {"shape": shape, "blocks_per_step": nb, "launches_per_block": d["launches"] / nb, "ms_per_block": ms_blk,
+                            "share_of_step": d["ms"] / tot_ms, "algorithmic_mb": by_blk / 1e6, "algorithmic_gflop": fl_blk / 1e9,
+                            "bound": "hbm" if t_h >= t_t else "tensor", "ms_at_peak": max(t_h, t_t),
+                            "achieved_gbs": by_blk / (ms_blk / 1e3) / 1e9, "achieved_tflops": fl_blk / (ms_blk / 1e3) / 1e12,
+                            "frac": max(t_h, t_t) / ms_blk}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE_NOTE[args.precision],
             "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                     "steps": Ke},
-            "gpu_launches": K * (plan.plan.n_kernels + 1), "kernels_per_step": plan.plan.n_kernels + 1,
+            "gpu_launches": K * (plan.plan.n_kernels + 2), "kernels_per_step": plan.plan.n_kernels + 1,
+            "timed_call": "dist.sample_sharded -> ContinuousTimeGaussianDiffusion.sample(batch_size, num_steps=K, mode='ddim')",
             "roofline": roof,
             "algorithmic_gflop_per_sample_step": plan.plan.flops / B / 1e9}
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only

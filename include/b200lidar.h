@@ -215,6 +215,29 @@ int b200_range_project(const float* points, const int* npts, float* out, int* gr
                        int M, int H, int W, float min_depth, float max_depth, float fov_up_deg,
                        float fov_down_deg, void* stream);
 
+/* the same projection of a FLOAT64 point array (the temporal glue re-projects the ego-motion-warped background, a float64
+ * array: tools/vis_tools/utils/pipe_related.py:244-255,271-280 -> custom_dataset.py:59-62; every intermediate of
+ * common.py:38-91 is float64 there, only the final image is cast to float32).
+ *   points fp64 [F,M,4], npts int32 [F] (may be NULL), out fp32 [F,H,W,6], zbuf uint64 scratch [F,H,W],
+ *   winner int32 scratch [F,H,W] (index of the surviving point per pixel, -1: none)                                   */
+int b200_range_project_f64(const double* points, const int* npts, float* out, void* zbuf, int* winner, int F, int M,
+                           int H, int W, float min_depth, float max_depth, float fov_up_deg, float fov_down_deg,
+                           void* stream);
+
+/* ---- 3-D boxes -> 2-D boxes, condition mask, loss-weight map --------------------------------------------
+ * replaces convert_boxes_to_2d + convert_points_to_2d (dataset/transforms_3d/common.py:99-216), called per frame by
+ * NuscDataset.pre_process (dataset/nuscenes_dataset.py:389-398).
+ *   boxes     [F,N,8] (x, y, z, l, w, h, yaw, class) fp32 (boxes_f64 = 0) or fp64 (1): the reference's dtype flow
+ *             (corner offsets / cos, sin / centre depth in the array's dtype, projection in fp64) follows the input
+ *   boxes_2d  fp64 [F,N,4] normalised (x1, y1, x2, y2);  mask fp32 [F,2,H,W] (class id, centre depth; later boxes
+ *             overwrite earlier ones; a rectangle wider than 0.6 W wraps around the azimuth seam);
+ *   weight    fp32 [F,H,W] = exp(sum_i inside_i (3 - area_i / max area)) or NULL
+ *   workspace b200_boxes_to_mask_workspace(F, N) bytes of device memory                                            */
+size_t b200_boxes_to_mask_workspace(int F, int N);
+int b200_boxes_to_mask(const void* boxes, int boxes_f64, int F, int N, int H, int W, float fov_up_deg,
+                       float fov_down_deg, double* boxes_2d, float* mask, float* weight, void* workspace,
+                       void* stream);
+
 /* ---- K7: points in boxes / voxel index ----------------------------------------------------------------
  * points_in_boxes_cpu semantics (ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-168, MARGIN 1e-2):
  *   pts [M,3], boxes [N,7] -> out int32 [N,M] in {0,1}                                                */

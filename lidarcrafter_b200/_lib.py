@@ -48,6 +48,9 @@ PROTOTYPES = {
     "b200_sampler_update": (I, [P, P, P, P, P, I, I, I, I, F, P]),
     "b200_sampler_coefficients": (I, [P, P, I, F, F, F, F, F, P, P, I, P]),
     "b200_range_project": (I, [P, P, P, P, P, I, I, I, I, F, F, F, F, P]),
+    "b200_range_project_f64": (I, [P, P, P, P, P, I, I, I, I, F, F, F, F, P]),
+    "b200_boxes_to_mask_workspace": (SZ, [I, I]),
+    "b200_boxes_to_mask": (I, [P, I, I, I, I, I, F, F, P, P, P, P, P]),
     "b200_points_in_boxes": (I, [P, P, P, I, I, P]),
     "b200_points_in_boxes_first": (I, [P, P, P, I, I, I, P]),
     "b200_voxel_index": (I, [P, P, P, I, I, I, I, I, P]),
@@ -63,7 +66,7 @@ PROTOTYPES = {
 }
 
 _NO_STATUS = {"b200_conv_merged", "b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems",
-              "b200_sparse_quantize_workspace"}
+              "b200_sparse_quantize_workspace", "b200_boxes_to_mask_workspace"}
 
 
 class B200LidarError(RuntimeError):

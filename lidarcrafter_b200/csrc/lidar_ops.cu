@@ -179,6 +179,183 @@ __global__ void depth_to_xyz_kernel(const float* __restrict__ xn, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// range projection of float64 points (the temporal glue re-projects the ego-motion-warped background, a float64 array:
+// tools/vis_tools/utils/pipe_related.py:244-255 -> CustomDataset -> load_points_as_images; every intermediate is fp64
+// there and only the final image is cast to fp32).  The 64-bit depth leaves no room for the point index in one atomic
+// key, so: pass 1 atomicMin(depth bits), pass 2 atomicMax(index) among the points AT the minimum, pass 3 gather.
+// ---------------------------------------------------------------------------------------------------------
+struct ProjParams64 {
+    const double* points;
+    const int* npts;
+    float* out;
+    unsigned long long* zbuf;
+    int* win;
+    int F, M, H, W;
+    double min_depth, max_depth;
+    double h_up, h_down;
+};
+
+__device__ __forceinline__ void project_point64(const ProjParams64& p, double x, double y, double z, double& depth, int& gh,
+                                                int& gw) {
+    depth = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    const double elev = asin(__ddiv_rn(z, __dadd_rn(depth, 1e-6))) + fabs(p.h_down);
+    double g = __dsub_rn(1.0, __ddiv_rn(elev, __dsub_rn(p.h_up, p.h_down)));
+    g = floor(__dmul_rn(g, (double)p.H));
+    gh = (int)fmin(fmax(g, 0.0), (double)(p.H - 1));
+    const double az = -atan2(y, x);
+    double t = __dmul_rn(__dadd_rn(__ddiv_rn(az, 3.141592653589793), 1.0), 0.5);      // (az / pi + 1) / 2
+    t = fmod(t, 1.0);
+    if (t < 0.0) t = __dadd_rn(t, 1.0);
+    const double gwf = floor(__dmul_rn(t, (double)p.W));
+    gw = (int)fmin(fmax(gwf, 0.0), (double)(p.W - 1));
+}
+
+template <int PASS>
+__global__ void proj64_scatter_kernel(const ProjParams64 p) {
+    const int f = blockIdx.y;
+    const int n = p.npts ? p.npts[f] : p.M;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double* pt = p.points + ((size_t)f * p.M + i) * 4;
+        double depth;
+        int gh, gw;
+        project_point64(p, pt[0], pt[1], pt[2], depth, gh, gw);
+        const size_t px = ((size_t)f * p.H + gh) * p.W + gw;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(depth);   // depth >= 0: bits order like values
+        if (PASS == 0) atomicMin(p.zbuf + px, key);
+        else if (p.zbuf[px] == key) atomicMax(p.win + px, i);     // equal depth: highest index wins (as in the fp32 kernel)
+    }
+}
+
+__global__ void proj64_gather_kernel(const ProjParams64 p) {
+    const int f = blockIdx.y;
+    const int hw = p.H * p.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+        const int idx = p.win[(size_t)f * hw + i];
+        float* o = p.out + ((size_t)f * hw + i) * 6;
+        if (idx < 0) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) o[c] = 0.f;
+        } else {
+            const double* pt = p.points + ((size_t)f * p.M + idx) * 4;
+            const double depth = __longlong_as_double((long long)p.zbuf[(size_t)f * hw + i]);
+            o[0] = (float)pt[0]; o[1] = (float)pt[1]; o[2] = (float)pt[2]; o[3] = (float)pt[3];
+            o[4] = (float)depth;
+            o[5] = (depth >= p.min_depth && depth <= p.max_depth) ? 1.f : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-D boxes -> 2-D boxes / condition mask / loss-weight map (dataset/transforms_3d/common.py:99-216, convert_boxes_to_2d)
+//   boxes [F,N,8] (x, y, z, l, w, h, yaw, class) as fp32 or fp64 -- the reference's dtype flow depends on it: corner
+//   offsets, centre, centre depth, cos / sin of the yaw are evaluated in the boxes' dtype, the rotation and the projection
+//   of the 8 corners in fp64.  Pixel rectangles are int(x * W) of the fp64 grid coordinates; later boxes overwrite earlier
+//   ones; a rectangle wider than 0.6 W straddles the azimuth seam and is drawn as [0, x1) + [x2, W).
+// ---------------------------------------------------------------------------------------------------------
+struct BoxRec { int x1, y1, x2, y2, wrap; float cls, depth, weight; };
+
+template <typename T>
+__device__ __forceinline__ T box_cos(T a);
+template <> __device__ __forceinline__ float box_cos<float>(float a) { return cos_f(a); }
+template <> __device__ __forceinline__ double box_cos<double>(double a) { return cos(a); }
+template <typename T>
+__device__ __forceinline__ T box_sin(T a);
+template <> __device__ __forceinline__ float box_sin<float>(float a) { return sin_f(a); }
+template <> __device__ __forceinline__ double box_sin<double>(double a) { return sin(a); }
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+template <typename T>
+__global__ void box_rect_kernel(const T* __restrict__ boxes, int N, int H, int W, double h_up, double h_down,
+                                double* __restrict__ boxes_2d, BoxRec* __restrict__ rec) {
+    extern __shared__ double s_uv[];          // [N * 8][2] normalised (grid_w / W, grid_h / H) of the corners
+    __shared__ int s_max_area;
+    const int f = blockIdx.x;
+    const T* bf = boxes + (size_t)f * N * 8;
+    if (threadIdx.x == 0) s_max_area = INT_MIN;
+    for (int t = threadIdx.x; t < N * 8; t += blockDim.x) {
+        const int i = t >> 3, k = t & 7;
+        const T* b = bf + i * 8;
+        // corner offsets in the boxes' dtype: x: +l/2 for corners 0,1,4,5; y: +w/2 for 0,3,4,7; z: +h/2 for 0..3
+        const T hx = b[3] / (T)2, hy = b[4] / (T)2, hz = b[5] / (T)2;
+        const double lx = (double)((k == 0 || k == 1 || k == 4 || k == 5) ? hx : -hx);
+        const double ly = (double)((k == 0 || k == 3 || k == 4 || k == 7) ? hy : -hy);
+        const double lz = (double)(k < 4 ? hz : -hz);
+        const double c = (double)box_cos<T>(b[6]), s = (double)box_sin<T>(b[6]);
+        // rotz @ corner (fp64; the zero entries of the rotation add exact zeros), + centre
+        const double x = __dadd_rn(__dadd_rn(__dmul_rn(c, lx), __dmul_rn(-s, ly)), (double)b[0]);
+        const double y = __dadd_rn(__dadd_rn(__dmul_rn(s, lx), __dmul_rn(c, ly)), (double)b[1]);
+        const double z = __dadd_rn(lz, (double)b[2]);
+        const double depth = __dadd_rn(__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z))), 1e-6);
+        const double elev = asin(__ddiv_rn(z, depth)) + fabs(h_down);
+        double g = __dsub_rn(1.0, __ddiv_rn(elev, __dsub_rn(h_up, h_down)));
+        g = fmin(fmax(floor(__dmul_rn(g, (double)H)), 0.0), (double)(H - 1));
+        const double az = -atan2(y, x);
+        double tw = __dmul_rn(__dadd_rn(__ddiv_rn(az, 3.141592653589793), 1.0), 0.5);
+        tw = fmod(tw, 1.0);
+        if (tw < 0.0) tw = __dadd_rn(tw, 1.0);
+        const double gw = fmin(fmax(floor(__dmul_rn(tw, (double)W)), 0.0), (double)(W - 1));
+        s_uv[2 * t] = __ddiv_rn(gw, (double)W);
+        s_uv[2 * t + 1] = __ddiv_rn(g, (double)H);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double u0 = s_uv[16 * i], v0 = s_uv[16 * i + 1], u1 = u0, v1 = v0;
+        for (int k = 1; k < 8; ++k) {
+            u0 = fmin(u0, s_uv[16 * i + 2 * k]); u1 = fmax(u1, s_uv[16 * i + 2 * k]);
+            v0 = fmin(v0, s_uv[16 * i + 2 * k + 1]); v1 = fmax(v1, s_uv[16 * i + 2 * k + 1]);
+        }
+        double* o = boxes_2d + ((size_t)f * N + i) * 4;
+        o[0] = u0; o[1] = v0; o[2] = u1; o[3] = v1;
+        BoxRec r;
+        r.x1 = (int)__dmul_rn(u0, (double)W); r.x2 = (int)__dmul_rn(u1, (double)W);
+        r.y1 = (int)__dmul_rn(v0, (double)H); r.y2 = (int)__dmul_rn(v1, (double)H);
+        r.wrap = ((double)(r.x2 - r.x1) / (double)W > 0.6) ? 1 : 0;
+        const T* b = bf + i * 8;
+        r.cls = (float)b[7];
+        // centre depth in the boxes' dtype: ||(x, y, z)|| + 1e-6
+        const T cd = sqrt_rn(add_rn(add_rn(mul_rn(b[0], b[0]), mul_rn(b[1], b[1])), mul_rn(b[2], b[2])));
+        r.depth = (float)add_rn(cd, (T)1e-6);
+        const int area = (r.wrap ? (W - r.x2 + r.x1) : (r.x2 - r.x1)) * (r.y2 - r.y1);
+        r.weight = (float)area;          // finished below, once the largest area is known
+        atomicMax(&s_max_area, area);
+        rec[(size_t)f * N + i] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        BoxRec& r = rec[(size_t)f * N + i];
+        r.weight = __fsub_rn(3.f, __fdiv_rn(r.weight, (float)s_max_area));      // fp32: 3 - area / max(area)
+    }
+}
+
+__global__ void box_raster_kernel(const BoxRec* __restrict__ rec, int N, int H, int W, float* __restrict__ mask,
+                                  float* __restrict__ weight) {
+    extern __shared__ BoxRec s_rec[];
+    const int f = blockIdx.y;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_rec[i] = rec[(size_t)f * N + i];
+    __syncthreads();
+    const int hw = H * W;
+    for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < hw; px += gridDim.x * blockDim.x) {
+        const int y = px / W, x = px - y * W;
+        float cls = 0.f, dep = 0.f, wsum = 0.f;
+        for (int i = 0; i < N; ++i) {
+            const BoxRec& r = s_rec[i];
+            const bool in = y >= r.y1 && y < r.y2 && (r.wrap ? (x < r.x1 || x >= r.x2) : (x >= r.x1 && x < r.x2));
+            if (in) { cls = r.cls; dep = r.depth; }
+            wsum = __fadd_rn(wsum, in ? r.weight : 0.f);
+        }
+        mask[((size_t)f * 2 + 0) * hw + px] = cls;
+        mask[((size_t)f * 2 + 1) * hw + px] = dep;
+        if (weight) weight[(size_t)f * hw + px] = expf(wsum);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -237,6 +414,51 @@ extern "C" int b200_depth_to_xyz(const float* x_norm, const float* ray_angles, f
     dim3 g(cdiv(H * W, 256), B);
     depth_to_xyz_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(x_norm, ray_angles, depth, xyz, H * W, min_depth, max_depth,
                                                             log2f(max_depth + 1.f));
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" int b200_range_project_f64(const double* points, const int* npts, float* out, void* zbuf, int* winner, int F,
+                                      int M, int H, int W, float min_depth, float max_depth, float fov_up_deg,
+                                      float fov_down_deg, void* stream) {
+    B200_CHECK_ARG(points && out && zbuf && winner && F > 0 && M > 0 && H > 0 && W > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double d2r = 3.14159265358979323846 / 180.0;
+    ProjParams64 p{points, npts, out, (unsigned long long*)zbuf, winner, F, M, H, W, (double)min_depth, (double)max_depth,
+                   (double)fov_up_deg * d2r, (double)fov_down_deg * d2r};
+    if (cudaMemsetAsync(zbuf, 0xFF, (size_t)F * H * W * 8, st) != cudaSuccess ||
+        cudaMemsetAsync(winner, 0xFF, (size_t)F * H * W * 4, st) != cudaSuccess) {
+        set_error("range_project_f64: memset failed");
+        return B200_E_CUDA;
+    }
+    dim3 g1(cdiv(M, 256), F);
+    proj64_scatter_kernel<0><<<g1, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    proj64_scatter_kernel<1><<<g1, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    dim3 g2(cdiv(H * W, 256), F);
+    proj64_gather_kernel<<<g2, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
+extern "C" size_t b200_boxes_to_mask_workspace(int F, int N) { return (size_t)F * N * sizeof(BoxRec); }
+
+extern "C" int b200_boxes_to_mask(const void* boxes, int boxes_f64, int F, int N, int H, int W, float fov_up_deg,
+                                  float fov_down_deg, double* boxes_2d, float* mask, float* weight, void* workspace,
+                                  void* stream) {
+    B200_CHECK_ARG(boxes && boxes_2d && mask && workspace && F > 0 && N > 0 && N <= 512 && H > 0 && W > 0 && F <= 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    const double d2r = 3.14159265358979323846 / 180.0;
+    const double h_up = (double)fov_up_deg * d2r, h_down = (double)fov_down_deg * d2r;
+    BoxRec* rec = (BoxRec*)workspace;
+    if (boxes_f64)
+        box_rect_kernel<double><<<F, 128, (size_t)N * 16 * sizeof(double), st>>>((const double*)boxes, N, H, W, h_up, h_down, boxes_2d, rec);
+    else
+        box_rect_kernel<float><<<F, 128, (size_t)N * 16 * sizeof(double), st>>>((const float*)boxes, N, H, W, h_up, h_down, boxes_2d, rec);
+    B200_CHECK_LAUNCH();
+    dim3 g(cdiv(H * W, 256), F);
+    box_raster_kernel<<<g, 256, (size_t)N * sizeof(BoxRec), st>>>(rec, N, H, W, mask, weight);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }

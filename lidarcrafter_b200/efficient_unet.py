@@ -327,6 +327,18 @@ class EfficientUNetPlan:
         G, eps = m.gn_num_groups, m.gn_eps
         H, W = srcs[0].H, srcs[0].W
         has_skip = not isinstance(rb.skip, nn.Identity)
+        cin = sum(a.C for a in srcs)
+        self._n_rb = getattr(self, "_n_rb", 0) + 1
+        self.plan.tag = f"resblock {H}x{W} {cin}->{rb.cout}{' skip' if has_skip else ''} #{self._n_rb}"
+        try:
+            return self._resblock_ops(rb, srcs, has_skip)
+        finally:
+            self.plan.tag = ""
+
+    def _resblock_ops(self, rb: _ResBlockP, srcs: list[Act], has_skip: bool) -> Act:
+        pb, m = self.pb, self.m
+        G, eps = m.gn_num_groups, m.gn_eps
+        H, W = srcs[0].H, srcs[0].W
         # conv1(silu(norm1(x))): GroupNorm-apply + SiLU + operand split run inside the conv launch (b200_conv_gn_tc)
         hmid, st_h = pb.conv_gn(srcs, rb.conv1.weight, rb.conv1.bias, None, 1.0, True, gamma=rb.norm1.weight,
                                 beta=rb.norm1.bias, groups=G, eps=eps, silu=True)

@@ -158,6 +158,8 @@ class Plan:
         self.parts = parts
         self.ops = []                 # list of (callable, args-without-stream)
         self.meta = []                # (kernel name, algorithmic flops, algorithmic bytes) per op
+        self.tags = []                # per op: the block it belongs to (PlanBuilder.tag; "" outside a tagged block)
+        self.tag = ""
         self.bufs = []                # keep-alive
         self.stats_chunks = []
         self.stats_arena = None
@@ -198,6 +200,7 @@ class Plan:
     def add(self, fn, *args, name: str = "", flops: float = 0.0, nbytes: float = 0.0):
         self.ops.append((fn, args))
         self.meta.append((name or getattr(fn, "__name__", "op"), flops, nbytes))
+        self.tags.append(self.tag)
 
     def profile(self, stream: int, reps: int = 3):
         """Per-launch device time (CUDA events on the launching stream), one op at a time.

@@ -1,14 +1,17 @@
 """Box -> range-image conditioning (reference: lidargen/dataset/transforms_3d/common.py:99-216 and the batch
 preprocessors of tools/vis_tools/functions/lidargen_sampler.py:35-125).
 
-Runs once per frame on <= 13 boxes: host-side NumPy / torch, not a per-step kernel.  ``convert_boxes_to_2d`` is
-restated vectorised (the reference loops over boxes in Python); integer pixel rectangles are identical to the
-reference (tests/test_layout_ops.py compares against goldens of the unmodified function)."""
+``convert_boxes_to_2d`` runs on the device (b200_boxes_to_mask: all frames / samples of a batch in one launch pair);
+the <= 13 rows of box scaling / padding around it are host NumPy in the reference's own dtypes.  Pixel rectangles, masks
+and 2-D boxes are bit-identical to the reference (tests/golden/boxes2d.npz, temporal.npz: goldens of the unmodified
+functions for float32 and float64 boxes)."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+from . import _lib
 
 
 def convert_points_to_2d(points: np.ndarray, H: int = 64, W: int = 2048, min_depth: float = 1.45, max_depth: float = 80.0,
@@ -25,41 +28,109 @@ def convert_points_to_2d(points: np.ndarray, H: int = 64, W: int = 2048, min_dep
     return np.concatenate((grid_w, grid_h), axis=1)
 
 
-def convert_boxes_to_2d(boxes_3d: np.ndarray, H: int = 64, W: int = 2048, min_depth: float = 1.45, max_depth: float = 80.0,
+def convert_boxes_to_2d(boxes_3d, H: int = 64, W: int = 2048, min_depth: float = 1.45, max_depth: float = 80.0,
                         fov_up: float = 10.0, fov_down: float = -30.0):
-    """common.py:99-181: boxes [N, >=8] (x,y,z,l,w,h,yaw,class) -> (boxes_2d [N,4], condition_mask [2,H,W],
-    scene_loss_weight_map [H,W])."""
-    n = boxes_3d.shape[0]
-    l, w, h = boxes_3d[:, 3], boxes_3d[:, 4], boxes_3d[:, 5]
-    sx = np.array([1, 1, -1, -1, 1, 1, -1, -1]) * 0.5
-    sy = np.array([1, -1, -1, 1, 1, -1, -1, 1]) * 0.5
-    sz = np.array([1, 1, 1, 1, -1, -1, -1, -1]) * 0.5
-    local = np.stack([l[:, None] * sx, w[:, None] * sy, h[:, None] * sz], axis=1)            # [N,3,8]
-    c, s = np.cos(boxes_3d[:, 6]), np.sin(boxes_3d[:, 6])
-    rot = np.zeros((n, 3, 3)); rot[:, 0, 0] = c; rot[:, 0, 1] = -s; rot[:, 1, 0] = s; rot[:, 1, 1] = c; rot[:, 2, 2] = 1
-    centre = boxes_3d[:, :3][:, :, None]
-    corners = (rot @ local + centre).transpose(0, 2, 1).reshape(-1, 3)
-    c_depth = np.linalg.norm(centre, ord=2, axis=1, keepdims=True) + 1e-6
-    uv = convert_points_to_2d(corners, H, W, min_depth, max_depth, fov_up, fov_down).reshape(n, 8, 2)
-    boxes_2d = np.stack([uv[..., 0].min(1), uv[..., 1].min(1), uv[..., 0].max(1), uv[..., 1].max(1)], axis=1)
-    mask = np.zeros([2, H, W], dtype=np.float32)
-    weight = np.zeros([H, W, n], dtype=np.float32)
-    areas = []
-    for i, (x1, y1, x2, y2) in enumerate(boxes_2d):
-        x1, x2, y1, y2 = int(x1 * W), int(x2 * W), int(y1 * H), int(y2 * H)
-        if (x2 - x1) / W > 0.6:          # box straddles the azimuth seam: fill both ends (common.py:152-163)
-            cols = [slice(0, x1), slice(x2, W)]
-            areas.append((W - x2 + x1) * (y2 - y1))
-        else:
-            cols = [slice(x1, x2)]
-            areas.append((x2 - x1) * (y2 - y1))
-        for cs in cols:
-            mask[0, y1:y2, cs] = boxes_3d[i, 7]
-            mask[1, y1:y2, cs] = c_depth[i, 0, 0]
-            weight[y1:y2, cs, i] = 1.0
-    areas = np.array(areas, dtype=np.float32)
-    weight = weight * (3 - areas / np.max(areas))[None, None, :]
-    return boxes_2d, mask, np.exp(weight.sum(-1))
+    """common.py:99-181: boxes [N, 8] (x,y,z,l,w,h,yaw,class), float32 or float64 -> (boxes_2d [N,4] float64,
+    condition_mask [2,H,W] float32, scene_loss_weight_map [H,W] float32) on the device (b200_boxes_to_mask: corner
+    projection in the reference's dtype flow + one rasteriser pass).  NumPy in -> NumPy out, torch in -> device tensors;
+    batched form [F,N,8] -> ([F,N,4], [F,2,H,W], [F,H,W])."""
+    is_np = isinstance(boxes_3d, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(boxes_3d)) if is_np else boxes_3d
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.double()
+    single = t.dim() == 2
+    t = (t[None] if single else t)[..., :8].to(_lib.compute_device()).contiguous()
+    F_, N = t.shape[:2]
+    lib = _lib.get_lib()
+    dev = t.device
+    b2 = torch.empty(F_, N, 4, dtype=torch.float64, device=dev)
+    mask = torch.empty(F_, 2, H, W, dtype=torch.float32, device=dev)
+    weight = torch.empty(F_, H, W, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(int(lib.boxes_to_mask_workspace(F_, N)), 8), dtype=torch.uint8, device=dev)
+    lib.boxes_to_mask(t.data_ptr(), 1 if t.dtype == torch.float64 else 0, F_, N, H, W, float(fov_up), float(fov_down),
+                      b2.data_ptr(), mask.data_ptr(), weight.data_ptr(), ws.data_ptr(), _lib.current_stream(dev))
+    if single:
+        b2, mask, weight = b2[0], mask[0], weight[0]
+    if is_np:
+        return b2.cpu().numpy(), mask.cpu().numpy(), weight.cpu().numpy()
+    return b2, mask, weight
+
+
+# ---- NuscDataset.pre_process (dataset/nuscenes_dataset.py:145-236,375-421): per-frame box conditioning, <= 13 rows of host
+# float arithmetic in the reference's own NumPy dtypes + the device rasteriser above ----
+CLASS_NAMES = ("car", "truck", "construction_vehicle", "bus", "trailer", "motorcycle", "bicycle", "pedestrian")
+POINTS_RANGE = (-80, -80, -8, 80, 80, 8)
+
+
+def scale_boxes_3d(boxes_3d: np.ndarray, points_range=POINTS_RANGE) -> np.ndarray:
+    """nuscenes_dataset.py:145-158: [N,7+] -> float64 [N,8+]: centre / |range min|, log sizes, (sin, cos) yaw, extra columns"""
+    b = np.array(boxes_3d, copy=True)
+    out = np.zeros([b.shape[0], b.shape[-1] + 1])
+    x_min, y_min, z_min = points_range[:3]
+    b[:, 0] = (b[:, 0] - 0) / (0 - x_min)
+    b[:, 1] = (b[:, 1] - 0) / (0 - y_min)
+    b[:, 2] = (b[:, 2] - 0) / (0 - z_min)
+    b[:, 3:6] = np.log(b[:, 3:6] + 1e-6)
+    out[:, :6] = b[:, :6]
+    out[:, 6] = np.sin(b[:, 6])
+    out[:, 7] = np.cos(b[:, 6])
+    if b.shape[-1] > 7:
+        out[:, 8:] = b[:, 7:]
+    return out
+
+
+def encoding_boxes_3d(box: np.ndarray, unique_mode: bool = True, points_range=POINTS_RANGE) -> np.ndarray:
+    """nuscenes_dataset.py:194-214 (float32 [6] | [8])"""
+    enc = np.zeros((8), dtype=np.float32)
+    x, y, z, w, h, l, yaw = box
+    x_min, y_min, z_min = points_range[:3]
+    enc[0] = np.linalg.norm(np.array([(x - 0) / (0 - x_min), (y - 0) / (0 - y_min)]), ord=2, axis=0, keepdims=True)[0]
+    enc[1] = (z - 0) / (0 - z_min)
+    enc[2:5] = np.log(np.array([w, h, l]) + 1e-6)
+    if unique_mode:
+        enc[5] = yaw - np.arctan2(y, x)
+        return enc[:6]
+    enc[5] = (-np.arctan2(y, x) / np.pi + 1) / 2 % 1
+    enc[6] = np.sin(yaw)
+    enc[7] = np.cos(yaw)
+    return enc
+
+
+def allign_box_num(bbox_3d, bbox_2d, fg_encoding_box, expet_box_num: int = 13):
+    """nuscenes_dataset.py:174-192 (name as in the reference): pad / cut to 13 rows + validity flags"""
+    n = bbox_3d.shape[0]
+    if n > expet_box_num:
+        return (bbox_3d[:expet_box_num], bbox_2d[:expet_box_num], fg_encoding_box[:expet_box_num], np.ones([expet_box_num]))
+    b3, b2, fg = (np.zeros([expet_box_num, a.shape[-1]]) for a in (bbox_3d, bbox_2d, fg_encoding_box))
+    b3[:n], b2[:n], fg[:n] = bbox_3d, bbox_2d, fg_encoding_box
+    valid = np.zeros([expet_box_num])
+    valid[:n] = 1
+    return b3, b2, fg, valid
+
+
+def class_ids(gt_names, class_names=CLASS_NAMES) -> np.ndarray:
+    names = ["ego"] + list(class_names)
+    return np.array([names.index(n) for n in gt_names], dtype=np.int32)
+
+
+def layout_item(gt_boxes: np.ndarray, gt_names, H: int = 32, W: int = 1024, min_depth: float = 1.45, max_depth: float = 80.0,
+                fov_up: float = 10.0, fov_down: float = -30.0, class_names=CLASS_NAMES, host: bool = True) -> dict:
+    """pre_process for the tasks 'layout_cond' / 'autoregressive_generation' (nuscenes_dataset.py:375-421): gt_boxes [N+1,7]
+    with the ego row first + names -> the conditioning entries of one dataset item.  ``host=False`` keeps the rasteriser
+    outputs (gt_boxes_2d, condition_mask, scene_loss_weight_map) on the device as torch tensors."""
+    fg = np.stack([encoding_boxes_3d(b[:7], unique_mode=False) for b in gt_boxes[1:]], axis=0)
+    boxes8 = np.concatenate((gt_boxes, class_ids(gt_names, class_names).reshape(-1, 1).astype(np.float32)), axis=1)
+    if host:
+        b2, mask, weight = convert_boxes_to_2d(boxes8, H, W, min_depth, max_depth, fov_up, fov_down)
+        scaled, b2p, fgp, valid = allign_box_num(scale_boxes_3d(boxes8.copy())[1:], b2[1:], fg)
+    else:
+        b2, mask, weight = convert_boxes_to_2d(torch.from_numpy(boxes8), H, W, min_depth, max_depth, fov_up, fov_down)
+        scaled, _, fgp, valid = allign_box_num(scale_boxes_3d(boxes8.copy())[1:], np.zeros((boxes8.shape[0] - 1, 4)), fg)
+        b2p = torch.zeros(13, 4, dtype=torch.float64, device=b2.device)
+        n = min(13, b2.shape[0] - 1)
+        b2p[:n] = b2[1:1 + n]
+    return dict(gt_boxes=boxes8, scaled_gt_boxes=scaled, fg_encoding_box=fgp, gt_boxes_2d=b2p, is_valid_obj=valid,
+                condition_mask=mask, scene_loss_weight_map=weight)
 
 
 def preprocess_condition_mask(condition_mask: torch.Tensor, lidar_utils, num_classes: int = 9) -> torch.Tensor:

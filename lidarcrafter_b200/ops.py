@@ -21,9 +21,11 @@ def _dev(x, dtype=torch.float32):
 
 def load_points_as_images(point_path: str = None, points=None, scan_unfolding: bool = False, H: int = 64, W: int = 2048,
                           min_depth: float = 1.45, max_depth: float = 80.0, fov_up: float = 10.0,
-                          fov_down: float = -30.0, custom_feat_dim: int = 0, return_grid: bool = False):
+                          fov_down: float = -30.0, custom_feat_dim: int = 0, return_grid: bool = False, npts=None):
     """common.py:26-91 -> float32 [H, W, 6] (x, y, z, intensity, depth, mask); nearest return per pixel.
-    Batched form: points [F, M, 4] -> [F, H, W, 6]."""
+    Batched form: points [F, M, 4] -> [F, H, W, 6]; ``npts`` (int32 device tensor [F]) = valid rows per frame (ragged
+    clouds in a fixed-capacity buffer, no host round trip).  float64 points take the reference's float64 dtype flow
+    (b200_range_project_f64: what the temporal glue feeds the function), float32 / anything else the float32 one."""
     if scan_unfolding:
         raise NotImplementedError("scan_unfolding=True is not used by any nuScenes config (configs/*: False)")
     if custom_feat_dim:
@@ -31,7 +33,8 @@ def load_points_as_images(point_path: str = None, points=None, scan_unfolding: b
     assert point_path is not None or points is not None, "Either point_path or points must be provided."
     if point_path is not None:
         points = np.fromfile(point_path, dtype=np.float32).reshape(-1, 5)[:, :4]
-    pts, is_np = _dev(points)
+    is64 = (points.dtype == np.float64) if isinstance(points, np.ndarray) else (points.dtype == torch.float64)
+    pts, is_np = _dev(points, torch.float64 if is64 else torch.float32)
     single = pts.dim() == 2
     if single:
         pts = pts[None]
@@ -40,9 +43,17 @@ def load_points_as_images(point_path: str = None, points=None, scan_unfolding: b
     out = torch.empty(F, H, W, 6, device=pts.device)
     zbuf = torch.empty(F, H, W, dtype=torch.int64, device=pts.device)
     grid = torch.empty(F, M, 2, dtype=torch.int32, device=pts.device) if return_grid else None
-    _lib.get_lib().range_project(pts.data_ptr(), 0, out.data_ptr(), 0 if grid is None else grid.data_ptr(),
-                                 zbuf.data_ptr(), F, M, H, W, float(min_depth), float(max_depth), float(fov_up),
-                                 float(fov_down), _stream())
+    n_ptr = 0 if npts is None else npts.to(device=pts.device, dtype=torch.int32).contiguous().data_ptr()
+    if is64:
+        if return_grid:
+            raise NotImplementedError("return_grid with float64 points")
+        win = torch.empty(F, H, W, dtype=torch.int32, device=pts.device)
+        _lib.get_lib().range_project_f64(pts.data_ptr(), n_ptr, out.data_ptr(), zbuf.data_ptr(), win.data_ptr(), F, M, H, W,
+                                         float(min_depth), float(max_depth), float(fov_up), float(fov_down), _stream())
+    else:
+        _lib.get_lib().range_project(pts.data_ptr(), n_ptr, out.data_ptr(), 0 if grid is None else grid.data_ptr(),
+                                     zbuf.data_ptr(), F, M, H, W, float(min_depth), float(max_depth), float(fov_up),
+                                     float(fov_down), _stream())
     if single:
         out = out[0]
         grid = None if grid is None else grid[0]

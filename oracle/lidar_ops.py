@@ -36,6 +36,29 @@ def range_project(points, H=32, W=1024, min_depth=1.45, max_depth=80.0, fov_up=1
     return out, grid, win
 
 
+def range_project_f64(points, H=32, W=1024, min_depth=1.45, max_depth=80.0, fov_up=10.0, fov_down=-30.0):
+    """points float64 [M,4] -> (image float32 [H,W,6], winner int32 [H,W]); common.py:26-91 on a float64 array"""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.zeros((H, W, 6), np.float32)
+    win = np.zeros((H, W), np.int32)
+    lib().oracle_range_project_f64(_p(pts), pts.shape[0], H, W, C.c_double(min_depth), C.c_double(max_depth),
+                                   C.c_double(fov_up), C.c_double(fov_down), _p(out), _p(win))
+    return out, win
+
+
+def boxes_to_mask(boxes, H=32, W=1024, fov_up=10.0, fov_down=-30.0):
+    """convert_boxes_to_2d (common.py:99-181): boxes [N,8] float32 | float64 -> (boxes_2d f64 [N,4], mask f32 [2,H,W], weight f32 [H,W])"""
+    assert boxes.dtype in (np.float32, np.float64) and boxes.shape[1] == 8
+    bx = np.ascontiguousarray(boxes)
+    N = bx.shape[0]
+    b2 = np.zeros((N, 4), np.float64)
+    mask = np.zeros((2, H, W), np.float32)
+    w = np.zeros((H, W), np.float32)
+    lib().oracle_boxes_to_mask(_p(bx), int(bx.dtype == np.float64), N, H, W, C.c_double(fov_up), C.c_double(fov_down), _p(b2),
+                               _p(mask), _p(w))
+    return b2, mask, w
+
+
 def points_in_boxes(points, boxes):
     pts = np.ascontiguousarray(points, dtype=np.float32)
     bx = np.ascontiguousarray(boxes, dtype=np.float32)

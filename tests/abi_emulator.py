@@ -463,13 +463,37 @@ def _install_pointcloud_entries():
 
     def range_project(self, points, npts, out, grid, zbuf, F, M, H, W, min_d, max_d, fov_up, fov_down, stream):
         self._rec("range_project")
-        pts, o = f32(points, F, M, 4), f32(out, F, H, W, 6)
+        pts, o, n = f32(points, F, M, 4), f32(out, F, H, W, 6), i32(npts, F)
         g = i32(grid, F, M, 2)
         for f in range(F):
-            img, gr, _ = LO.range_project(pts[f].numpy(), H, W, min_d, max_d, fov_up, fov_down)
+            cnt = M if n is None else int(n[f])
+            img, gr, _ = LO.range_project(pts[f, :cnt].numpy(), H, W, min_d, max_d, fov_up, fov_down)
             o[f] = torch.from_numpy(img)
             if g is not None:
-                g[f] = torch.from_numpy(gr)
+                g[f, :cnt] = torch.from_numpy(gr)
+        return 0
+
+    def range_project_f64(self, points, npts, out, zbuf, winner, F, M, H, W, min_d, max_d, fov_up, fov_down, stream):
+        self._rec("range_project_f64")
+        pts, o, n = f64(points, F, M, 4), f32(out, F, H, W, 6), i32(npts, F)
+        for f in range(F):
+            cnt = M if n is None else int(n[f])
+            img, _ = LO.range_project_f64(pts[f, :cnt].numpy(), H, W, min_d, max_d, fov_up, fov_down)
+            o[f] = torch.from_numpy(img)
+        return 0
+
+    def boxes_to_mask_workspace(self, F, N):
+        return 32 * F * N
+
+    def boxes_to_mask(self, boxes, is64, F, N, H, W, fov_up, fov_down, boxes_2d, mask, weight, ws, stream):
+        self._rec("boxes_to_mask")
+        bx = (f64 if is64 else f32)(boxes, F, N, 8)
+        b2, m, w = f64(boxes_2d, F, N, 4), f32(mask, F, 2, H, W), f32(weight, F, H, W)
+        for f in range(F):
+            r2, rm, rw = LO.boxes_to_mask(bx[f].numpy(), H, W, fov_up, fov_down)
+            b2[f], m[f] = torch.from_numpy(r2), torch.from_numpy(rm)
+            if w is not None:
+                w[f] = torch.from_numpy(rw)
         return 0
 
     def points_in_boxes(self, pts, boxes, out, N, M, stream):
@@ -571,7 +595,7 @@ def _install_pointcloud_entries():
         f32(vol, *dims).copy_(torch.from_numpy(out))
         return 0
 
-    for fn in (range_project, points_in_boxes, points_in_boxes_first, voxel_index, pcd2range, range2xyz, quantize_coords,
+    for fn in (range_project, range_project_f64, boxes_to_mask_workspace, boxes_to_mask, points_in_boxes, points_in_boxes_first, voxel_index, pcd2range, range2xyz, quantize_coords,
                sparse_quantize_workspace, ravel_hash, sparse_quantize, bev_occupancy_sum, voxel_occupancy):
         setattr(EmulatedLib, fn.__name__, fn)
 

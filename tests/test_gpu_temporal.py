@@ -1,0 +1,96 @@
+"""Temporal (autoregressive 4D) glue and the composed clip generation on the GPU: the device kernels
+(b200_boxes_to_mask, b200_range_project_f64, points-in-boxes, projection) against goldens of the reference's OWN functions
+(tests/golden/make_golden_temporal.py), and TemporalSampler.generate end to end (sample_and_save_temporal.py:203-333)."""
+import numpy as np
+import pytest
+import torch
+
+import temporal_checks as TC
+
+pytestmark = pytest.mark.gpu
+
+
+def test_layout_item_matches_reference_dataset_item():
+    TC.check_layout_item()
+
+
+def test_clip_glue_matches_reference():
+    TC.check_clip_glue("cuda")
+
+
+def test_boxes_to_mask_device_vs_reference_goldens_and_oracle():
+    """both dtype flows of convert_boxes_to_2d, batched; + 64 random box sets against the C oracle (bit-exact rectangles)"""
+    import os
+    from lidarcrafter_b200 import layout_ops as LO
+    from oracle import lidar_ops as ORA
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "boxes2d.npz"))
+    for dt, cases in ((np.float64, (0, 1, 2)), (np.float32, (3, 4, 5))):
+        stack = torch.from_numpy(np.stack([G[f"boxes_{c}"] for c in cases]).astype(dt))
+        b2, mask, w = LO.convert_boxes_to_2d(stack, H=32, W=1024, fov_up=10.0, fov_down=-30.0)
+        assert b2.is_cuda and mask.is_cuda
+        for i, c in enumerate(cases):
+            assert np.array_equal(b2[i].cpu().numpy(), G[f"b2_{c}"]) and np.array_equal(mask[i].cpu().numpy(), G[f"mask_{c}"])
+            assert np.allclose(w[i].cpu().numpy(), G[f"w_{c}"], rtol=1e-6)
+    rs = np.random.RandomState(5)
+    for dt in (np.float32, np.float64):
+        boxes = np.zeros((64, 13, 8), dt)
+        boxes[..., :2] = rs.uniform(-50, 50, (64, 13, 2)); boxes[..., 2] = rs.uniform(-3, 1, (64, 13))
+        boxes[..., 3:6] = rs.uniform(0.4, 12, (64, 13, 3)); boxes[..., 6] = rs.uniform(-np.pi, np.pi, (64, 13))
+        boxes[..., 7] = rs.randint(0, 9, (64, 13))
+        boxes[:, 0] = 0
+        for HW in ((32, 1024), (64, 2048)):
+            b2, mask, w = LO.convert_boxes_to_2d(torch.from_numpy(boxes), H=HW[0], W=HW[1], fov_up=10.0, fov_down=-30.0)
+            bad = 0
+            for f in range(64):
+                r2, rm, rw = ORA.boxes_to_mask(boxes[f], HW[0], HW[1], 10.0, -30.0)
+                bad += int(not (np.array_equal(b2[f].cpu().numpy(), r2) and np.array_equal(mask[f].cpu().numpy(), rm)))
+                assert np.allclose(w[f].cpu().numpy(), rw, rtol=1e-6)
+            assert bad == 0, (dt, HW, bad)
+
+
+def test_range_project_f64_vs_oracle():
+    """float64 dtype flow of load_points_as_images (the re-projection of the warped background): pixels, winners, values"""
+    from lidarcrafter_b200 import ops
+    from oracle import lidar_ops as ORA
+    rs = np.random.RandomState(3)
+    for M in (1, 777, 40000):
+        d = rs.uniform(0.5, 90, M)
+        az, el = rs.uniform(-np.pi, np.pi, M), np.deg2rad(rs.uniform(-32, 12, M))
+        pts = np.stack([d * np.cos(el) * np.cos(az), d * np.cos(el) * np.sin(az), d * np.sin(el), rs.uniform(0, 255, M)], 1)
+        pts[: M // 10] = pts[M // 2: M // 2 + M // 10]                     # exact duplicates: ties -> highest index
+        img = ops.load_points_as_images(points=torch.from_numpy(pts).cuda(), H=32, W=1024, fov_up=10.0, fov_down=-30.0)
+        ref, _ = ORA.range_project_f64(pts)
+        assert np.array_equal(img.cpu().numpy(), ref)
+    # ragged batch through the device-side counts
+    pts = np.stack([pts[:3000], pts[3000:6000]])
+    img = ops.load_points_as_images(points=torch.from_numpy(pts).cuda(), H=32, W=1024, fov_up=10.0, fov_down=-30.0,
+                                    npts=torch.tensor([3000, 1234], dtype=torch.int32, device="cuda"))
+    assert np.array_equal(img[1].cpu().numpy(), ORA.range_project_f64(pts[1, :1234])[0])
+    assert np.array_equal(img[0].cpu().numpy(), ORA.range_project_f64(pts[0])[0])
+
+
+def _sampler(precision=None):
+    import bench
+    ts, models = bench.build_temporal(torch.device("cuda"), precision or bench.DEFAULT_PRECISION)
+    return ts, models, bench.synth_scenes
+
+
+def test_generate_clip_end_to_end():
+    """3-frame clip, 2 steps per frame, batch 2: frame 0 is the box-layout sampler's output, later frames come from the
+    autoregressive model fed with the glue's conditioning; the same seeds give the same clip, another layout another clip"""
+    ts, (ddpm, auto), synth = _sampler()
+    scenes = synth(2, 3)
+    gens = lambda: [torch.Generator(device="cuda").manual_seed(7 + i) for i in range(2)]
+    clip = ts.generate(scenes, num_frames=3, num_steps=2, mode="ddim", temporal_mode="ddim", rng=gens())
+    assert clip.shape == (2, 3, 5, 32, 1024) and bool(torch.isfinite(clip).all())
+    # frame 0 = ddpm.sample on the same conditioning + postprocess
+    batch = ts.prepare_batch(ts.box_batch([s["gt_boxes"] for s in scenes], [s["gt_names"] for s in scenes]))
+    x = ddpm.sample(batch_dict=batch, batch_size=2, num_steps=2, mode="ddim", progress=False, rng=gens()).clamp(-1, 1)
+    assert torch.equal(ts.postprocess(x), clip[:, 0])
+    assert torch.equal(clip, ts.generate(scenes, num_frames=3, num_steps=2, mode="ddim", temporal_mode="ddim", rng=gens()))
+    other = ts.generate(synth(2, 3, seed=9), num_frames=3, num_steps=2, mode="ddim", temporal_mode="ddim", rng=gens())
+    assert not torch.equal(other[:, 1], clip[:, 1])
+    # depth channel is metric and masked to [min_depth, max_depth]; xyz consistent with depth
+    d, xyz = clip[:, :, 0], clip[:, :, 1:4]
+    assert float(d.max()) <= 80.0 and bool(((d == 0) | (d > 1.45)).all())
+    assert torch.allclose(xyz.norm(dim=2), d, atol=1e-3)
