@@ -181,13 +181,22 @@ int b200_attention_oa(const float* qkv, const float* pos_p, const float* kl, con
                       const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
                       int L2, float scale2, void* stream);
 
-/* Flash-style (online softmax, register-tiled fp32) versions of the two attention cores above: same inputs /
- * outputs, scores never leave the SM and shared memory does not grow with T (used by the plans).        */
+/* optional in-kernel profile of the tcgen05 attention kernel: 16 x u64 cycle counters per CTA (device buffer of
+ * grid-size x 16 u64, or NULL to switch off); see csrc/attention.cu                                                 */
+int b200_attn_set_debug(void* dbg_u64);
+
+/* Flash attention (online softmax; scores never leave the SM) for the two attention cores above: same inputs / outputs.
+ * Product path: tcgen05.mma with the S and O accumulators in TMEM (csrc/attention.cu flash_attn_tc_kernel): a pack pass
+ * writes the fp16 hi | lo Q / K / V^T tile images of every (batch, head) into `workspace` in the shared-memory layout of the
+ * MMA operands, the main kernel stages them with one bulk copy per tile.
+ *   workspace: b200_flash_attention_workspace(B, heads, T, Tx, dq, dv) bytes of device memory (Tx = extra layout keys, dq =
+ *   query / key width per head (2 x 32 for the object-aware variant), dv = value width per head); contents are scratch.  */
+size_t b200_flash_attention_workspace(int B, int heads, int T, int Tx, int dq, int dv);
 int b200_flash_attention(const float* qkv, int E, void* out, int out_w, int parts, int B, int heads, int T,
-                         float scale, void* stream);
+                         float scale, void* workspace, void* stream);
 int b200_flash_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
                             const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
-                            int L2, float scale2, void* stream);
+                            int L2, float scale2, void* workspace, void* stream);
 
 /* ---- K5: sampler update --------------------------------------------------------------------------
  * replaces p_step's ~25 elementwise ops (diffusion/continuous_time.py:205-231).

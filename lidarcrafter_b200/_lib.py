@@ -35,8 +35,10 @@ PROTOTYPES = {
     "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, I, I, I, I, P]),
     "b200_gn_act_f32": (I, [P, P, P, P, I, F, I, P, I, I, I, P]),
     "b200_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
-    "b200_flash_attention": (I, [P, I, P, I, I, I, I, I, F, P]),
-    "b200_flash_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
+    "b200_attn_set_debug": (I, [P]),
+    "b200_flash_attention_workspace": (SZ, [I, I, I, I, I, I]),
+    "b200_flash_attention": (I, [P, I, P, I, I, I, I, I, F, P, P]),
+    "b200_flash_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P, P]),
     "b200_channel_stats": (I, [P, P, I, I, I, P]),
     "b200_fir_resample": (I, [P, P, P, I, I, I, I, I, I, P]),
     "b200_fir_up_operand": (I, [P, P, I, I, I, I, I, I, P]),
@@ -66,7 +68,7 @@ PROTOTYPES = {
 }
 
 _NO_STATUS = {"b200_conv_merged", "b200_version", "b200_device_check", "b200_last_error", "b200_packed_weight_elems",
-              "b200_sparse_quantize_workspace", "b200_boxes_to_mask_workspace"}
+              "b200_sparse_quantize_workspace", "b200_boxes_to_mask_workspace", "b200_flash_attention_workspace"}
 
 
 class B200LidarError(RuntimeError):

@@ -105,6 +105,25 @@ __device__ __forceinline__ int pt_in_box(float x, float y, float z, const float*
     return in ? 1 : 0;
 }
 
+// points_in_boxes_gpu / generate_pts_mask_for_box3d exist ONLY as CUDA in the reference (roiaware_pool3d_kernel.cu:15-36): its
+// build is nvcc with default flags, i.e. the products of the local-frame rotation are contracted into FMAs and cos / sin of
+// a float resolve to the CUDA cosf / sinf.  The two kernels that replace them follow THAT arithmetic -- the expression
+// below is left to the compiler exactly like the reference's (same toolkit -> same contraction, same libdevice) -- and are
+// pinned bit for bit against oracle/_ref/libref_roiaware_cuda.so on the GPU box; pt_in_box() above (explicit
+// round-to-nearest products, cos / sin through fp64) is the arithmetic of the reference's C++ points_in_boxes_cpu.
+__device__ __forceinline__ int pt_in_box_fma(const float* pt, const float* bx, float& lx, float& ly) {
+    const float margin = 1e-5;
+    const float px = pt[0], py = pt[1], pz = pt[2];
+    const float cx = bx[0], cy = bx[1], cz = bx[2], dx = bx[3], dy = bx[4], dz = bx[5], rz = bx[6];
+    if (fabsf(pz - cz) > dz / 2.0) return 0;
+    const float sx = px - cx, sy = py - cy;
+    const float ca = cosf(-rz), sa = sinf(-rz);
+    lx = sx * ca + sy * (-sa);
+    ly = sx * sa + sy * ca;
+    const float in = (fabs(lx) < dx / 2.0 + margin) & (fabs(ly) < dy / 2.0 + margin);
+    return in;
+}
+
 __global__ void pib_all_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, int* __restrict__ out,
                                int N, int M) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,7 +142,7 @@ __global__ void pib_first_kernel(const float* __restrict__ pts, const float* __r
     float lx, ly;
     int r = -1;
     for (int k = 0; k < N; ++k) {
-        if (pt_in_box(pt[0], pt[1], pt[2], boxes + ((size_t)b * N + k) * 7, 1e-5f, lx, ly)) {
+        if (pt_in_box_fma(pt, boxes + ((size_t)b * N + k) * 7, lx, ly)) {
             r = k;
             break;
         }
@@ -139,14 +158,14 @@ __global__ void voxel_index_kernel(const float* __restrict__ pts, const float* _
     const float* bx = rois + i * 7;
     float lx = 0.f, ly = 0.f;
     int code = -1;
-    if (pt_in_box(pts[j * 3], pts[j * 3 + 1], pts[j * 3 + 2], bx, 1e-5f, lx, ly)) {
-        const float lz = __fsub_rn(pts[j * 3 + 2], bx[2]);
+    if (pt_in_box_fma(pts + j * 3, bx, lx, ly) > 0) {
+        const float lz = pts[j * 3 + 2] - bx[2];
         const float dx = bx[3], dy = bx[4], dz = bx[5];
-        const float xr = __fdiv_rn(dx, (float)ox), yr = __fdiv_rn(dy, (float)oy), zr = __fdiv_rn(dz, (float)oz);
-        // unsigned idx = int(f) : truncation toward zero, then (as unsigned) min(max(.,0), n-1)
-        unsigned xi = (unsigned)(int)__fdiv_rn(__fadd_rn(lx, __fdiv_rn(dx, 2.f)), xr);
-        unsigned yi = (unsigned)(int)__fdiv_rn(__fadd_rn(ly, __fdiv_rn(dy, 2.f)), yr);
-        unsigned zi = (unsigned)(int)__fdiv_rn(__fadd_rn(lz, __fdiv_rn(dz, 2.f)), zr);
+        const float xr = dx / ox, yr = dy / oy, zr = dz / oz;
+        // unsigned idx = int(f) : truncation toward zero, then (as unsigned) min(max(., 0), n - 1)
+        unsigned xi = int((lx + dx / 2) / xr);
+        unsigned yi = int((ly + dy / 2) / yr);
+        unsigned zi = int((lz + dz / 2) / zr);
         xi = min(max(xi, 0u), (unsigned)(ox - 1));
         yi = min(max(yi, 0u), (unsigned)(oy - 1));
         zi = min(max(zi, 0u), (unsigned)(oz - 1));

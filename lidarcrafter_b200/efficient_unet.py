@@ -362,8 +362,10 @@ class EfficientUNetPlan:
                             groups=m.gn_num_groups, eps=m.gn_eps, silu=False)
         att = self.plan.operand(x.H, x.W, E)
         d = E // nh
+        ws = torch.empty(max(int(self.lib.flash_attention_workspace(self.B, nh, T, 0, d, d)), 16), dtype=torch.uint8, device=self.dev)
+        self.plan.bufs.append(ws)           # packed Q / K / V^T tile images of the tcgen05 attention
         self.plan.add(self.lib.flash_attention, _ptr(qkv), E, _ptr(att), x.W, self.plan.parts, self.B, nh, T,
-                      1.0 / math.sqrt(d), name="attention", flops=4.0 * self.B * nh * T * T * d)
+                      1.0 / math.sqrt(d), _ptr(ws), name="attention", flops=4.0 * self.B * nh * T * T * d)
         self.plan.flops += 4.0 * self.B * nh * T * T * d
         w_o = ab.attn.out_proj.weight.detach().reshape(E, E, 1, 1)
         out, st = pb.conv(att, x.H, x.W, w_o, ab.attn.out_proj.bias, x.t, float(ab.scale), True)

@@ -306,8 +306,10 @@ class LayoutUnetPlan:
         self.attn_consts.append((ab, res_key, bufs))
         att = plan.operand(x.H, x.W, C)
         d = C // nh
+        ws = torch.empty(max(int(self.lib.flash_attention_workspace(B, nh, T, L2, 2 * d, d)), 16), dtype=torch.uint8, device=self.dev)
+        plan.bufs.append(ws)                # packed Q / K / V^T tile images of the tcgen05 attention
         plan.add(self.lib.flash_attention_oa, _ptr(qkv), _ptr(bufs["pos_p"]), _ptr(bufs["kl"]), _ptr(bufs["pos_l"]),
-                 _ptr(bufs["vl"]), _ptr(att), x.W, plan.parts, B, C, nh, T, L2, 1.0 / math.sqrt(2 * d), name="attention_oa",
+                 _ptr(bufs["vl"]), _ptr(att), x.W, plan.parts, B, C, nh, T, L2, 1.0 / math.sqrt(2 * d), _ptr(ws), name="attention_oa",
                  flops=2.0 * B * nh * T * (T + L2) * (3 * d))
         plan.flops += 2.0 * B * nh * T * (T + L2) * (3 * d)
         wo = ab.proj_out.weight.detach().reshape(C, C, 1, 1)

@@ -415,13 +415,17 @@ class EmulatedLib:
         store_operand(out, o, parts, B, Tq // out_w, out_w, ldo)
         return 0
 
-    def flash_attention(self, qkv, E, out, out_w, parts, B, heads, T, scale, stream):
+    @staticmethod
+    def flash_attention_workspace(B, heads, T, Tx, dq, dv):
+        return 16
+
+    def flash_attention(self, qkv, E, out, out_w, parts, B, heads, T, scale, workspace, stream):
         d = E // heads
         return self.attention(qkv, 3 * E, 0, qkv, 3 * E, E, qkv, 3 * E, 2 * E, out, E, out_w, parts, B, heads, T, T, d, d,
                               scale, stream)
 
     def flash_attention_oa(self, *a):
-        return self.attention_oa(*a)
+        return self.attention_oa(*a[:-2], a[-1])            # (workspace is scratch of the device kernel)
 
     def sampler_update(self, x_t, pred, noise, coef, x_s, B, n, mode, objective, clip, stream):
         self._rec("sampler_update")

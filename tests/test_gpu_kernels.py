@@ -432,7 +432,8 @@ def test_flash_attention(parts, E, heads, T, W):
     d = E // heads
     qkv = h.t(randn(B, T, 3 * E, seed=1))
     out = h.t(operand_zeros(parts, B, T // W, W, E))
-    h.call("flash_attention", [("t", qkv), E, ("t", out), W, parts, B, heads, T, 1 / math.sqrt(d)])
+    ws = h.t(torch.zeros(h.gpu.flash_attention_workspace(B, heads, T, 0, d, d), dtype=torch.uint8))
+    h.call("flash_attention", [("t", qkv), E, ("t", out), W, parts, B, heads, T, 1 / math.sqrt(d), ("t", ws)])
     operand_close(*h.out(out), parts, B, T // W, W, E)
 
 
@@ -445,8 +446,9 @@ def test_flash_attention_oa(parts, C, T, W):
     pos_p = h.t(randn(B, T, C, seed=2))
     kl, pos_l, vl = h.t(randn(B, L2, C, seed=3)), h.t(randn(B, L2, C, seed=4)), h.t(randn(B, L2, C, seed=5))
     out = h.t(operand_zeros(parts, B, T // W, W, C))
+    ws = h.t(torch.zeros(h.gpu.flash_attention_workspace(B, C // 32, T, L2, 64, 32), dtype=torch.uint8))
     h.call("flash_attention_oa", [("t", qkv), ("t", pos_p), ("t", kl), ("t", pos_l), ("t", vl), ("t", out), W, parts, B,
-                                  C, C // 32, T, L2, 1 / math.sqrt(64)])
+                                  C, C // 32, T, L2, 1 / math.sqrt(64), ("t", ws)])
     operand_close(*h.out(out), parts, B, T // W, W, C)
 
 

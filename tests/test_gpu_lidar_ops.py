@@ -60,10 +60,13 @@ def test_points_in_boxes_and_voxel_index_bit_exact():
     big = boxes.copy(); big[:, 3:6] += np.float32(0.2)
     assert np.array_equal(got, LO.points_in_boxes(pts, big))
     assert got.sum() > 100
+    # points_in_boxes_gpu / voxel index follow the arithmetic of the reference's CUDA build (FMA contraction, cosf / sinf:
+    # pinned bit for bit below against oracle/_ref); the C oracle (non-contracted) may disagree on a point that lies within
+    # an fp32 ulp of a face or of a voxel boundary
     first = ops.points_in_boxes_gpu(torch.from_numpy(pts[None]), torch.from_numpy(boxes[None])).cpu().numpy()
-    assert np.array_equal(first, LO.points_in_boxes_first(pts[None], boxes[None]))
+    assert (first != LO.points_in_boxes_first(pts[None], boxes[None])).mean() < 1e-3
     code = ops.voxel_index(pts, boxes, (14, 14, 14))
-    assert np.array_equal(code, LO.voxel_index(pts, boxes, (14, 14, 14)))
+    assert (code != LO.voxel_index(pts, boxes, (14, 14, 14))).mean() < 1e-3
     assert (code >= 0).sum() > 100
 
 
@@ -82,37 +85,30 @@ def test_depth_to_xyz_vs_numpy():
 
 
 def test_rollout_glue_on_device():
-    """delete_fg_points / extract_object_points / get_next_frame_points (pipe_related.py:54-68,243-288) against a
-    NumPy restatement built on the C oracle."""
+    """delete_fg_points / extract_object_points / compact (pipe_related.py:54-68,282-288) against a NumPy restatement built
+    on the C oracle (the full glue is pinned to the reference's own functions in test_gpu_temporal.py)."""
     from lidarcrafter_b200 import rollout
     rs = np.random.RandomState(1)
     boxes = _boxes(rs, 6)
     pts = synth_sweep(4)
     pts[:3000, :3] = (boxes[rs.randint(0, 6, 3000), :3] + rs.normal(0, 1.0, (3000, 3))).astype(np.float32)
-    tp, tb = torch.from_numpy(pts).cuda(), torch.from_numpy(boxes).cuda()
+    tp = torch.from_numpy(pts).cuda()
     big = boxes.copy(); big[:, 3:6] += np.float32(0.2)
     m = LO.points_in_boxes(pts[:, :3], big)
-    bg = rollout.delete_fg_points(tp, tb).cpu().numpy()
+    allp = rollout.PointSet(tp, torch.tensor([pts.shape[0]], dtype=torch.int32, device="cuda"))
+    bg = rollout.delete_fg_points(allp, boxes).numpy()
     assert np.array_equal(bg, pts[m.sum(0) == 0])
-    objs, inten = rollout.extract_object_points(tp, tb)
+    canon, inten, box = rollout.extract_object_points(tp, torch.ones(pts.shape[0], dtype=torch.bool, device="cuda"), boxes)
+    canon, inten, box = canon.cpu().numpy(), inten.cpu().numpy(), box.cpu().numpy()
     for k in range(6):
         sel = pts[m[k] > 0]
-        assert objs[k].shape[0] == sel.shape[0] and np.array_equal(inten[k].cpu().numpy(), sel[:, 3])
-        c, s = np.cos(-boxes[k, 6]), np.sin(-boxes[k, 6])
-        ref = (sel[:, :3] - boxes[k, :3]) @ np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]], np.float32)
-        assert np.allclose(objs[k].cpu().numpy(), ref, atol=1e-4)
-    T = rollout.compute_inter_frame_transforms(np.array([[0.02, 0.5]]))[0]
-    nxt = rollout.get_next_frame_points(torch.from_numpy(bg).cuda(), objs, inten, tb, T).cpu().numpy()
-    # oracle: warp in fp64, project with the C oracle, drop masked / empty pixels, paste the objects
-    h = np.concatenate([bg[:, :3].astype(np.float64), np.ones((len(bg), 1))], 1)
-    w = (T @ h.T).T
-    w[:, 3] = bg[:, 3]
-    img, _, _ = LO.range_project(w.astype(np.float32))
-    img = img * img[..., 5:6]
-    p = img[..., :4].reshape(-1, 4)
-    p = p[np.linalg.norm(p[:, :3], axis=1) > 1e-2]
-    assert nxt.shape[0] == p.shape[0] + sum(o.shape[0] for o in objs)
-    assert np.array_equal(nxt[:p.shape[0]], p)
+        assert (box == k).sum() == sel.shape[0] and np.array_equal(inten[box == k], sel[:, 3])
+        c, s_ = np.cos(-boxes[k, 6]), np.sin(-boxes[k, 6])
+        ref = (sel[:, :3] - boxes[k, :3]) @ np.array([[c, s_, 0], [-s_, c, 0], [0, 0, 1]], np.float32)
+        assert np.allclose(canon[box == k], ref, atol=1e-4)
+    # a partially filled buffer: rows behind the count are ignored
+    part = rollout.PointSet(tp, torch.tensor([5000], dtype=torch.int32, device="cuda"))
+    assert np.array_equal(rollout.delete_fg_points(part, boxes).numpy(), pts[:5000][m[:, :5000].sum(0) == 0])
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -144,8 +140,9 @@ def _local_fp64(pts, bx):
 @pytest.mark.skipif(not LO.ref_cuda_available(), reason="oracle/_ref CUDA build not shipped")
 def test_first_box_and_voxel_index_vs_reference_cuda_kernels():
     """Our points_in_boxes_gpu / voxel-index kernels against the reference's own CUDA kernels (roiaware_pool3d_kernel.cu
-    compiled unmodified for sm_100a, nvcc default flags = FMA contraction + CUDA cosf/sinf).  The two may only differ
-    where fp32 rounding decides: within 1e-4 m of a box face or 1e-3 of a voxel boundary; everywhere else bit-exact."""
+    compiled unmodified for sm_100a, nvcc default flags = FMA contraction + CUDA cosf/sinf): BIT-EXACT, with a third of the
+    points within ~1 fp32 ulp of a box face (these two functions exist only as CUDA in the reference, so its CUDA build is the
+    authority and the kernels follow its arithmetic)."""
     import ctypes as C
     from lidarcrafter_b200 import ops
     ref = LO.ref_cuda_lib()
@@ -173,16 +170,12 @@ def test_first_box_and_voxel_index_vs_reference_cuda_kernels():
         near |= close
         q = (loc + half[None]) / (boxes[i, 3:6].astype(np.float64) / 14)[None]
         frac_near[i] = close | np.any(np.abs(q - np.round(q)) < 1e-3, 1)
-    assert (ours >= 0).sum() > 10000
-    assert np.array_equal(ours[~near], theirs[~near])
-    print("first-box mismatches vs reference CUDA (all within 1e-4 m of a face):", int((ours != theirs).sum()), "of", M)
-    assert (ours != theirs).mean() < 1e-2      # a third of the points sit ~1 fp32 ulp from a face
+    assert (ours >= 0).sum() > 10000 and near.sum() > 1000
+    assert np.array_equal(ours, theirs), int((ours != theirs).sum())
     # ---- voxel index (generate_pts_mask_for_box3d, kernel.cu:39-75)
     code = ops.voxel_index(tp, tb, (14, 14, 14)).cpu().numpy()
     mask = torch.empty(N, M, dtype=torch.int32, device="cuda")
     assert ref.ref_voxel_index(N, M, 14, 14, 14, vp(tb), vp(tp), vp(mask)) == 0
     mask = mask.cpu().numpy()
-    assert (code >= 0).sum() > 10000
-    assert np.array_equal(code[~frac_near], mask[~frac_near])
-    print("voxel-code mismatches vs reference CUDA (all at fp32 ties):", int((code != mask).sum()), "of", code.size)
-    assert (code != mask).mean() < 1e-2
+    assert (code >= 0).sum() > 10000 and frac_near.sum() > 1000
+    assert np.array_equal(code, mask), int((code != mask).sum())
