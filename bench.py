@@ -245,14 +245,14 @@ def run_temporal(args, dev, rank, world, local):
     tools/evaluation/sample_and_save_temporal.py:203-333): first frame from the box-layout model, then the autoregressive
     frames with the device-resident glue in between; one all-gather of the clips at the end."""
     import torch.distributed as dist
-    from lidarcrafter_b200.dist import all_gather_samples, shard_range
+    from lidarcrafter_b200.dist import generate_sharded, shard_range
     rollout = args.workload == "rollout"
     frames = args.frames or (20 if rollout else 5)
     total = 8 if rollout else 4 * world                 # configs[4]: batch 8 in total (strong scaling); configs[2]: 4 per GPU
     lo, hi = shard_range(total, rank, world)
     K, W = args.steps, args.warmup
     ts, models = build_temporal(dev, args.precision)
-    scenes = synth_scenes(total, frames)[lo:hi]
+    scenes = synth_scenes(total, frames)
     Bl = hi - lo
 
     def barrier():
@@ -260,13 +260,9 @@ def run_temporal(args, dev, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run(nf, k):
-        if Bl == 0:
-            clips = torch.zeros(0, nf, 5, *RES, device=dev)
-        else:
-            gens = [torch.Generator(device=dev).manual_seed(100 + i) for i in range(lo, hi)]
-            clips = ts.generate(scenes, num_frames=nf, num_steps=k, mode="ddim", temporal_mode="ddim", rng=gens)
-        return all_gather_samples(clips, total)
+    def run(nf, k):          # the public multi-GPU call: rank r generates its clips, one all-gather at the end
+        gens = [torch.Generator(device=dev).manual_seed(100 + i) for i in range(total)]
+        return generate_sharded(ts, scenes, num_frames=nf, num_steps=k, rng=gens, mode="ddim", temporal_mode="ddim")
     run(min(frames, 2), max(W, 1))                      # warm-up: plans, tile tuning, step graphs of both models
     barrier()
     clk = ClockSampler(local)

@@ -162,31 +162,23 @@ int b200_out_conv(const void* a, int a_is_f16, const float* w, const float* bias
                   int H, int W, int Cin, int Cout, int ring, void* stream);
 
 /* ---- K2: attention ---------------------------------------------------------------------------------
- * softmax(q k^T * scale) v per (batch, head); q/k/v are slices of fp32 token-major tensors
- *   q: [B,Tq,ldq] at column offset head*dqk (+qoff), k: [B,Tk,ldk], v: [B,Tk,ldv];
- *   out: conv operand layout for an image [B][Tq/out_w][out_w][ldo] (token t = row t/out_w, col t%out_w; out_w % 128 == 0)
- * replaces: nn.MultiheadAttention core (efficient_unet.py:39-53) / QKVAttentionLegacy einsum-softmax-einsum
- *           (layout_unet_v1.py:488-505)                                                              */
-int b200_attention(const float* q, int ldq, int qoff, const float* k, int ldk, int koff, const float* v,
-                   int ldv, int voff, void* out, int ldo, int out_w, int parts, int B, int heads, int Tq,
-                   int Tk, int dqk, int dv, float scale, void* stream);
-
-/* ObjectAwareCrossAttention core (models/unets/layout_unet_v1.py:416-505, norm_first=False, scale 1.0):
- *   qkv fp32 [B,T,3C] (q|k|v of qkv_projector, head-major), pos_p fp32 [B,T,C] (normalised image-patch
- *   positional embedding), kl / pos_l / vl fp32 [B,L2,C] (layout key content, positional, value);
- *   per head (d = C/heads = 32): q = [q_c;pos_p], k = [[k_c;pos_p] | [k_l;pos_l]], v = [v_c | v_l];
- *   scale2 = 1/sqrt(2d) (the reference multiplies q and k each by (2d)^-1/4).
- *   out: conv operand layout for an image [B][T/out_w][out_w][C] (out_w % 128 == 0)                    */
-int b200_attention_oa(const float* qkv, const float* pos_p, const float* kl, const float* pos_l,
-                      const float* vl, void* out, int out_w, int parts, int B, int C, int heads, int T,
-                      int L2, float scale2, void* stream);
+ * softmax(q k^T * scale) v per (batch, head), flash style (online softmax; scores never leave the SM).
+ *   self-attention (replaces the nn.MultiheadAttention core, efficient_unet.py:39-53):
+ *     qkv fp32 [B,T,3E] (q | k | v of the fused in-projection, head-major), d = E / heads = 32 or 64
+ *   object-aware cross attention (replaces ObjectAwareCrossAttention / QKVAttentionLegacy, layout_unet_v1.py:416-532,
+ *   norm_first=False, scale 1.0):
+ *     qkv fp32 [B,T,3C] (q|k|v of qkv_projector, head-major), pos_p fp32 [B,T,C] (normalised image-patch positional
+ *     embedding), kl / pos_l / vl fp32 [B,L2,C] (layout key content, positional, value); per head (d = C/heads = 32):
+ *     q = [q_c;pos_p], k = [[k_c;pos_p] | [k_l;pos_l]], v = [v_c | v_l]; scale2 = 1/sqrt(2d) (the reference multiplies q and
+ *     k each by (2d)^-1/4)
+ *   out: conv operand layout (parts 1 | 2 | 3) for an image [B][T/out_w][out_w][E] (token t = row t/out_w, col t%out_w;
+ *   out_w % 128 == 0) = the A operand of the out-projection conv                                                      */
 
 /* optional in-kernel profile of the tcgen05 attention kernel: 16 x u64 cycle counters per CTA (device buffer of
  * grid-size x 16 u64, or NULL to switch off); see csrc/attention.cu                                                 */
 int b200_attn_set_debug(void* dbg_u64);
 
-/* Flash attention (online softmax; scores never leave the SM) for the two attention cores above: same inputs / outputs.
- * Product path: tcgen05.mma with the S and O accumulators in TMEM (csrc/attention.cu flash_attn_tc_kernel): a pack pass
+/* Product path: tcgen05.mma with the S and O accumulators in TMEM (csrc/attention.cu flash_attn_tc_kernel): a pack pass
  * writes the fp16 hi | lo Q / K / V^T tile images of every (batch, head) into `workspace` in the shared-memory layout of the
  * MMA operands, the main kernel stages them with one bulk copy per tile.
  *   workspace: b200_flash_attention_workspace(B, heads, T, Tx, dq, dv) bytes of device memory (Tx = extra layout keys, dq =

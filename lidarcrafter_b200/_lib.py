@@ -34,7 +34,6 @@ PROTOTYPES = {
     "b200_conv_ffma": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, P]),
     "b200_gn_act_f16": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, I, I, I, I, P]),
     "b200_gn_act_f32": (I, [P, P, P, P, I, F, I, P, I, I, I, P]),
-    "b200_attention_oa": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, F, P]),
     "b200_attn_set_debug": (I, [P]),
     "b200_flash_attention_workspace": (SZ, [I, I, I, I, I, I]),
     "b200_flash_attention": (I, [P, I, P, I, I, I, I, I, F, P, P]),
@@ -46,7 +45,6 @@ PROTOTYPES = {
     "b200_in_conv": (I, [P, P, P, I, P, P, I, I, I, I, I, I, P]),
     "b200_conv_direct_f32": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
     "b200_out_conv": (I, [P, I, P, P, P, I, I, I, I, I, I, P]),
-    "b200_attention": (I, [P, I, I, P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, F, P]),
     "b200_sampler_update": (I, [P, P, P, P, P, I, I, I, I, F, P]),
     "b200_sampler_coefficients": (I, [P, P, I, F, F, F, F, F, P, P, I, P]),
     "b200_range_project": (I, [P, P, P, P, P, I, I, I, I, F, F, F, F, P]),

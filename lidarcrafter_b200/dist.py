@@ -57,3 +57,20 @@ def sample_sharded(ddpm, total_batch: int, num_steps: int, batch_dict: dict | No
     else:
         x = ddpm.sample(shard_batch_dict(batch_dict, rank, world), batch_size=hi - lo, **kw)
     return all_gather_samples(x, total_batch)
+
+
+@torch.inference_mode()
+def generate_sharded(sampler, scenes: list, num_frames: int, num_steps: int, rng=None, **kw) -> torch.Tensor:
+    """Data-parallel ``TemporalSampler.generate`` (clips are independent; frames inside a clip are sequential,
+    tools/evaluation/sample_and_save_temporal.py:203-333): rank r generates the clips of scenes [lo, hi), then ONE all-gather
+    of the [b_local, num_frames, 5, H, W] clips.  ``rng``: one generator per scene (sliced like the scenes) or None."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    total = len(scenes)
+    lo, hi = shard_range(total, rank, world)
+    local_rng = rng[lo:hi] if isinstance(rng, list) else rng
+    if hi > lo:
+        clips = sampler.generate(scenes[lo:hi], num_frames=num_frames, num_steps=num_steps, rng=local_rng, **kw)
+    else:       # more ranks than clips: this rank only takes part in the collective
+        clips = torch.zeros(0, num_frames, 5, sampler.H, sampler.W, device=sampler.device)
+    return all_gather_samples(clips, total)

@@ -118,7 +118,7 @@ def _save_tune_file():
     if path:
         import json
         with open(path, "w") as f:
-            json.dump({json.dumps([int(x) if not isinstance(x, bool) else x for x in k]): list(v)
+            json.dump({json.dumps([x if isinstance(x, (bool, str)) else int(x) for x in k]): list(v)
                        for k, v in _TUNE_CACHE.items()}, f)
 
 

@@ -65,3 +65,45 @@ def test_two_ranks_equal_single_process(total):
     # DDIM step amplifies it by 1/alpha_t ~ 2e3)
     d = np.abs(res[1] - res[2])
     assert d.max() < 1e-2 and np.linalg.norm(d) / np.linalg.norm(res[1]) < 2e-4, (d.max(),)
+
+
+class _FakeSampler:
+    """stands in for TemporalSampler: a clip that encodes the scene id, so the gather order / ragged shards can be checked"""
+    H, W = 2, 4
+    device = torch.device("cpu")
+
+    def generate(self, scenes, num_frames, num_steps, rng=None, **kw):
+        assert rng is None or len(rng) == len(scenes)
+        return torch.stack([torch.full((num_frames, 5, self.H, self.W), float(s["id"])) + (0 if rng is None else rng[i])
+                            for i, s in enumerate(scenes)])
+
+
+def _gen_worker(rank, world, port, total, q):
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lidarcrafter_b200.dist import generate_sharded
+    scenes = [{"id": i} for i in range(total)]
+    out = generate_sharded(_FakeSampler(), scenes, num_frames=3, num_steps=1, rng=[0.25 * i for i in range(total)])
+    if rank == 0:
+        q.put(out.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total,world", [(3, 2), (1, 2), (4, 2)])
+def test_generate_sharded_gathers_clips_in_scene_order(total, world):
+    """clips of scenes split over 2 gloo ranks (ragged / empty shards) come back in scene order with their own generators"""
+    ctx = mp.get_context("spawn")
+    port = 31500 + (os.getpid() % 2000) + total
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gen_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out.shape == (total, 3, 5, 2, 4)
+    for i in range(total):
+        assert (out[i] == i + 0.25 * i).all()

@@ -368,19 +368,6 @@ def test_in_conv_out_conv_direct():
         assert rel(*h.out(pred)) < 1e-6
 
 
-@pytest.mark.parametrize("parts", [2, 1, 3])
-@pytest.mark.parametrize("E,heads,T", [(512, 8, 512), (256, 8, 128)])
-def test_attention(parts, E, heads, T):
-    h = Both()
-    B = 2
-    d = E // heads
-    qkv = h.t(randn(B, T, 3 * E, seed=1))
-    out = h.t(operand_zeros(parts, B, T // 128, 128, E))
-    h.call("attention", [("t", qkv), 3 * E, 0, ("t", qkv), 3 * E, E, ("t", qkv), 3 * E, 2 * E, ("t", out), E, 128, parts,
-                         B, heads, T, T, d, d, 1 / math.sqrt(d)])
-    operand_close(*h.out(out), parts, B, T // 128, 128, E)
-
-
 @pytest.mark.parametrize("mode,objective", [(0, 0), (0, 1), (0, 2), (1, 0)])
 def test_sampler_update(mode, objective):
     h = Both()
@@ -407,21 +394,6 @@ def test_gn_act_f32():
     y = h.t(torch.zeros(B, HW, C))
     h.call("gn_act_f32", [("t", ix), ("t", st), ("t", gam), ("t", bet), 32, 1e-5, 1, ("t", y), B, HW, C])
     assert rel(*h.out(y)) < 3e-6
-
-
-@pytest.mark.parametrize("parts", [2, 1, 3])
-@pytest.mark.parametrize("C,T,W", [(256, 2048, 256), (512, 512, 128)])
-def test_attention_oa(parts, C, T, W):
-    h = Both()
-    B, L2 = 2, 13
-    heads = C // 32
-    qkv = h.t(randn(B, T, 3 * C, seed=1))
-    pos_p = h.t(randn(B, T, C, seed=2))
-    kl, pos_l, vl = h.t(randn(B, L2, C, seed=3)), h.t(randn(B, L2, C, seed=4)), h.t(randn(B, L2, C, seed=5))
-    out = h.t(operand_zeros(parts, B, T // W, W, C))
-    h.call("attention_oa", [("t", qkv), ("t", pos_p), ("t", kl), ("t", pos_l), ("t", vl), ("t", out), W, parts, B, C,
-                            heads, T, L2, 1 / math.sqrt(64)])
-    operand_close(*h.out(out), parts, B, T // W, W, C)
 
 
 @pytest.mark.parametrize("parts", [2, 1, 3])
