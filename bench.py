@@ -38,6 +38,12 @@ DTYPE_NOTE = {"fp16x3": "f32 (fp16x3 split tensor-core MMAs, fp32 accumulate)",
               "fp16": "f16 operands, f32 accumulate"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv shape (32x1024, 64 -> 64, 3x3) from the committed
+# ncu --set full captures: mean of the launches without / with the residual read (profiles/r02_ncu_summary.md; the part of the
+# output that is still in L2 when the kernel ends is not in dram__bytes_write)
+NCU_TRAFFIC_32x1024_C64 = 1.42e8
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -381,7 +387,7 @@ def main():
     # the timed call is the PUBLIC sampler: dist.sample_sharded -> GaussianDiffusion.sample(batch_size, num_steps, mode="ddim")
     # (continuous_time.py:236-260: initial noise, per-step tables, per-step noise draw, K denoiser steps) + the path's single
     # collective at the end (all-gather of the final frames, 16 MiB at batch 64)
-    gens = [torch.Generator(device=dev).manual_seed(100 + i) for i in range(B * world)]
+    gens = torch.Generator(device=dev).manual_seed(100 + rank)     # one generator per rank (a per-sample list draws B times per step)
     sample_sharded(ddpm, B * world, num_steps=max(W, 1), rng=gens, mode="ddim")          # W untimed warm-up steps
     barrier()
     clk = ClockSampler(local)
@@ -502,7 +508,7 @@ def main():
     # DRAM traffic of this shape from the committed ncu --set full capture (profiles/), per launch; None if unknown
     # (profiles/r01s2_ncu_summary.md: 101.8 MB without / 182.2 MB with the residual read, 6 launches each per step; the writes
     # of a launch that are still in L2 when it ends are not in dram__bytes_write)
-    ncu_traffic = {(32, 1024, 64, 64, 9): 1.42e8}.get(dk)
+    ncu_traffic = {(32, 1024, 64, 64, 9): NCU_TRAFFIC_32x1024_C64}.get(dk)
     roof = {"bound": bound, "kernel": "conv_tc_kernel %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
                 dk + (dv[3], 100 * dv[0] / tot_ms)),
             "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,

@@ -63,49 +63,51 @@ POINTS_RANGE = (-80, -80, -8, 80, 80, 8)
 
 
 def scale_boxes_3d(boxes_3d: np.ndarray, points_range=POINTS_RANGE) -> np.ndarray:
-    """nuscenes_dataset.py:145-158: [N,7+] -> float64 [N,8+]: centre / |range min|, log sizes, (sin, cos) yaw, extra columns"""
-    b = np.array(boxes_3d, copy=True)
-    out = np.zeros([b.shape[0], b.shape[-1] + 1])
-    x_min, y_min, z_min = points_range[:3]
-    b[:, 0] = (b[:, 0] - 0) / (0 - x_min)
-    b[:, 1] = (b[:, 1] - 0) / (0 - y_min)
-    b[:, 2] = (b[:, 2] - 0) / (0 - z_min)
-    b[:, 3:6] = np.log(b[:, 3:6] + 1e-6)
-    out[:, :6] = b[:, :6]
-    out[:, 6] = np.sin(b[:, 6])
-    out[:, 7] = np.cos(b[:, 6])
-    if b.shape[-1] > 7:
-        out[:, 8:] = b[:, 7:]
+    """nuscenes_dataset.py:145-158: [N,7+] (x,y,z,l,w,h,yaw,extra...) -> float64 [N,8+]: centre over the half extent of the point
+    range, log sizes, (sin, cos) of the yaw, extra columns.  The divisions / log / sin / cos run in the INPUT's dtype (as in
+    the reference, which edits its argument in place) and are widened to float64 only when stored."""
+    src = np.asarray(boxes_3d)
+    n, d = src.shape
+    out = np.zeros((n, d + 1))
+    for axis, lo in enumerate(points_range[:3]):            # Python-int divisors keep a float32 input in float32
+        out[:, axis] = src[:, axis] / (0 - lo)
+    out[:, 3:6] = np.log(src[:, 3:6] + 1e-6)
+    out[:, 6], out[:, 7] = np.sin(src[:, 6]), np.cos(src[:, 6])
+    out[:, 8:] = src[:, 7:]
     return out
 
 
 def encoding_boxes_3d(box: np.ndarray, unique_mode: bool = True, points_range=POINTS_RANGE) -> np.ndarray:
-    """nuscenes_dataset.py:194-214 (float32 [6] | [8])"""
-    enc = np.zeros((8), dtype=np.float32)
-    x, y, z, w, h, l, yaw = box
-    x_min, y_min, z_min = points_range[:3]
-    enc[0] = np.linalg.norm(np.array([(x - 0) / (0 - x_min), (y - 0) / (0 - y_min)]), ord=2, axis=0, keepdims=True)[0]
-    enc[1] = (z - 0) / (0 - z_min)
-    enc[2:5] = np.log(np.array([w, h, l]) + 1e-6)
+    """nuscenes_dataset.py:194-214 for ONE box (x,y,z,w,h,l,yaw) -> float32 [6] (unique_mode) | [8]:
+    (planar distance of the normalised centre, normalised z, log sizes, then the viewing-relative yaw | azimuth bin + sin / cos yaw)"""
+    x, y, z, yaw = box[0], box[1], box[2], box[6]
+    lo = points_range[:3]
+    enc = np.zeros(8, dtype=np.float32)
+    enc[0] = np.linalg.norm(np.array([x / (0 - lo[0]), y / (0 - lo[1])]), ord=2, axis=0, keepdims=True)[0]
+    enc[1] = z / (0 - lo[2])
+    enc[2:5] = np.log(np.array([box[3], box[4], box[5]]) + 1e-6)
+    bearing = np.arctan2(y, x)
     if unique_mode:
-        enc[5] = yaw - np.arctan2(y, x)
+        enc[5] = yaw - bearing
         return enc[:6]
-    enc[5] = (-np.arctan2(y, x) / np.pi + 1) / 2 % 1
-    enc[6] = np.sin(yaw)
-    enc[7] = np.cos(yaw)
+    enc[5:8] = (-bearing / np.pi + 1) / 2 % 1, np.sin(yaw), np.cos(yaw)
     return enc
 
 
+def _fit_rows(a: np.ndarray, rows: int) -> np.ndarray:
+    """first `rows` rows of `a`, zero-padded to `rows` (float64 when padding, like the reference's np.zeros buffers)"""
+    if a.shape[0] >= rows:
+        return a[:rows]
+    out = np.zeros((rows, a.shape[-1]))
+    out[:a.shape[0]] = a
+    return out
+
+
 def allign_box_num(bbox_3d, bbox_2d, fg_encoding_box, expet_box_num: int = 13):
-    """nuscenes_dataset.py:174-192 (name as in the reference): pad / cut to 13 rows + validity flags"""
-    n = bbox_3d.shape[0]
-    if n > expet_box_num:
-        return (bbox_3d[:expet_box_num], bbox_2d[:expet_box_num], fg_encoding_box[:expet_box_num], np.ones([expet_box_num]))
-    b3, b2, fg = (np.zeros([expet_box_num, a.shape[-1]]) for a in (bbox_3d, bbox_2d, fg_encoding_box))
-    b3[:n], b2[:n], fg[:n] = bbox_3d, bbox_2d, fg_encoding_box
-    valid = np.zeros([expet_box_num])
-    valid[:n] = 1
-    return b3, b2, fg, valid
+    """nuscenes_dataset.py:174-192 (name as in the reference): the layout encoder takes exactly 13 object rows -> the three
+    per-object arrays cut / zero-padded to 13 rows + the validity flags"""
+    valid = (np.arange(expet_box_num) < bbox_3d.shape[0]).astype(np.float64)
+    return (_fit_rows(bbox_3d, expet_box_num), _fit_rows(bbox_2d, expet_box_num), _fit_rows(fg_encoding_box, expet_box_num), valid)
 
 
 def class_ids(gt_names, class_names=CLASS_NAMES) -> np.ndarray:
