@@ -999,6 +999,10 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     return B200_OK;
 }
 
+}  // namespace b200
+#include "conv_col.cuh"
+namespace b200 {
+
 // ---------------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> fp16 tiles in the exact shared-memory image of a B stage
 //   layout [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8]; parts = 1 (fp16) or 2 (hi, lo); values pre-multiplied
@@ -1281,8 +1285,13 @@ static int conv_tc_impl(const void* a, const GnFront& gn, const void* wpacked, c
     B200_CHECK_ARG(parts >= 1 && parts <= 4);
     B200_CHECK_ARG(W % PIX == 0 && Cin % 32 == 0 && Cin >= 32);
     B200_CHECK_ARG((bn == 64 || bn == 128) && Cout % bn == 0);
-    B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
-    B200_CHECK_ARG(rows * bn <= 256);   // two TMEM accumulator sets <= 512 columns (merged mode is chosen when 2x fits)
+    const bool col = fuse && rows == 0;   // column walk (conv_col.cuh): 64 -> 64 channels, 3x3, fp16f8 operands
+    if (col) {
+        B200_CHECK_ARG(parts == 3 && taps == 9 && bn == 64 && Cin == 64 && Cout == 64 && gn.C1 == 0);
+    } else {
+        B200_CHECK_ARG((rows == 1 || rows == 2 || rows == 4) && H % rows == 0);
+        B200_CHECK_ARG(rows * bn <= 256);   // two TMEM accumulator sets <= 512 columns (merged mode is chosen when 2x fits)
+    }
     ConvParams p{};
     p.a = (const __half*)a; p.w = (const __half*)wpacked; p.bias = bias; p.res = res; p.out = out; p.stats = stats;
     p.out_scale = out_scale; p.w_inv = w_inv; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ring = ring;
@@ -1310,6 +1319,7 @@ static int conv_tc_impl(const void* a, const GnFront& gn, const void* wpacked, c
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (num_sms <= 0) num_sms = 148;
     }
+    if (col) return launch_conv_col(p, num_sms, st);
 #define B200_CONV_CASE(BN_, R_, NP_)                                                                                  \
     if (!fuse && bn == BN_ && rows == R_ && parts == NP_)                                                             \
         return taps == 9 ? launch_conv<BN_, R_, 9, NP_, false>(p, num_sms, st) : launch_conv<BN_, R_, 1, NP_, false>(p, num_sms, st);

@@ -242,8 +242,10 @@ class EmulatedLib:
         self.gn_act_f16(x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, scratch.data_ptr(), 0,
                         parts, B, H, W, stream)
         self.calls.pop()
+        if rows == 0:      # column walk (csrc/conv_col.cuh): same contract, restricted shapes
+            assert parts == 3 and taps == 9 and bn == 64 and C0 == 64 and C1 == 0 and Cout == 64
         self.conv_tc(scratch.data_ptr(), wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn,
-                     rows, parts, stream)
+                     rows or 1, parts, stream)
         self.calls[-1] = "conv_gn_tc"
         self.n_launches = n0 + 1
         return 0

@@ -102,6 +102,29 @@ def main():
                 print(f"  m{m}", end="")
                 print(f"    bn{bn}R{rows} cycles/CTA: mma_total {d[0]:8.0f} waitA {d[1]:7.0f} waitB {d[2]:7.0f} waitAcc {d[3]:7.0f} | "
                       f"epi_total {d[4]:8.0f} epi_wait {d[5]:8.0f} | xf_total {d[7]:8.0f} xf_waitEmptyA {d[6]:8.0f}", flush=True)
+        if parts == 3 and taps == 9 and C0 == 64 and C1 == 0 and Cout == 64:      # column walk (rows = 0)
+            packed = torch.empty(Cout * Cin * taps * 2, dtype=torch.float16, device=dev)
+            ws = 2.0 ** 16
+            lib.pack_conv_weight(w.data_ptr(), packed.data_ptr(), Cout, Cin, taps, 64, 2, parts, ws, st)
+            tail = (packed.data_ptr(), bias.data_ptr(), 0 if r is None else r.data_ptr(), 1.0, 1.0 / ws)
+            f = lambda: lib.conv_gn_tc(*front, *tail, out.data_ptr(), stats.data_ptr(), B, H, W, Cout, taps, 1, 64, 0, parts, st)
+            t_f = timeit(f)
+            err = float((out - out2).norm() / out2.norm())
+            line.append(f"col: fused {t_f:6.1f} (rel vs tile walk {err:.1e})")
+            for m in masks[1:]:
+                lib.conv_set_ablate(m)
+                line[-1] += f" m{m}:{timeit(f):6.1f}"
+                lib.conv_set_ablate(0)
+            if os.environ.get("COUNTERS", "0") == "1":
+                dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+                lib.conv_set_debug(dbg.data_ptr())
+                f()
+                torch.cuda.synchronize()
+                lib.conv_set_debug(0)
+                d = dbg.view(148, 8).double()
+                d = d[d[:, 0] > 0].mean(0).tolist()
+                print(f"    col cycles/CTA: mma_total {d[0]:8.0f} waitRow {d[1]:7.0f} waitB8 {d[2]:7.0f} waitAcc {d[3]:7.0f} | "
+                      f"epi_total {d[4]:8.0f} epi_wait {d[5]:8.0f} | xf_total {d[7]:8.0f} xf_waitEmptyRow {d[6]:8.0f}", flush=True)
         print(f"{H:2d}x{W:<4d} B{B} C{C0}+{C1}->{Cout:<4d} t{taps} res{res} parts{parts}: gn_act {t_gn:6.1f} us | " + " | ".join(line),
               flush=True)
 
