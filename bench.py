@@ -509,8 +509,11 @@ def main():
     # (profiles/r01s2_ncu_summary.md: 101.8 MB without / 182.2 MB with the residual read, 6 launches each per step; the writes
     # of a launch that are still in L2 when it ends are not in dram__bytes_write)
     ncu_traffic = {(32, 1024, 64, 64, 9): NCU_TRAFFIC_32x1024_C64}.get(dk)
-    roof = {"bound": bound, "kernel": "conv_tc_kernel %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
-                dk + (dv[3], 100 * dv[0] / tot_ms)),
+    dom_names = sorted({("conv_col_kernel (fused GroupNorm+SiLU front end, column walk)" if conv_shape(name, a)[6] == 0 else
+                         "conv_tc_kernel (fused front end)" if name == "conv_gn_tc" else "conv_tc_kernel")
+                        for (fn, a), (name, _, _, _) in zip(plan.plan.ops, prof) if conv_shape(name, a) and conv_shape(name, a)[:5] == dk})
+    roof = {"bound": bound, "kernel": "%s %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
+                (" | ".join(dom_names),) + dk + (dv[3], 100 * dv[0] / tot_ms)),
             "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
             "traffic": ncu_traffic, "peak_source": pk["src"],
             "per_launch": {"ms": d_ms, "algorithmic_gflop": d_fl / 1e9, "algorithmic_mb": d_by / 1e6,

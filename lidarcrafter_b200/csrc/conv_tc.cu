@@ -1235,6 +1235,12 @@ extern "C" int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, in
     B200_CHECK_ARG(bn == 64 || bn == 128);
     B200_CHECK_ARG(parts >= 1 && parts <= 4);
     B200_CHECK_ARG(Cout % bn == 0 && Cin % 32 == 0);
+    if (rows == 0) {   // column walk (conv_col.cuh): filter rows stacked along N, all weights of the layer in one image
+        B200_CHECK_ARG(parts == 3 && taps == 9 && bn == 64 && Cin == 64 && Cout == 64);
+        pack_weight_col_kernel<<<pack_blocks((size_t)Cout * Cin * taps), 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)wpacked, wscale);
+        B200_CHECK_LAUNCH();
+        return B200_OK;
+    }
     if (parts >= 3) {
         const size_t n = (size_t)Cout * Cin * taps;
         pack_weight_f8_kernel<<<pack_blocks(n), 256, 0, (cudaStream_t)stream>>>(w, (__half*)wpacked, Cout, Cin, taps, bn,

@@ -133,6 +133,16 @@ def tile_candidates(B: int, H: int, W: int, Cout: int, parts: int):
     return out
 
 
+def col_walk_ok(B: int, H: int, W: int, C0: int, C1: int, Cout: int, taps: int, parts: int, sms: int = NUM_SMS) -> bool:
+    """shapes the column-walk variant of the fused conv accepts (csrc/conv_col.cuh, tile code rows = 0): 64 -> 64 channels,
+    3x3, fp16f8 operands, and a CTA's run of row tiles inside at most two samples"""
+    if not (parts == 3 and taps == 9 and C0 == 64 and C1 == 0 and Cout == 64 and W % 128 == 0):
+        return False
+    n = B * H * (W // 128)
+    grid = min(n, sms)
+    return math.ceil(n / grid) <= H * (W // 128)
+
+
 class PackedConv:
     """fp16 tile image of one conv's weights + fp32 bias (device)."""
 
@@ -392,10 +402,14 @@ class PlanBuilder:
             return pick_tile(self.B, H, W, Cout, taps, self.p.parts)
         best = None
         packed = {}
-        for bn, rows in tile_candidates(self.B, H, W, Cout, self.p.parts):
+        cands = tile_candidates(self.B, H, W, Cout, self.p.parts)
+        if front is not None and col_walk_ok(self.B, H, W, front[1], front[3], Cout, taps, self.p.parts) \
+                and os.environ.get("B200_COL_WALK", "1") != "0":
+            cands.append((64, 0))     # column walk: every input row converted once, all weights resident (csrc/conv_col.cuh)
+        for bn, rows in cands:
             if front is not None and taps == 9 and rows == 4:
                 continue          # 6 staged rows: the transform warps' register-resident prefetch stage does not fit (spills)
-            pk = (bn, conv_merged(bn, rows, self.p.parts))
+            pk = (bn, conv_merged(bn, rows, self.p.parts), rows == 0)
             if pk not in packed:
                 packed[pk] = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             pc = packed[pk]

@@ -164,6 +164,17 @@ class EmulatedLib:
     def pack_conv_weight(self, w, out, Cout, Cin, taps, bn, rows, parts, wscale, stream):
         self._rec("pack_conv_weight")
         v = f32(w, Cout, Cin, taps) * wscale
+        if rows == 0:
+            # column walk (csrc/conv_col.cuh): per (16-channel chunk c, dx) two planes of [2 k-groups][192 = dy * 64 + cout][16 B]:
+            # plane 0 fp16(w s) (k-group = 8 channels), plane 1 e4m3 {w s 2^-11 | w s - fp16(w s)} (16 channels each)
+            assert parts == 3 and taps == 9 and bn == 64 and Cin == 64 and Cout == 64
+            hi = v.half().view(64, 4, 2, 8, 3, 3).permute(1, 5, 2, 4, 0, 3).contiguous()        # [c][dx][kg][dy][n][8]
+            w1 = e4m3(v / F8_LO_SCALE).view(64, 4, 16, 3, 3)
+            w2 = e4m3(v - v.half().float()).view(64, 4, 16, 3, 3)
+            p1 = torch.stack([w1, w2], dim=0).permute(2, 5, 0, 4, 1, 3).contiguous()            # [c][dx][2][dy][n][16]
+            img = torch.cat([hi.view(torch.uint8).reshape(4, 3, -1), p1.reshape(4, 3, -1)], dim=-1)
+            u8(out, Cout * Cin * taps * 4).copy_(img.reshape(-1))
+            return 0
         if parts >= 3:
             # per (n-tile, 16-channel chunk, tap): plane 0 [2][bn][8] fp16, plane 1 [2 (hi8, lo8)][bn][16] e4m3
             hi = v.half().view(Cout // bn, bn, Cin // 16, 2, 8, taps).permute(0, 2, 5, 3, 1, 4).contiguous()
@@ -242,10 +253,21 @@ class EmulatedLib:
         self.gn_act_f16(x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, scratch.data_ptr(), 0,
                         parts, B, H, W, stream)
         self.calls.pop()
-        if rows == 0:      # column walk (csrc/conv_col.cuh): same contract, restricted shapes
+        if rows == 0:      # column walk (csrc/conv_col.cuh): same contract, restricted shapes, its own weight image
             assert parts == 3 and taps == 9 and bn == 64 and C0 == 64 and C1 == 0 and Cout == 64
+            img = u8(wpacked, 4, 3, 2, 2 * 192 * 16)
+            hi = img[:, :, 0].contiguous().view(torch.float16).view(4, 3, 2, 3, 64, 8)          # [c][dx][kg][dy][n][8]
+            Wp = [hi.float().permute(4, 0, 2, 5, 3, 1).reshape(64, 64, 3, 3)]
+            p1 = e4m3_value(img[:, :, 1].contiguous()).view(4, 3, 2, 3, 64, 16)                 # [c][dx][sub][dy][n][16]
+            for sub in range(2):
+                Wp.append(p1[:, :, sub].permute(3, 0, 4, 2, 1).reshape(64, 64, 3, 3))
+            self._rec("conv_tc")
+            self._conv(scratch.data_ptr(), Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, 3)
+            self.calls[-1] = "conv_gn_tc"
+            self.n_launches = n0 + 1
+            return 0
         self.conv_tc(scratch.data_ptr(), wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn,
-                     rows or 1, parts, stream)
+                     rows, parts, stream)
         self.calls[-1] = "conv_gn_tc"
         self.n_launches = n0 + 1
         return 0

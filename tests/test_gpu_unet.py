@@ -179,7 +179,22 @@ def test_unet_fused_front_equals_separate_launches(monkeypatch):
     m2, _ = make_unet(res, nres)
     y1 = m2.cuda()(x.cuda(), t.cuda()).cpu()
     assert "gn_act_f16" in [n for n, _, _ in m2.get_plan(B).plan.meta]
-    assert rel_l2(y1, y0) < 1e-6 and rel_l2(y0, y_ref) < TOL
+    # the tile-walk fused kernel issues the same MMAs as the separate launches (bit-identical); the column walk of the 64 -> 64
+    # layers (csrc/conv_col.cuh) accumulates filter row by filter row: another fp32 summation order (3.5e-7 per conv), which
+    # flips e4m3 roundings of the correction operands downstream -- differences at the fp16f8 noise level (5e-5 vs fp32)
+    assert rel_l2(y1, y0) < 5e-5 and rel_l2(y0, y_ref) < TOL and rel_l2(y1, y_ref) < TOL
+    from lidarcrafter_b200 import engine
+    monkeypatch.setenv("B200_COL_WALK", "0")       # tile-walk fused kernels only: bit-identical operands and MMA order
+    monkeypatch.setenv("B200_FUSE_FRONT", "1")
+    saved = dict(engine._TUNE_CACHE)
+    engine._TUNE_CACHE.clear()
+    try:
+        m3, _ = make_unet(res, nres)
+        y3 = m3.cuda()(x.cuda(), t.cuda()).cpu()
+    finally:
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_CACHE.update(saved)
+    assert rel_l2(y1, y3) < 1e-6
 
 
 @pytest.mark.parametrize("schedule,kw", [("linear", {}), ("cosine", {}),

@@ -105,7 +105,7 @@ def main():
         if parts == 3 and taps == 9 and C0 == 64 and C1 == 0 and Cout == 64:      # column walk (rows = 0)
             packed = torch.empty(Cout * Cin * taps * 2, dtype=torch.float16, device=dev)
             ws = 2.0 ** 16
-            lib.pack_conv_weight(w.data_ptr(), packed.data_ptr(), Cout, Cin, taps, 64, 2, parts, ws, st)
+            lib.pack_conv_weight(w.data_ptr(), packed.data_ptr(), Cout, Cin, taps, 64, 0, parts, ws, st)
             tail = (packed.data_ptr(), bias.data_ptr(), 0 if r is None else r.data_ptr(), 1.0, 1.0 / ws)
             f = lambda: lib.conv_gn_tc(*front, *tail, out.data_ptr(), stats.data_ptr(), B, H, W, Cout, taps, 1, 64, 0, parts, st)
             t_f = timeit(f)
@@ -123,7 +123,7 @@ def main():
                 lib.conv_set_debug(0)
                 d = dbg.view(148, 8).double()
                 d = d[d[:, 0] > 0].mean(0).tolist()
-                print(f"    col cycles/CTA: mma_total {d[0]:8.0f} waitRow {d[1]:7.0f} waitB8 {d[2]:7.0f} waitAcc {d[3]:7.0f} | "
+                print(f"    col cycles/CTA: mma_total {d[0]:8.0f} waitHalf {d[1]:7.0f} waitTurn {d[2]:7.0f} waitAcc {d[3]:7.0f} | "
                       f"epi_total {d[4]:8.0f} epi_wait {d[5]:8.0f} | xf_total {d[7]:8.0f} xf_waitEmptyRow {d[6]:8.0f}", flush=True)
         print(f"{H:2d}x{W:<4d} B{B} C{C0}+{C1}->{Cout:<4d} t{taps} res{res} parts{parts}: gn_act {t_gn:6.1f} us | " + " | ".join(line),
               flush=True)
