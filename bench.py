@@ -508,10 +508,20 @@ def main():
     # DRAM traffic of this shape from the committed ncu --set full capture (profiles/), per launch; None if unknown
     # (profiles/r01s2_ncu_summary.md: 101.8 MB without / 182.2 MB with the residual read, 6 launches each per step; the writes
     # of a launch that are still in L2 when it ends are not in dram__bytes_write)
-    ncu_traffic = {(32, 1024, 64, 64, 9): NCU_TRAFFIC_32x1024_C64}.get(dk)
     dom_names = sorted({("conv_col_kernel (fused GroupNorm+SiLU front end, column walk)" if conv_shape(name, a)[6] == 0 else
                          "conv_tc_kernel (fused front end)" if name == "conv_gn_tc" else "conv_tc_kernel")
                         for (fn, a), (name, _, _, _) in zip(plan.plan.ops, prof) if conv_shape(name, a) and conv_shape(name, a)[:5] == dk})
+    ncu_traffic = {(32, 1024, 64, 64, 9): NCU_TRAFFIC_32x1024_C64}.get(dk)
+    if ncu_traffic is not None and any("conv_col" in n for n in dom_names):
+        # the column-walk kernel: mean DRAM bytes per launch from ITS capture (tools/ncu_traffic.py on the .ncu-rep of
+        # `ncu --set full -k regex:conv_col` over this bench command; profiles/r02b_col_traffic.json)
+        for path in ("gpurun_out/r02b_col_traffic.json", "profiles/r02b_col_traffic.json"):
+            full = os.path.join(os.path.dirname(os.path.abspath(__file__)), path)
+            if os.path.exists(full):
+                ncu_traffic = json.load(open(full))["traffic_bytes"]
+                break
+        else:
+            ncu_traffic = None
     roof = {"bound": bound, "kernel": "%s %dx%d Cin%d Cout%d taps%d (x%d launches/step, %.0f%% of the step)" % (
                 (" | ".join(dom_names),) + dk + (dv[3], 100 * dv[0] / tot_ms)),
             "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,

@@ -72,7 +72,11 @@ int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const fl
  * e4m3 pair) and write them straight into the K-major shared-memory slab (rows above / below the image and non-ring edges
  * are exact zeros) that the tcgen05 issuers read.  Everything after the operand is b200_conv_tc: same wpacked / bias /
  * res / out / stats / tiles, Cin = C0 + C1 <= 1024, groups <= 32.  Result == b200_gn_act_f16 followed by b200_conv_tc
- * (bit-identical operands).  512 threads per CTA, register file re-balanced with setmaxnreg.            */
+ * (bit-identical operands).  640 threads per CTA, register file re-balanced with setmaxnreg.
+ * rows = 0 selects the COLUMN WALK (csrc/conv_col.cuh) for the 64 -> 64 channel 3x3 layers (parts == 3, taps == 9, bn == 64,
+ * C0 == 64, C1 == 0, Cout == 64; wpacked from b200_pack_conv_weight with rows = 0): a CTA owns a run of image rows of one
+ * 128-pixel column, converts every input row ONCE into shared memory, keeps all weights resident and adds a row's contribution
+ * to its three output rows with one N = 192 MMA per (chunk, dx, operand plane); same result up to the fp32 summation order.  */
 int b200_conv_gn_tc(const float* x0, int C0, const float* x1, int C1, const double* stats0,
                     const double* stats1, const float* gamma, const float* beta, const float* ada,
                     int ada_stride, int groups, float eps, int silu, const void* wpacked, const float* bias,
@@ -88,7 +92,9 @@ size_t b200_packed_weight_elems(int Cout, int Cin, int taps, int parts);
 /* w: fp32 OIHW [Cout,Cin,k,k] (k*k == taps), multiplied by wscale (a power of two), ->
  * packed fp16 tiles [Cout/bn][Cin/KC][taps][parts][KC/8][bn][8] (merged mode: [..][KC/8][parts][bn][8]),
  * KC = 32 (parts 1) or 16 (parts 2);  parts 3/4: per (n-tile, 16-channel chunk, tap) [2][bn][8] fp16(w*wscale)
- * followed by [2][bn][16] e4m3 {w*wscale*2^-11, w*wscale - fp16(w*wscale)}                          */
+ * followed by [2][bn][16] e4m3 {w*wscale*2^-11, w*wscale - fp16(w*wscale)};
+ * rows == 0 (column walk of b200_conv_gn_tc; parts 3, taps 9, Cin = Cout = bn = 64): per (16-channel chunk, dx) two planes of
+ * [2 k-groups][192 = dy*64 + cout][16 B]: fp16(w*wscale) | e4m3 {w*wscale*2^-11, w*wscale - fp16(w*wscale)}            */
 int b200_pack_conv_weight(const float* w, void* wpacked, int Cout, int Cin, int taps, int bn, int rows,
                           int parts, float wscale, void* stream);
 /* 1 if b200_conv_tc runs (bn, rows, parts) in merged mode (hi/lo weight rows adjacent: the packed image and the

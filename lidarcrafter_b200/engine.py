@@ -223,6 +223,9 @@ class Plan:
             for _ in range(reps):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
+                # a ~20 us spin kernel in front: event, launch and event are all queued behind it, so the interval is the
+                # kernel as the GPU sees it (as inside the step graph), not kernel + the host's launch latency on an idle GPU
+                torch.cuda._sleep(40000)
                 e0.record()
                 fn(*args, stream)
                 e1.record()
