@@ -204,6 +204,28 @@ def test_conv_gn_tc_fused_front(parts, taps, bn, rows, C0, C1, Cout, H, W, B, gr
         assert torch.equal(g, g2), float((g - g2).abs().max())
 
 
+@pytest.mark.parametrize("H,W,B,with_stats", [(1, 128, 1, False), (2, 256, 3, True), (32, 1024, 1, True), (16, 512, 16, False)])
+def test_conv_col_optional_arguments_and_borders(H, W, B, with_stats):
+    """column walk (b200_conv_gn_tc rows = 0) without bias / residual / statistics / normalisation, single-row images, one CTA
+    per row tile, and runs that span two samples: vs the emulator"""
+    h = Both()
+    w = h.t(randn(64, 64, 3, 3, seed=1, scale=1 / math.sqrt(64 * 9)))
+    x0 = h.t(randn(B, H, W, 64, seed=2) * 1.3 - 0.1)
+    wp = h.t(wp_zeros(64, 64, 9, 3))
+    out = h.t(torch.zeros(B, H, W, 64))
+    st = h.t(torch.zeros(B, 64, 2, dtype=torch.float64))
+    wscale = 2.0 ** 16
+    h.call("pack_conv_weight", [("t", w), ("t", wp), 64, 64, 9, 64, 0, 3, wscale])
+    g, c = h.out(wp)
+    assert torch.equal(g, c), "packed weight image differs"
+    h.call("conv_gn_tc", [("t", x0), 64, None, 0, None, None, None, None, None, 0, 8, 1e-6, 1, ("t", wp), None, None, 1.0,
+                          1.0 / wscale, ("t", out), ("t", st) if with_stats else None, B, H, W, 64, 9, 1, 64, 0, 3])
+    g, c = h.out(out)
+    assert rel(g, c) < 2e-5, rel(g, c)
+    if with_stats:
+        assert rel(*h.out(st)) < 2e-5
+
+
 def test_conv_tc_zero_pad_no_bias_no_res():
     h = Both()
     B, H, W, Cin, Cout = 1, 4, 128, 64, 64

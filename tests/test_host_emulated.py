@@ -113,6 +113,37 @@ def test_registry_keys():
     assert L.unets.__all__["efficient_unet"] is L.EfficientUNet
 
 
+def test_column_walk_plan_matches_tile_walk(emu, monkeypatch):
+    """a plan whose tuned tile for the 64 -> 64 layers is (bn 64, rows 0) -- the column-walk schedule of b200_conv_gn_tc with its
+    own stacked-filter-row weight image (csrc/conv_col.cuh) -- gives the forward of the tile-walk plan, and the eligibility
+    rule mirrors the kernel's argument checks"""
+    from lidarcrafter_b200 import engine
+    assert engine.col_walk_ok(8, 32, 1024, 64, 0, 64, 9, 3) and engine.col_walk_ok(1, 32, 1024, 64, 0, 64, 9, 3)
+    assert not engine.col_walk_ok(8, 32, 1024, 64, 0, 64, 9, 2)          # fp16x3: the weights do not fit
+    assert not engine.col_walk_ok(8, 32, 1024, 64, 64, 64, 9, 3)         # channel concat
+    assert not engine.col_walk_ok(8, 32, 1024, 64, 0, 128, 9, 3) and not engine.col_walk_ok(8, 32, 1024, 64, 0, 64, 1, 3)
+    assert not engine.col_walk_ok(400, 4, 128, 64, 0, 64, 9, 3)          # a CTA's run would span more than two samples
+    res, nres, B = CASES["eunet_mini"]
+    x, t, y_ref = golden_inputs("eunet_mini")
+    m, _ = make_unet(res, nres, precision="fp16f8")
+    y0 = m(x, t)
+    saved = dict(engine._TUNE_CACHE)
+    try:
+        engine._TUNE_CACHE.clear()
+        H, W = res
+        for has_res in (False, True):
+            engine._TUNE_CACHE[(B, H, W, 64, 64, 9, 3, has_res, True)] = (64, 0)
+        m2, _ = make_unet(res, nres, precision="fp16f8")
+        emu.calls.clear()
+        y1 = m2(x, t)
+        rows0 = [a for fn, a in m2.get_plan(B).plan.ops if getattr(fn, "__name__", "") == "conv_gn_tc" and a[27] == 0]
+        assert len(rows0) >= 2, "no layer of the plan runs the column walk"
+    finally:
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_CACHE.update(saved)
+    assert rel_l2(y1, y0) < 1e-6 and rel_l2(y1, y_ref) < 2e-4
+
+
 def test_tile_picker_respects_kernel_limits():
     from lidarcrafter_b200.engine import pick_tile
     for B in (1, 2, 8, 64):
