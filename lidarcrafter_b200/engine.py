@@ -213,26 +213,29 @@ class Plan:
         self.tags.append(self.tag)
 
     def profile(self, stream: int, reps: int = 3):
-        """Per-launch device time (CUDA events on the launching stream), one op at a time.
+        """Per-launch device time of every op INSIDE a replay of the whole step: CUDA events on the launching stream between
+        consecutive launches, the whole sequence queued behind a ~1.5 ms spin kernel so that the host stays ahead of the GPU.
+        The interval of a launch is then the kernel as it runs in the step -- same order, same L2 contents (its inputs were
+        written by the launch before it) -- plus one event; timing every op on its own long after its producer (the earlier
+        method) read every input cold from HBM.  Best of ``reps`` replays per op.
         Returns [(name, ms, algorithmic flops, algorithmic bytes)]."""
-        out = []
         self.run(stream)
         torch.cuda.synchronize(self.device)
-        for (fn, args), (name, fl, by) in zip(self.ops, self.meta):
-            best = float("inf")
-            for _ in range(reps):
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                # a ~20 us spin kernel in front: event, launch and event are all queued behind it, so the interval is the
-                # kernel as the GPU sees it (as inside the step graph), not kernel + the host's launch latency on an idle GPU
-                torch.cuda._sleep(40000)
-                e0.record()
+        n = len(self.ops)
+        best = [float("inf")] * n
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            with torch.inference_mode():
+                self.stats_arena.zero_()
+            torch.cuda._sleep(3_000_000)
+            ev[0].record()
+            for i, (fn, args) in enumerate(self.ops):
                 fn(*args, stream)
-                e1.record()
-                e1.synchronize()
-                best = min(best, e0.elapsed_time(e1))
-            out.append((name, best, fl, by))
-        return out
+                ev[i + 1].record()
+            ev[n].synchronize()
+            for i in range(n):
+                best[i] = min(best[i], ev[i].elapsed_time(ev[i + 1]))
+        return [(name, best[i], fl, by) for i, (name, fl, by) in enumerate(self.meta)]
 
     def run(self, stream: int):
         with torch.inference_mode():     # buffers may have been created under sample()'s inference_mode
