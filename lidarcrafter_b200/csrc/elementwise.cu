@@ -788,7 +788,8 @@ __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restri
                                                            int W, int Cx, int Cout, int ring, int rows_per_block) {
     __shared__ float red[256 * 8];
     __shared__ float sw[4 * 9 * 128];                 // [ci][tap][co], Cout <= 128
-    __shared__ float sx[4 * 3 * (IC_PIX + 2)];        // [ci][dy][pixel + 1]
+    constexpr int IC_RMAX = 4;                        // rows per block (host: rows_per_block <= IC_RMAX)
+    __shared__ float sx[4 * (IC_RMAX + 2) * (IC_PIX + 2)];   // [ci][row + 1][pixel + 1]: ALL input rows of the block, staged once
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.z, w0 = blockIdx.x * IC_PIX;
@@ -805,20 +806,22 @@ __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restri
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
     constexpr int PB = 8;                              // pixels per register batch
     // several image rows per block: the weight staging above and the statistics reduction below are paid once
-    const int h_end = min((int)(blockIdx.y + 1) * rows_per_block, H);
-    for (int h = blockIdx.y * rows_per_block; h < h_end; ++h) {
-        __syncthreads();                               // the previous row's sx has been consumed
-        for (int i = threadIdx.x; i < Cx * 3 * (IC_PIX + 2); i += blockDim.x) {
-            const int px = i % (IC_PIX + 2), r = i / (IC_PIX + 2);
-            const int dy = r % 3, ci = r / 3;
-            const int gh = h + dy - 1;
-            int gw = w0 + px - 1;
-            bool ok = gh >= 0 && gh < H;
-            if (gw < 0) { if (ring) gw += W; else ok = false; }
-            else if (gw >= W) { if (ring) gw -= W; else ok = false; }
-            sx[i] = ok ? x[((size_t)b * Cx + ci) * HW + (size_t)gh * W + gw] : 0.f;
-        }
-        __syncthreads();
+    const int h_beg = blockIdx.y * rows_per_block, h_end = min(h_beg + rows_per_block, H);
+    // every input row of the block (rows_per_block + 2) in ONE staging pass, issued together with the weight staging above
+    // (a pass per output row exposed a global-load round trip + two block barriers per row: 51 -> 47 us at the headline shape)
+    const int NRX = rows_per_block + 2;
+    for (int i = threadIdx.x; i < Cx * NRX * (IC_PIX + 2); i += blockDim.x) {
+        const int px = i % (IC_PIX + 2), r = i / (IC_PIX + 2);
+        const int ry = r % NRX, ci = r / NRX;
+        const int gh = h_beg + ry - 1;
+        int gw = w0 + px - 1;
+        bool ok = gh >= 0 && gh < H;
+        if (gw < 0) { if (ring) gw += W; else ok = false; }
+        else if (gw >= W) { if (ring) gw -= W; else ok = false; }
+        sx[i] = ok ? x[((size_t)b * Cx + ci) * HW + (size_t)gh * W + gw] : 0.f;
+    }
+    __syncthreads();
+    for (int h = h_beg; h < h_end; ++h) {
         for (int pb = poff; pb < IC_PIX; pb += PB * pstep) {
             float4 acc[PB];
 #pragma unroll
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(256) in_conv_rows_kernel(const float* __restri
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const float4 wv = *reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * Cout + c4 * 4);
-                    const float* xr = sx + (ci * 3 + tap / 3) * (IC_PIX + 2) + tap % 3;
+                    const float* xr = sx + (ci * NRX + (h - h_beg) + tap / 3) * (IC_PIX + 2) + tap % 3;
 #pragma unroll
                     for (int i = 0; i < PB; ++i) {
                         const int px = pb + i * pstep;
