@@ -241,6 +241,8 @@ def conv_shape(name, a):
     """(H, W, Cin, Cout, taps, bn, rows) of a conv launch of the plan (b200_conv_tc / b200_conv_gn_tc argument lists)"""
     if name == "conv_tc":
         return a[9], a[10], a[11], a[12], a[13], a[15], a[16]
+    if name == "conv_tc_splitk":        # + workspace, splits in front of the dimensions
+        return a[11], a[12], a[13], a[14], a[15], a[17], a[18]
     if name == "conv_gn_tc":
         return a[21], a[22], a[1] + a[3], a[23], a[24], a[26], a[27]
     return None
@@ -489,7 +491,7 @@ def main():
         for name, v in sorted(by.items(), key=lambda kv: -kv[1][0]):
             print(f"  {name:20s} n={v[3]:4d} {v[0]:8.3f} ms  {100 * v[0] / tot_ms:5.1f}%  "
                   f"{v[1] / max(v[0], 1e-9) / 1e9:8.1f} TFLOP/s  {v[2] / max(v[0], 1e-9) / 1e6:8.1f} GB/s", file=sys.stderr)
-    c = [sum(by.get(n, [0, 0, 0, 0])[i] for n in ("conv_tc", "conv_gn_tc")) for i in range(4)]
+    c = [sum(by.get(n, [0, 0, 0, 0])[i] for n in ("conv_tc", "conv_tc_splitk", "conv_gn_tc")) for i in range(4)]
     # tensor-pipe time units per algorithmic product (1 unit = one fp16 MMA; the e4m3 K=32 correction MMA of fp16f8 = 1)
     mma_per_product = {"fp16x3": 3, "fp16f8": 2, "fp16": 1}[args.precision]
     # dominant kernel = the conv shape with the largest share of the step (per-launch numbers)

@@ -60,6 +60,15 @@ const char* b200_last_error(void);
 int b200_conv_tc(const void* a, const void* wpacked, const float* bias, const float* res,
                  float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin,
                  int Cout, int taps, int ring, int bn, int rows, int parts, void* stream);
+/* b200_conv_tc with the reduction split over `splits` (2, 4 or 8; (Cin / 16) % splits == 0, Cin / 32 for parts 1) CTAs per
+ * output tile: for the layers with few tiles and a long K (deep levels at small batch -- 4x128 C512 at B = 1 is 32 CTAs that
+ * each walk K = 4608 alone).  workspace: fp32 [splits][B, H*W, Cout] scratch (raw partial sums of the channel slices); a
+ * second kernel adds the slices in index order and applies the epilogue of b200_conv_tc.  Same arguments / result otherwise
+ * (up to the fp32 summation order).                                                                    */
+int b200_conv_tc_splitk(const void* a, const void* wpacked, const float* bias, const float* res,
+                        float out_scale, float w_inv, float* out, double* stats, float* workspace, int splits,
+                        int B, int H, int W, int Cin, int Cout, int taps, int ring, int bn, int rows, int parts,
+                        void* stream);
 /* GroupNorm(+AdaGN)-apply + SiLU + operand split fused IN FRONT of b200_conv_tc: replaces  conv(silu(norm(x)))  of
  * ResidualBlock.forward (models/unets/efficient_unet.py:104-115, ops.py:176-200; layout_unet_v1.py:229-249), the GroupNorm
  * -> QKV projection of the attention blocks (efficient_unet.py:46-49) and the plain fp32 -> operand casts in ONE launch.

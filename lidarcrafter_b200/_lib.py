@@ -24,6 +24,7 @@ PROTOTYPES = {
     "b200_device_check": (I, [I]),
     "b200_last_error": (C.c_char_p, []),
     "b200_conv_tc": (I, [P, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+    "b200_conv_tc_splitk": (I, [P, P, P, P, F, F, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "b200_conv_gn_tc": (I, [P, I, P, I, P, P, P, P, P, I, I, F, I, P, P, P, F, F, P, P, I, I, I, I, I, I, I, I, I, P]),
     "b200_conv_set_debug": (I, [P]),
     "b200_conv_set_ablate": (I, [I]),

@@ -32,6 +32,11 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// elementwise.cu: out = ((sum_s part[s]) * w_inv + bias + res) * scale (+ per-channel statistics) -- the conv epilogue on the
+// partial sums of the K slices of b200_conv_tc_splitk
+int launch_splitk_reduce(const float* part, int splits, size_t stride, const float* bias, const float* res, float w_inv,
+                         float scale, float* out, double* stats, int B, int HW, int Cout, void* stream);
+
 // Programmatic dependent launch (PDL): every kernel of the denoiser step is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, calls pdl_launch_dependents() first thing and pdl_wait() before
 // its first global-memory access.  The next kernel's CTAs are then scheduled (and run their prologue: barrier init,

@@ -63,6 +63,10 @@ struct ConvParams {
     const float* gn_ada;
     int C0, C1, gn_ada_stride, gn_groups, gn_silu;
     float gn_eps;
+    // split-K (b200_conv_tc_splitk): blockIdx.y = K slice; slice s accumulates the chunks [s, s + 1) * (Cin / KC / k_splits) and
+    // writes its raw partial sums to out + s * split_stride (no bias / residual / statistics: conv_splitk_reduce_kernel)
+    int k_splits;
+    long long split_stride;
 };
 
 __device__ __align__(128) unsigned char g_zero_page[16384];  // source of zero-padding rows / pixels
@@ -526,7 +530,9 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.Cout / BN, WT = p.W / PIX, HG = p.H / R;
-    const int NCH = p.Cin / KC;
+    const int NCH_ALL = p.Cin / KC;
+    const int NCH = NCH_ALL / (p.k_splits > 1 ? p.k_splits : 1);     // K chunks of this CTA (split-K: its slice)
+    const int cb = (int)blockIdx.y * NCH;                            // first chunk of the slice
     const int CG = p.Cin / 8;
     // contiguous chunk of tiles per CTA (same image rows / same batch index: L2 locality, few statistic flushes)
     const int tiles_per_cta = (p.n_tiles + gridDim.x - 1) / gridDim.x;
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
                             continue;
                         }
                         const __half* src = p.a + part * part_elems +
-                                            operand_unit((size_t)b * p.H + gh, WT, CG, wt, c * C::KG, 0) * 8;
+                                            operand_unit((size_t)b * p.H + gh, WT, CG, wt, (cb + c) * C::KG, 0) * 8;
                         const bool edge_l = !p.ring && wt == 0, edge_r = !p.ring && wt == WT - 1;
                         if (!(edge_l || edge_r)) {
                             bulk_copy_g2s(dst, src, C::ROWB, FULL_A(s));
@@ -655,7 +661,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
             unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
                 const int nt = (tile / (WT * HG)) % NT;
-                const __half* wsrc = p.w + (size_t)nt * NCH * TAPS * (C::PL * BN * KC);
+                const __half* wsrc = p.w + ((size_t)nt * NCH_ALL + cb) * TAPS * (C::PL * BN * KC);
                 for (int q = 0; q < NCH * C::TG; ++q, ++ib) {
                     const int s = ib % C::SB;
                     const uint32_t ph = (ib / C::SB) & 1;
@@ -814,6 +820,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
         float* stg = reinterpret_cast<float*>(smem + C::OFF_EPI) + ew * (32 * 36);
         const int col4 = lane & 7, rb = lane >> 3;
         const float scale = p.out_scale, winv = p.w_inv;
+        float* const out_base = p.out + (size_t)blockIdx.y * (size_t)p.split_stride;
         uint32_t it = 0;
         unsigned long long* dbg = g_conv_dbg;
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -919,7 +926,7 @@ __global__ void __launch_bounds__(FUSE ? FUSE_THREADS : CONV_THREADS, 1) conv_tc
                         tv.z = fmaf(tv.z, winv, bi.z); tv.w = fmaf(tv.w, winv, bi.w);
                         if (do_res) { tv.x += rv[i].x; tv.y += rv[i].y; tv.z += rv[i].z; tv.w += rv[i].w; }
                         tv.x *= scale; tv.y *= scale; tv.z *= scale; tv.w *= scale;
-                        if (!ABL(4)) *reinterpret_cast<float4*>(p.out + gi) = tv;
+                        if (!ABL(4)) *reinterpret_cast<float4*>(out_base + gi) = tv;
                         s1[0] += tv.x; s1[1] += tv.y; s1[2] += tv.z; s1[3] += tv.w;
                         s2[0] += tv.x * tv.x; s2[1] += tv.y * tv.y; s2[2] += tv.z * tv.z; s2[3] += tv.w * tv.w;
                     }
@@ -994,7 +1001,8 @@ static int launch_conv(ConvParams p, int num_sms, cudaStream_t st) {
     int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     const int tpc = (p.n_tiles + grid - 1) / grid;
     grid = (p.n_tiles + tpc - 1) / tpc;     // no empty CTAs with contiguous chunks
-    launch_pdl_if(pdl_enabled_conv(), conv_tc_kernel<BN, R, TAPS, NP, FUSE>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM, st, p);
+    launch_pdl_if(pdl_enabled_conv(), conv_tc_kernel<BN, R, TAPS, NP, FUSE>, dim3(grid, p.k_splits > 1 ? p.k_splits : 1),
+                  dim3(C::THREADS), (size_t)C::SMEM, st, p);
     B200_CHECK_LAUNCH();
     return B200_OK;
 }
@@ -1282,7 +1290,7 @@ struct GnFront {
 
 static int conv_tc_impl(const void* a, const GnFront& gn, const void* wpacked, const float* bias, const float* res,
                         float out_scale, float w_inv, float* out, double* stats, int B, int H, int W, int Cin, int Cout,
-                        int taps, int ring, int bn, int rows, int parts, void* stream) {
+                        int taps, int ring, int bn, int rows, int parts, void* stream, int k_splits = 1) {
     const bool fuse = gn.x0 != nullptr;
     B200_CHECK_ARG((a != nullptr) != fuse);
     B200_CHECK_ARG(wpacked && out);
@@ -1304,6 +1312,11 @@ static int conv_tc_impl(const void* a, const GnFront& gn, const void* wpacked, c
     p.x0 = nullptr; p.x1 = nullptr; p.st0 = nullptr; p.st1 = nullptr;
     p.gn_gamma = nullptr; p.gn_beta = nullptr; p.gn_ada = nullptr;
     p.C0 = p.C1 = p.gn_ada_stride = p.gn_silu = 0; p.gn_groups = 1; p.gn_eps = 0.f;
+    p.k_splits = k_splits; p.split_stride = (long long)B * H * W * Cout;
+    if (k_splits > 1) {
+        B200_CHECK_ARG(!fuse && (Cin / (parts == 1 ? 32 : 16)) % k_splits == 0);
+        B200_CHECK_ARG(!bias && !res && !stats);      // the slices hold raw partial sums
+    }
     if (fuse) {
         B200_CHECK_ARG(parts == 2 || parts == 3);                               // fp16x3 / fp16f8 operands
         B200_CHECK_ARG(gn.C0 > 0 && gn.C1 >= 0 && gn.C0 + gn.C1 == Cin && Cin <= MAX_CIN);
@@ -1372,6 +1385,23 @@ extern "C" int b200_conv_tc(const void* a, const void* wpacked, const float* bia
     B200_CHECK_ARG(a != nullptr);
     return conv_tc_impl(a, GnFront{}, wpacked, bias, res, out_scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn,
                         rows, parts, stream);
+}
+
+// split-K for the layers with few output tiles and a long reduction (deep levels at small batch: 4x128 C512 at B = 1 is 32 CTAs
+// that each walk K = 4608 alone and stream 1.2 MB of weights): `splits` CTAs per tile accumulate disjoint channel slices into
+// workspace[splits][B, H*W, Cout] (raw partial sums), conv_splitk_reduce_kernel adds them in slice order and applies the conv
+// epilogue (x w_inv + bias + residual, x scale, per-channel statistics).  Same contract as b200_conv_tc.
+extern "C" int b200_conv_tc_splitk(const void* a, const void* wpacked, const float* bias, const float* res, float out_scale,
+                                   float w_inv, float* out, double* stats, float* workspace, int splits, int B, int H, int W,
+                                   int Cin, int Cout, int taps, int ring, int bn, int rows, int parts, void* stream) {
+    B200_CHECK_ARG(a != nullptr && workspace != nullptr && out != nullptr);
+    B200_CHECK_ARG(splits == 2 || splits == 4 || splits == 8);
+    B200_CHECK_ARG(Cout % 4 == 0 && Cout / 4 <= 256 && 256 % (Cout / 4) == 0);
+    const int rc = conv_tc_impl(a, GnFront{}, wpacked, nullptr, nullptr, 1.0f, 1.0f, workspace, nullptr, B, H, W, Cin, Cout, taps,
+                                ring, bn, rows, parts, stream, splits);
+    if (rc != B200_OK) return rc;
+    return launch_splitk_reduce(workspace, splits, (size_t)B * H * W * Cout, bias, res, w_inv, out_scale, out, stats, B, H * W, Cout,
+                                stream);
 }
 
 // GroupNorm(+AdaGN)-apply + SiLU + operand split fused IN FRONT of the conv: replaces the gn_act launch and the operand

@@ -445,6 +445,72 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
     block_channel_reduce(s1, s2, C, b, stats, red);
 }
 
+// split-K reduce: the conv epilogue on the partial sums of the K slices (b200_conv_tc_splitk); slices are added in index order.
+// The tensors are small (a deep level at small batch: 512 pixels x 512 channels): the grid is sized for ~64 blocks per launch
+// (enough loads in flight, few same-address fp64 atomics) and a thread requests 4 pixels x splits 16-byte loads at a time.
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                                 const float* __restrict__ bias, const float* __restrict__ res,
+                                                                 float w_inv, float scale, float* __restrict__ out,
+                                                                 double* __restrict__ stats, int HW, int C, int pix_per_block) {
+    __shared__ float red[256 * 8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int c4n = C / 4;  // <= 256, divides 256
+    const int c4 = threadIdx.x % c4n, poff = threadIdx.x / c4n, pstep = 256 / c4n;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
+    const float4 bi = bias ? *reinterpret_cast<const float4*>(bias + c4 * 4) : make_float4(0, 0, 0, 0);
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+    constexpr int PB = 4;
+    for (int pb = p0 + poff; pb < p1; pb += PB * pstep) {
+        float4 v[PB], r[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const int pp = pb + j * pstep;
+            const size_t gi = ((size_t)b * HW + min(pp, p1 - 1)) * C + c4 * 4;
+            v[j] = *reinterpret_cast<const float4*>(part + gi);
+            r[j] = res ? *reinterpret_cast<const float4*>(res + gi) : make_float4(0, 0, 0, 0);
+        }
+        for (int s = 1; s < splits; ++s) {
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const int pp = pb + j * pstep;
+                const size_t gi = ((size_t)b * HW + min(pp, p1 - 1)) * C + c4 * 4;
+                const float4 t = *reinterpret_cast<const float4*>(part + (size_t)s * stride + gi);
+                v[j].x += t.x; v[j].y += t.y; v[j].z += t.z; v[j].w += t.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const int pp = pb + j * pstep;
+            if (pp >= p1) continue;
+            const size_t gi = ((size_t)b * HW + pp) * C + c4 * 4;
+            float4 o;
+            o.x = (fmaf(v[j].x, w_inv, bi.x) + r[j].x) * scale; o.y = (fmaf(v[j].y, w_inv, bi.y) + r[j].y) * scale;
+            o.z = (fmaf(v[j].z, w_inv, bi.z) + r[j].z) * scale; o.w = (fmaf(v[j].w, w_inv, bi.w) + r[j].w) * scale;
+            *reinterpret_cast<float4*>(out + gi) = o;
+            s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+            s2.x += o.x * o.x; s2.y += o.y * o.y; s2.z += o.z * o.z; s2.w += o.w * o.w;
+        }
+    }
+    if (stats) block_channel_reduce(s1, s2, C, b, stats, red);
+}
+
+int launch_splitk_reduce(const float* part, int splits, size_t stride, const float* bias, const float* res, float w_inv,
+                         float scale, float* out, double* stats, int B, int HW, int Cout, void* stream) {
+    const int pstep = 256 / (Cout / 4);
+    int ppb = (int)(((long long)HW * B + 63) / 64);           // ~64 blocks per launch
+    ppb = ((ppb + pstep - 1) / pstep) * pstep;
+    if (ppb < pstep) ppb = pstep;
+    if (ppb > ST_PIX_PER_BLOCK) ppb = ST_PIX_PER_BLOCK;
+    dim3 grid(cdiv(HW, ppb), B);
+    launch_pdl(conv_splitk_reduce_kernel, grid, dim3(256), 0, (cudaStream_t)stream, part, splits, stride, bias, res, w_inv, scale,
+               out, stats, HW, Cout, ppb);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FIR resample ([1,3,3,1] window), circular W / zero H
 // ---------------------------------------------------------------------------------------------------------

@@ -288,9 +288,16 @@ class PlanBuilder:
             bn, rows = self.tune_tile(a16, H, W, weight, bias, res, out)
             pc = PackedConv(self.lib, weight, bias, bn, rows, self.p.parts, self.stream)
             self.p.bufs.append(pc)
-            self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
-                       1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
-                       self.p.parts, name="conv_tc", flops=fl, nbytes=by)
+            splits = self.tune_split(a16, H, W, pc, res, out, bn, rows)
+            if splits > 1:
+                ws = self.p.f32(splits, self.B * H * W * Cout)
+                self.p.add(self.lib.conv_tc_splitk, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
+                           1.0 / pc.wscale, _ptr(out), _sp(st), _ptr(ws), splits, self.B, H, W, Cin, Cout, taps, self.ring, bn,
+                           rows, self.p.parts, name="conv_tc_splitk", flops=fl, nbytes=by)
+            else:
+                self.p.add(self.lib.conv_tc, _ptr(a16), _ptr(pc.packed), _ptr(pc.bias), _ptr(res), float(scale),
+                           1.0 / pc.wscale, _ptr(out), _sp(st), self.B, H, W, Cin, Cout, taps, self.ring, bn, rows,
+                           self.p.parts, name="conv_tc", flops=fl, nbytes=by)
         else:
             w = weight.detach().float().contiguous()
             ws = weight_scale(w, self.p.parts)
@@ -376,6 +383,34 @@ class PlanBuilder:
         _TUNE_CACHE[key] = (1 if t_fused < t_gn + t_conv else 0, 0)
         _save_tune_file()
         return bool(_TUNE_CACHE[key][0])
+
+    def tune_split(self, a16, H, W, pc, res, out, bn: int, rows: int) -> int:
+        """K slices per output tile for b200_conv_tc_splitk (1 = plain b200_conv_tc): only layers whose tiles fill less than half
+        of the SMs are candidates (deep levels at small batch: few tiles, long K, every CTA streams the whole weight tile);
+        conv + reduce kernel are timed against the plain conv on the device, cached per shape.  B200_SPLIT_K=0 disables."""
+        Cout, Cin, taps = pc.Cout, pc.Cin, pc.taps
+        tiles = self.B * (H // rows) * (W // 128) * (Cout // bn)
+        nch = Cin // (32 if self.p.parts == 1 else 16)
+        key = ("split", self.B, H, W, Cin, Cout, taps, self.p.parts, res is not None, bn, rows)
+        _load_tune_file()
+        if key in _TUNE_CACHE:
+            return int(_TUNE_CACHE[key][0])
+        if (self.p.device.type != "cuda" or os.environ.get("B200_SPLIT_K", "1") == "0" or 2 * tiles > NUM_SMS
+                or Cout // 4 > 256 or 256 % (Cout // 4)):
+            return 1
+        tail = (_ptr(pc.packed), _ptr(pc.bias), _ptr(res), 1.0, 1.0 / pc.wscale, _ptr(out), 0)
+        dims = (self.B, H, W, Cin, Cout, taps, self.ring, bn, rows, self.p.parts, self.stream)
+        best = (self._time(self.lib.conv_tc, (_ptr(a16),) + tail + dims), 1)
+        for s in (2, 4, 8):
+            if nch % s or tiles * s > 2 * NUM_SMS:
+                continue
+            ws = torch.empty(s, self.B * H * W * Cout, dtype=torch.float32, device=self.p.device)
+            ms = self._time(self.lib.conv_tc_splitk, (_ptr(a16),) + tail + (_ptr(ws), s) + dims)
+            if ms < best[0]:
+                best = (ms, s)
+        _TUNE_CACHE[key] = (best[1], 0)
+        _save_tune_file()
+        return best[1]
 
     @staticmethod
     def _time(fn, args, batches: int = 3, n: int = 5) -> float:

@@ -242,6 +242,14 @@ class EmulatedLib:
         self._conv(a, Wp, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, parts)
         return 0
 
+    def conv_tc_splitk(self, a, wpacked, bias, res, scale, w_inv, out, stats, workspace, splits, B, H, W, Cin, Cout, taps,
+                       ring, bn, rows, parts, stream):
+        """split-K variant of conv_tc: same contract (the K slices are an implementation detail of the GPU kernel)"""
+        assert splits in (2, 4, 8) and (Cin // (32 if parts == 1 else 16)) % splits == 0 and workspace
+        self.conv_tc(a, wpacked, bias, res, scale, w_inv, out, stats, B, H, W, Cin, Cout, taps, ring, bn, rows, parts, stream)
+        self.calls[-1] = "conv_tc_splitk"
+        return 0
+
     def conv_gn_tc(self, x0, C0, x1, C1, st0, st1, gamma, beta, ada, ada_stride, groups, eps, silu, wpacked, bias, res,
                    scale, w_inv, out, stats, B, H, W, Cout, taps, ring, bn, rows, parts, stream):
         """GroupNorm(+AdaGN)-apply + SiLU + operand split fused in front of conv_tc: == gn_act_f16 into a scratch operand,

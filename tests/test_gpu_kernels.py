@@ -204,6 +204,48 @@ def test_conv_gn_tc_fused_front(parts, taps, bn, rows, C0, C1, Cout, H, W, B, gr
         assert torch.equal(g, g2), float((g - g2).abs().max())
 
 
+@pytest.mark.parametrize("parts,taps,bn,rows,Cin,Cout,H,W,B,splits", [
+    (3, 9, 64, 1, 512, 512, 4, 128, 1, 4),        # the B = 1 deep level: 32 tiles, K = 4608
+    (3, 9, 128, 1, 256, 256, 8, 256, 1, 2),
+    (2, 9, 64, 1, 256, 256, 4, 128, 2, 8),
+    (3, 1, 64, 1, 512, 256, 4, 128, 1, 4),
+    (1, 9, 128, 2, 256, 128, 4, 128, 3, 2),
+    (3, 9, 64, 2, 128, 64, 8, 256, 1, 8),
+])
+def test_conv_tc_splitk_matches_conv_tc(parts, taps, bn, rows, Cin, Cout, H, W, B, splits):
+    """b200_conv_tc_splitk (K slices on `splits` CTAs per tile + reduce / epilogue kernel) vs the emulator and vs b200_conv_tc on
+    the GPU: same operands, same epilogue, another fp32 summation order"""
+    h = Both()
+    k = 3 if taps == 9 else 1
+    w = h.t(randn(Cout, Cin, k, k, seed=1, scale=1 / math.sqrt(Cin * taps)))
+    a = h.t(split(randn(B, H, W, Cin, seed=2), parts))
+    bias = h.t(randn(Cout, seed=3, scale=0.1))
+    res = h.t(randn(B, H, W, Cout, seed=4))
+    wp = h.t(wp_zeros(Cout, Cin, taps, parts))
+    out = h.t(torch.zeros(B, H, W, Cout))
+    out2 = h.t(torch.zeros(B, H, W, Cout))
+    st = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    st2 = h.t(torch.zeros(B, Cout, 2, dtype=torch.float64))
+    ws = h.t(torch.zeros(splits, B * H * W * Cout))
+    wscale = 64.0 if parts < 3 else 2.0 ** 16
+    h.call("pack_conv_weight", [("t", w), ("t", wp), Cout, Cin, taps, bn, rows, parts, wscale])
+    h.call("conv_tc_splitk", [("t", a), ("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out), ("t", st),
+                              ("t", ws), splits, B, H, W, Cin, Cout, taps, 1, bn, rows, parts])
+    g, c = h.out(out)
+    assert rel(g, c) < 1e-5, rel(g, c)
+    assert rel(*h.out(st)) < 2e-5
+    h.call("conv_tc", [("t", a), ("t", wp), ("t", bias), ("t", res), 0.70710678, 1.0 / wscale, ("t", out2), ("t", st2),
+                       B, H, W, Cin, Cout, taps, 1, bn, rows, parts])
+    g2, _ = h.out(out2)
+    assert rel(g, g2) < 2e-5, rel(g, g2)       # K up to 4608 products summed in another order (fp32: ~sqrt(K) 2^-24)
+    assert rel(h.out(st)[0], h.out(st2)[0]) < 1e-5
+    # no bias / residual / statistics
+    h.call("conv_tc_splitk", [("t", a), ("t", wp), None, None, 1.0, 1.0 / wscale, ("t", out), None, ("t", ws), splits, B, H, W,
+                              Cin, Cout, taps, 0, bn, rows, parts])
+    g, c = h.out(out)
+    assert rel(g, c) < 1e-5, rel(g, c)
+
+
 @pytest.mark.parametrize("H,W,B,with_stats", [(1, 128, 1, False), (2, 256, 3, True), (32, 1024, 1, True), (16, 512, 16, False)])
 def test_conv_col_optional_arguments_and_borders(H, W, B, with_stats):
     """column walk (b200_conv_gn_tc rows = 0) without bias / residual / statistics / normalisation, single-row images, one CTA

@@ -144,6 +144,31 @@ def test_column_walk_plan_matches_tile_walk(emu, monkeypatch):
     assert rel_l2(y1, y0) < 1e-6 and rel_l2(y1, y_ref) < 2e-4
 
 
+def test_split_k_plan_matches_plain_plan(emu):
+    """a plan whose tuner chose split-K for the deepest 3x3 convs (b200_conv_tc_splitk + workspace) gives the forward of the
+    plain plan"""
+    from lidarcrafter_b200 import engine
+    res, nres, B = CASES["eunet_mini"]
+    x, t, y_ref = golden_inputs("eunet_mini")
+    m, _ = make_unet(res, nres)
+    y0 = m(x, t)
+    shapes = {(a[9], a[10], a[11], a[12], a[13], a[15], a[16], a[3] != 0) for fn, a in m.get_plan(B).plan.ops
+              if getattr(fn, "__name__", "") == "conv_tc" and a[11] >= 128 and a[13] == 9}
+    assert shapes
+    saved = dict(engine._TUNE_CACHE)
+    try:
+        for (H, W, Cin, Cout, taps, bn, rows, has_res) in shapes:
+            engine._TUNE_CACHE[("split", B, H, W, Cin, Cout, taps, 2, has_res, bn, rows)] = (2, 0)
+        m2, _ = make_unet(res, nres)
+        emu.calls.clear()
+        y1 = m2(x, t)
+        assert emu.calls.count("conv_tc_splitk") >= len(shapes)
+    finally:
+        engine._TUNE_CACHE.clear()
+        engine._TUNE_CACHE.update(saved)
+    assert rel_l2(y1, y0) < 1e-6 and rel_l2(y1, y_ref) < 2e-5
+
+
 def test_tile_picker_respects_kernel_limits():
     from lidarcrafter_b200.engine import pick_tile
     for B in (1, 2, 8, 64):
