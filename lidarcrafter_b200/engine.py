@@ -245,7 +245,8 @@ class Plan:
 
     @property
     def n_kernels(self):
-        return len(self.ops) + 1  # + the arena memset
+        # + the arena memset; a split-K conv is two launches (K slices + reduce / epilogue)
+        return len(self.ops) + 1 + sum(1 for name, _, _ in self.meta if name == "conv_tc_splitk")
 
 
 def _sp(holder):
