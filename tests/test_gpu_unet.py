@@ -169,8 +169,14 @@ def test_per_sample_generators_and_sampling_shape():
 def test_unet_fused_front_equals_separate_launches(monkeypatch):
     """B200_FUSE_FRONT=1 (GroupNorm + SiLU + operand split inside every conv launch, b200_conv_gn_tc) gives the same forward
     as B200_FUSE_FRONT=0 (separate gn_act launches writing the operand to HBM); the default "auto" picks per layer shape"""
+    from lidarcrafter_b200 import engine
     res, nres, B = CASES["eunet_mini"]
     x, t, y_ref = golden_inputs("eunet_mini")
+    # split-K (another summation order, chosen by timing) is kept out of this comparison of the front ends
+    monkeypatch.setenv("B200_SPLIT_K", "0")
+    dropped = {k: v for k, v in engine._TUNE_CACHE.items() if k and k[0] == "split"}
+    for k in dropped:
+        del engine._TUNE_CACHE[k]
     monkeypatch.setenv("B200_FUSE_FRONT", "1")
     m, _ = make_unet(res, nres)
     y0 = m.cuda()(x.cuda(), t.cuda()).cpu()
@@ -183,7 +189,6 @@ def test_unet_fused_front_equals_separate_launches(monkeypatch):
     # layers (csrc/conv_col.cuh) accumulates filter row by filter row: another fp32 summation order (3.5e-7 per conv), which
     # flips e4m3 roundings of the correction operands downstream -- differences at the fp16f8 noise level (5e-5 vs fp32)
     assert rel_l2(y1, y0) < 5e-5 and rel_l2(y0, y_ref) < TOL and rel_l2(y1, y_ref) < TOL
-    from lidarcrafter_b200 import engine
     monkeypatch.setenv("B200_COL_WALK", "0")       # tile-walk fused kernels only: bit-identical operands and MMA order
     monkeypatch.setenv("B200_FUSE_FRONT", "1")
     saved = dict(engine._TUNE_CACHE)
@@ -194,6 +199,7 @@ def test_unet_fused_front_equals_separate_launches(monkeypatch):
     finally:
         engine._TUNE_CACHE.clear()
         engine._TUNE_CACHE.update(saved)
+        engine._TUNE_CACHE.update(dropped)
     assert rel_l2(y1, y3) < 1e-6
 
 
