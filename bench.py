@@ -213,13 +213,15 @@ def cpu_reference_run(steps: int, warmup: int, B: int):
     x = torch.randn(B, 2, *RES, generator=torch.Generator().manual_seed(0))
     ts = torch.linspace(1.0, 0.0, 51)
     # thread count: the box is shared and torch's default (all logical cores) oversubscribes badly
-    # (measured: 128 threads 38 s vs 16 threads 0.40 s for a batch-2 forward) -> pick the best of a short probe
+    # (measured: 128 threads 38 s vs 16 threads 0.40 s for a batch-2 forward) -> pick the best of a short probe AT THE BATCH
+    # SIZE OF THE RUN (a batch-1 probe picked 8 threads on some boxes where 16 were faster at batch 8)
     best = None
+    lt_probe = O.log_snr_cosine(ts[:1].repeat(B))
+    O.efficient_unet_forward(sd, x[:1], O.log_snr_cosine(ts[:1]), cfg)        # first touch: allocator, weight layout caches
     for n in sorted({8, 16, 32, min(64, os.cpu_count() or 8)}):
         torch.set_num_threads(n)
-        O.efficient_unet_forward(sd, x[:1], O.log_snr_cosine(ts[:1]), cfg)
         t0 = time.perf_counter()
-        O.efficient_unet_forward(sd, x[:1], O.log_snr_cosine(ts[:1]), cfg)
+        O.efficient_unet_forward(sd, x, lt_probe, cfg)
         dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, n)
